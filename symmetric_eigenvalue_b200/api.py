@@ -1,0 +1,295 @@
+"""ctypes binding of the C ABI in include/cuppen_b200.h (one function per entry point)."""
+import ctypes
+import os
+from collections import namedtuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+FLAG_VECTORS = 1
+FLAG_NO_RESIDUALS = 2
+NCCL_ID_BYTES = 128
+
+
+class CuppenError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("cuppen error %d: %s" % (code, msg))
+        self.code = code
+
+
+class _MergeStat(ctypes.Structure):
+    _fields_ = [("offset", ctypes.c_int), ("m", ctypes.c_int), ("n1", ctypes.c_int), ("mode", ctypes.c_int),
+                ("zdefl", ctypes.c_int), ("givens", ctypes.c_int), ("k", ctypes.c_int), ("height", ctypes.c_int),
+                ("rho", ctypes.c_double)]
+
+
+class _Timers(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_double) for k in (
+        "total_s", "root_finding_s", "ev_extract_s", "backtransform_s", "backtransform_ev_s", "gemm_s",
+        "gemm_flop", "leaf_s", "deflation_s", "pack_s", "residual_s")] + [("kernel_launches", ctypes.c_long)]
+
+
+_BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
+                             ctypes.c_int, ctypes.c_int)
+_ALLRED_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t)
+_ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+
+
+class _Callbacks(ctypes.Structure):
+    _fields_ = [("user", ctypes.c_void_p), ("group_bcast", _BCAST_FN), ("allreduce_sum_f64", _ALLRED_FN),
+                ("allgather", _ALLGATHER_FN)]
+
+
+MergeStat = namedtuple("MergeStat", "offset m n1 mode zdefl givens k height rho")
+
+
+def library_path():
+    return os.path.join(_HERE, "lib", "libcuppen_b200.so")
+
+
+def _declare(lib):
+    dp = ctypes.POINTER(ctypes.c_double)
+    ip = ctypes.POINTER(ctypes.c_int)
+    H = ctypes.c_void_p
+    sig = {
+        "cuppen_create": [ctypes.POINTER(H), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int],
+        "cuppen_nccl_unique_id": [ctypes.c_char_p],
+        "cuppen_create_nccl": [ctypes.POINTER(H), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                               ctypes.c_int, ctypes.c_int, ctypes.c_char_p],
+        "cuppen_create_callbacks": [ctypes.POINTER(H), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(_Callbacks)],
+        "cuppen_destroy": [H],
+        "cuppen_set_tridiagonal": [H, dp, dp],
+        "cuppen_solve": [H],
+        "cuppen_resolve": [H],
+        "cuppen_get_eigenvalues": [H, dp],
+        "cuppen_get_residuals": [H, ip, ctypes.c_int, dp],
+        "cuppen_get_merge_stats": [H, ctypes.POINTER(_MergeStat), ctypes.c_int, ip],
+        "cuppen_get_timers": [H, ctypes.POINTER(_Timers)],
+        "cuppen_local_rows": [H, ip, ip],
+        "cuppen_copy_eigenvectors": [H, dp, ctypes.c_long],
+        "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
+        "cuppen_read_mtx": [ctypes.c_char_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ip],
+        "cuppen_read_ev_file": [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ip), ip],
+        "cuppen_write_results": [ctypes.c_char_p, ctypes.c_int, dp, dp, ctypes.c_int, ip, ctypes.c_int],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)      # AttributeError here = the library does not export the ABI
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
+    lib.cuppen_last_error.argtypes = []
+    lib.cuppen_last_error.restype = ctypes.c_char_p
+    return lib
+
+
+EXPORTED_SYMBOLS = (
+    "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
+    "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
+    "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_copy_eigenvectors",
+    "cuppen_last_error", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
+)
+
+
+def load_library(path=None):
+    """Load libcuppen_b200.so (built in-tree by ``make`` / ``__graft_entry__.build()``)."""
+    global _LIB
+    if path is None and _LIB is not None:
+        return _LIB
+    p = path or library_path()
+    if not os.path.exists(p):
+        raise CuppenError(-10, "CUDA library %s is missing: run `make` (there is no CPU fallback)" % p)
+    lib = _declare(ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL))
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+def _chk(lib, rc):
+    if rc != 0:
+        raise CuppenError(rc, lib.cuppen_last_error().decode("utf-8", "replace"))
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def nccl_unique_id(lib=None):
+    lib = lib or load_library()
+    buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
+    _chk(lib, lib.cuppen_nccl_unique_id(buf))
+    return buf.raw
+
+
+class CuppenSolver:
+    """One tridiagonal eigenproblem on one GPU (or one rank's share of it).
+
+    n            matrix size
+    ref_leaves   P of the reference run ``mpirun -n P cuppens`` whose divide tree, theta rule and
+                 deflation thresholds are reproduced at the top log2(P) levels (1: none)
+    vectors      materialise eigenvectors (the reference's ``-e``)
+    """
+
+    def __init__(self, n, ref_leaves=1, vectors=True, residuals=True, device=0, rank=0, world=1,
+                 nccl_id=None, callbacks=None, lib=None):
+        self.lib = lib or load_library()
+        self.n = int(n)
+        self.vectors = bool(vectors)
+        flags = (FLAG_VECTORS if vectors else 0) | (0 if residuals else FLAG_NO_RESIDUALS)
+        self._h = ctypes.c_void_p()
+        self._cb = None
+        if callbacks is not None:
+            self._cb = callbacks                     # keep the ctypes thunks alive
+            rc = self.lib.cuppen_create_callbacks(ctypes.byref(self._h), self.n, ref_leaves, flags, device, rank,
+                                                  world, ctypes.byref(callbacks))
+        elif world > 1:
+            if nccl_id is None or len(nccl_id) != NCCL_ID_BYTES:
+                raise CuppenError(-1, "world > 1 needs the 128-byte NCCL unique id of rank 0")
+            rc = self.lib.cuppen_create_nccl(ctypes.byref(self._h), self.n, ref_leaves, flags, device, rank, world,
+                                             nccl_id)
+        else:
+            rc = self.lib.cuppen_create(ctypes.byref(self._h), self.n, ref_leaves, flags, device)
+        _chk(self.lib, rc)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self.lib.cuppen_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_tridiagonal(self, D, E):
+        D = np.ascontiguousarray(D, dtype=np.float64)
+        E = np.ascontiguousarray(E, dtype=np.float64)
+        if D.size != self.n or E.size != max(self.n - 1, 0):
+            raise CuppenError(-1, "D must have n and E n-1 entries")
+        if E.size == 0:
+            E = np.zeros(1)
+        _chk(self.lib, self.lib.cuppen_set_tridiagonal(self._h, _dp(D), _dp(E)))
+
+    def solve(self):
+        _chk(self.lib, self.lib.cuppen_solve(self._h))
+
+    def eigenvalues(self):
+        out = np.empty(self.n)
+        _chk(self.lib, self.lib.cuppen_get_eigenvalues(self._h, _dp(out)))
+        return out
+
+    def residuals(self, indices=None):
+        if indices is None:
+            out = np.empty(self.n)
+            _chk(self.lib, self.lib.cuppen_get_residuals(self._h, None, self.n, _dp(out)))
+            return out
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        out = np.empty(idx.size)
+        _chk(self.lib, self.lib.cuppen_get_residuals(self._h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)),
+                                                     idx.size, _dp(out)))
+        return out
+
+    def merge_stats(self):
+        cnt = ctypes.c_int(0)
+        _chk(self.lib, self.lib.cuppen_get_merge_stats(self._h, None, 0, ctypes.byref(cnt)))
+        arr = (_MergeStat * max(cnt.value, 1))()
+        _chk(self.lib, self.lib.cuppen_get_merge_stats(self._h, arr, cnt.value, ctypes.byref(cnt)))
+        return [MergeStat(*(getattr(arr[i], f[0]) for f in _MergeStat._fields_)) for i in range(cnt.value)]
+
+    def timers(self):
+        t = _Timers()
+        _chk(self.lib, self.lib.cuppen_get_timers(self._h, ctypes.byref(t)))
+        return {f[0]: getattr(t, f[0]) for f in _Timers._fields_}
+
+    def local_rows(self):
+        r0, rows = ctypes.c_int(0), ctypes.c_int(0)
+        _chk(self.lib, self.lib.cuppen_local_rows(self._h, ctypes.byref(r0), ctypes.byref(rows)))
+        return r0.value, rows.value
+
+    def eigenvectors(self):
+        """Rows of V owned by this rank (all rows when world == 1), columns in ascending-lambda order."""
+        _, rows = self.local_rows()
+        V = np.empty((rows, self.n), order="F")
+        _chk(self.lib, self.lib.cuppen_copy_eigenvectors(self._h, _dp(V), rows))
+        return V
+
+
+# ---- mirrors of the reference's helper / file functions (host side of the C ABI) --------------------
+def _scheme(s, n, lib=None):
+    lib = lib or load_library()
+    D = np.empty(n)
+    E = np.empty(max(n - 1, 1))
+    _chk(lib, lib.cuppen_scheme(s, n, _dp(D), _dp(E)))
+    return D, E[: n - 1]
+
+
+def createMatrixScheme1(n, lib=None):
+    """src/helper.h:28 -- d_i evenly spaced in [1,100], e = -1."""
+    return _scheme(1, n, lib)
+
+
+def createMatrixScheme2(n, lib=None):
+    """src/helper.h:39 -- [-1 2 -1]."""
+    return _scheme(2, n, lib)
+
+
+def readSymmTriadiagonalMatrixFromSparseMTX(filename, lib=None):
+    """src/filehandling.h:56 -- returns (D, E); raises CuppenError(-2) where the reference returns -1."""
+    lib = lib or load_library()
+    dp = ctypes.POINTER(ctypes.c_double)
+    D, E, n = dp(), dp(), ctypes.c_int(0)
+    _chk(lib, lib.cuppen_read_mtx(os.fsencode(filename), ctypes.byref(D), ctypes.byref(E), ctypes.byref(n)))
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+    try:
+        d = np.ctypeslib.as_array(D, shape=(n.value,)).copy()
+        e = np.ctypeslib.as_array(E, shape=(max(n.value - 1, 1),)).copy()[: n.value - 1]
+    finally:
+        libc.free(D)
+        libc.free(E)
+    return d, e
+
+
+def determineEigenvectorsToCompute(filename, n, lib=None):
+    """src/filehandling.h:69 -- sorted 0-based ranks (ascending-lambda order) listed in the -eFILE file."""
+    lib = lib or load_library()
+    ip = ctypes.POINTER(ctypes.c_int)
+    idx, cnt = ip(), ctypes.c_int(0)
+    _chk(lib, lib.cuppen_read_ev_file(os.fsencode(filename), n, ctypes.byref(idx), ctypes.byref(cnt)))
+    libc = ctypes.CDLL(None)
+    libc.free.argtypes = [ctypes.c_void_p]
+    out = np.ctypeslib.as_array(idx, shape=(max(cnt.value, 1),)).copy()[: cnt.value] if cnt.value else np.zeros(0, np.int32)
+    libc.free(idx)
+    return out
+
+
+def writeResults(filename, lam, resid=None, indices=None, lib=None):
+    """src/filehandling.h:81 (output part) -- '%20.19g %20.19g' / '%20.19g' lines in ascending lambda."""
+    lib = lib or load_library()
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    n = lam.size
+    rp = _dp(np.ascontiguousarray(resid, dtype=np.float64)) if resid is not None else None
+    if indices is None:
+        rc = lib.cuppen_write_results(os.fsencode(filename), n, _dp(lam), rp, 1 if resid is not None else 0, None, 0)
+    else:
+        idx = np.ascontiguousarray(indices, dtype=np.int32)
+        rc = lib.cuppen_write_results(os.fsencode(filename), n, _dp(lam), rp, 0,
+                                      idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), idx.size)
+    _chk(lib, rc)
+
+
+def cuppens(D, E, ref_leaves=1, vectors=True, device=0, lib=None):
+    """Convenience: full decomposition.  Returns dict(lam, resid, V, stats, timers)."""
+    s = CuppenSolver(len(D), ref_leaves=ref_leaves, vectors=vectors, device=device, lib=lib)
+    try:
+        s.set_tridiagonal(D, E)
+        s.solve()
+        out = dict(lam=s.eigenvalues(), stats=s.merge_stats(), timers=s.timers(), resid=None, V=None)
+        if vectors:
+            out["resid"] = s.residuals()
+            out["V"] = s.eigenvectors()
+        return out
+    finally:
+        s.close()

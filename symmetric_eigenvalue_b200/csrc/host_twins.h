@@ -1,0 +1,204 @@
+// TEST-ONLY host twins of the named CUDA kernels in matrix_stages.h / gemm_dmma.h, compiled only
+// with -DCUPPEN_HOST_EMULATION (tests/host/Makefile).  They let the container without a GPU
+// exercise the orchestration in solver.cu end to end.  Never part of libcuppen_b200.so.
+#ifndef CUPPEN_HOST_TWINS_H
+#define CUPPEN_HOST_TWINS_H
+#if !CUPPEN_CUDA
+
+#include <algorithm>
+#include "matrix_stages.h"
+#include "gemm_dmma.h"
+
+namespace cuppen {
+
+inline int host_leaf_ql(int nl, double* d, double* e, double* q /* row-major nl x nl, identity in */) {
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < nl; ++l) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < nl - 1; ++m) {
+                double dd = fabs(d[m]) + fabs(d[m + 1]);
+                if (fabs(e[m]) <= eps * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 90) return 1 + l;
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = sqrt(g * g + 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                bool early = false;
+                for (i = m - 1; i >= l; --i) {
+                    double f = s * e[i], b = c * e[i];
+                    r = hypot(f, g);
+                    e[i + 1] = r;
+                    if (r == 0.0) { d[i + 1] -= p; e[m] = 0.0; early = true; break; }
+                    s = f / r; c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    d[i + 1] = g + p;
+                    g = c * r - b;
+                    for (int row = 0; row < nl; ++row) {
+                        double f2 = q[row * nl + i + 1], q0 = q[row * nl + i];
+                        q[row * nl + i + 1] = s * q0 + c * f2;
+                        q[row * nl + i] = c * q0 - s * f2;
+                    }
+                }
+                if (!early) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+            }
+        } while (m != l);
+    }
+    for (int i = 0; i < nl - 1; ++i) {
+        int kmin = i; double p = d[i];
+        for (int k2 = i + 1; k2 < nl; ++k2) if (d[k2] < p) { kmin = k2; p = d[k2]; }
+        if (kmin != i) {
+            d[kmin] = d[i]; d[i] = p;
+            for (int row = 0; row < nl; ++row) std::swap(q[row * nl + i], q[row * nl + kmin]);
+        }
+    }
+    return 0;
+}
+
+inline void leaf_ql_host(const LeafDesc* leaves, int nleaves, const double* Dm, const double* E, double* lam,
+                         double* frow, double* lrow, double* Q, long ldq, int R0, int* fail) {
+    for (int leaf = 0; leaf < nleaves; ++leaf) {
+        const int off = leaves[leaf].off, nl = leaves[leaf].n;
+        std::vector<double> d(Dm + off, Dm + off + nl), e(nl, 0.0), q((size_t)nl * nl, 0.0);
+        for (int i = 0; i < nl - 1; ++i) e[i] = E[off + i];
+        for (int i = 0; i < nl; ++i) q[(size_t)i * nl + i] = 1.0;
+        int rc = host_leaf_ql(nl, d.data(), e.data(), q.data());
+        if (rc) *fail = off + rc;
+        for (int c = 0; c < nl; ++c) {
+            lam[off + c] = d[c];
+            frow[off + c] = q[c];
+            lrow[off + c] = q[(size_t)(nl - 1) * nl + c];
+            if (Q) for (int r = 0; r < nl; ++r) Q[(long)(off + r - R0) + (long)(off + c) * ldq] = q[(size_t)r * nl + c];
+        }
+    }
+}
+
+inline void secular_host(LevelCtx c, int ndesc, int part, int nparts) {
+    SerialLanes L;
+    for (int id = 0; id < ndesc; ++id) {
+        const MergeDesc& D = c.desc[id];
+        const int k = D.k;
+        const int per = (k + nparts - 1) / nparts;
+        const int i0 = part * per, i1 = std::min(k, i0 + per);
+        for (int i = i0; i < i1; ++i) {
+            SecularRoot r = secular_solve(L, k, c.dl + D.off, c.wl + D.off, fabs(D.rho), D.sumw, i);
+            c.org[D.off + i] = r.origin;
+            c.tau[D.off + i] = r.tau;
+        }
+    }
+}
+
+inline void pack_host(LevelCtx c, MatCtx M) {
+    for (int g = 0; g < c.n; ++g) {
+        const int id = c.node_of[g];
+        if (id < 0) continue;
+        const MergeDesc& D = c.desc[id];
+        const int off = D.off, e = g - off;
+        const bool zdefl = c.G[g] == -2;
+        if (!zdefl && !c.head[g]) continue;
+        const int rlo = std::max(off, M.R0), rhi = std::min(off + D.m, M.R1);
+        const int split = off + D.n1;
+        for (int r = rlo; r < rhi; ++r) {
+            const long rl = r - M.R0;
+            const bool rtop = r < split;
+            if (zdefl) {
+                const bool mine = (e < D.n1) == rtop;
+                M.Qnew[rl + (long)g * M.ldq] = mine ? M.Qold[rl + (long)g * M.ldq] : 0.0;
+                continue;
+            }
+            int a = e, b;
+            double carry = ((a < D.n1) == rtop) ? M.Qold[rl + (long)(off + a) * M.ldq] : 0.0;
+            while ((b = c.G[off + a]) >= 0) {
+                const double cs = c.gc[off + a], sn = c.gs[off + a];
+                const double x = ((b < D.n1) == rtop) ? M.Qold[rl + (long)(off + b) * M.ldq] : 0.0;
+                M.Qnew[rl + (long)(off + a) * M.ldq] = cs * carry - sn * x;
+                carry = sn * carry + cs * x;
+                a = b;
+            }
+            const int pos = rtop ? c.tpos[off + a] : c.bpos[off + a];
+            if (pos >= 0) M.Apack[rl + (long)(off + pos) * M.ldq] = carry;
+        }
+    }
+}
+
+inline void pack_tail_host(LevelCtx c, MatCtx M, int ndesc) {
+    for (int id = 0; id < ndesc; ++id) {
+        const MergeDesc& D = c.desc[id];
+        const int rlo = std::max(D.off, M.R0), rhi = std::min(D.off + D.m, M.R1);
+        for (int r = rlo; r < rhi; ++r) {
+            const bool rtop = r < D.off + D.n1;
+            const int kh = rtop ? D.ktop : D.kbot;
+            const int kend = (kh + K_PAD - 1) / K_PAD * K_PAD;
+            for (int kk = kh; kk < kend; ++kk) M.Apack[(long)(r - M.R0) + (long)(D.off + kk) * M.ldq] = 0.0;
+        }
+    }
+}
+
+inline void ugen_host(LevelCtx c, MatCtx M, int p0, int width) {
+    for (int row = 0; row < c.n; ++row) {
+        const int id = c.node_of[row];
+        if (id < 0) continue;
+        const MergeDesc& D = c.desc[id];
+        const bool top = row < D.off + D.n1;
+        const int jj = row - (top ? D.off : D.off + D.n1);
+        const int kh = top ? D.ktop : D.kbot;
+        if (jj >= kh) continue;
+        const int j = top ? c.toplist[row] : c.botlist[row];
+        const double* dl = c.dl + D.off;
+        const double dj = dl[j], zj = c.zhat[D.off + j];
+        for (int i = p0; i < D.k && i < p0 + width; ++i) {
+            double den = ((dj - dl[c.org[D.off + i]]) - c.tau[D.off + i]) * c.nrm[D.off + i];
+            if (den == 0.0) den = 4.9e-324;
+            double v = zj / den;
+            if (!(fabs(v) < 1.7e308)) v = (v > 0) ? 1.7e308 : -1.7e308;
+            M.B[(long)row * M.ldb + (i - p0)] = v;
+        }
+    }
+}
+
+inline void gemm_host(const GemmProblem* probs, int nprobs) {
+    for (int p = 0; p < nprobs; ++p) {
+        const GemmProblem& P = probs[p];
+        const int Kpad = (P.K + K_PAD - 1) / K_PAD * K_PAD;     // read the padded K like the device kernel
+        for (int nn = 0; nn < P.N; ++nn) {
+            double* ccol = P.C + (long)P.colidx[nn] * P.ldc;
+            for (int mm = 0; mm < P.M; ++mm) ccol[mm] = 0.0;
+            for (int kk = 0; kk < Kpad; ++kk) {
+                const double b = P.B[(long)kk * P.ldb + nn];
+                const double* acol = P.A + (long)kk * P.lda;
+                for (int mm = 0; mm < P.M; ++mm) ccol[mm] += acol[mm] * b;
+            }
+        }
+    }
+}
+
+inline void residual_host(const double* Q, long ldq, int n, int R0, int R1, const double* OD, const double* OE,
+                          const double* lam_sorted, const double* halo_lo, const double* halo_hi, double* res2) {
+    for (int col = 0; col < n; ++col) {
+        const double* x = Q + (long)col * ldq;
+        const double lambda = lam_sorted[col];
+        double acc = 0;
+        for (int r = R0; r < R1; ++r) {
+            const double xc = x[r - R0];
+            double y = OD[r] * xc - lambda * xc;
+            if (r > 0) y += OE[r - 1] * ((r > R0) ? x[r - 1 - R0] : halo_lo[col]);
+            if (r < n - 1) y += OE[r] * ((r + 1 < R1) ? x[r + 1 - R0] : halo_hi[col]);
+            acc += y * y;
+        }
+        res2[col] = acc;
+    }
+}
+
+inline void gather_cols_host(const double* src, double* dst, long ldq, int rows, const int* perm, int n) {
+    for (int c = 0; c < n; ++c)
+        for (int r = 0; r < rows; ++r) dst[(long)c * ldq + r] = src[(long)perm[c] * ldq + r];
+}
+
+}  // namespace cuppen
+#endif
+#endif

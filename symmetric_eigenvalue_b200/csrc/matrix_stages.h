@@ -1,0 +1,281 @@
+// Named CUDA kernels of the hot path (one `__global__` each, so that they show up under their
+// own names in ncu) and their TEST-ONLY host twins (CUPPEN_HOST_EMULATION, see platform.h):
+//
+//   leaf_ql_kernel      K0  warp-per-leaf implicit QL  (replaces LAPACKE_dsteqr, src/main.c:460)
+//   secular_kernel      K3  warp-per-root secular solver (replaces the bisection, src/eigenvalues.c:161-247)
+//   pack_kernel         K5a rotated / deflated column moves (inverse Givens of getEigenVector,
+//                           src/eigenvalues.c:343-357, applied to the columns of Q instead of per vector)
+//   ugen_kernel         K5b eigenvector matrix of the rank-one update (src/eigenvalues.c:316-321 with
+//                           the Loewner z-hat and cancellation-free differences)
+//   dgemm_dmma_kernel   K6  FP64 tensor-core GEMM  Q' = diag(Q1,Q2) U   (see gemm_dmma.h)
+//   residual_kernel     K8  ||T x - lambda x||_2 per column (src/filehandling.c:511-531)
+//   gather_cols_kernel      column permutation into ascending-lambda order (src/filehandling.c:315-321)
+#ifndef CUPPEN_MATRIX_STAGES_H
+#define CUPPEN_MATRIX_STAGES_H
+
+#include "merge_stages.h"
+#include "secular_core.h"
+
+namespace cuppen {
+
+enum { K_PAD = 32 };            // the GEMM reads K in multiples of this; A is zero-padded up to it
+enum { LEAF_MAX = 32 };         // largest leaf handled by one warp
+
+struct LeafDesc { int off, n; };
+
+struct MatCtx {
+    int n;                // global size
+    int R0, R1;           // global rows owned by this rank: [R0,R1)
+    long ldq;             // leading dimension of the Q buffers and of Apack (local rows, padded)
+    const double* Qold;   // children (block diagonal), column-major, local rows
+    double* Qnew;         // parents
+    double* Apack;        // packed live columns (K order), same shape as Q plus K_PAD columns
+    double* B;            // U arena, row-major [n + pad][ldb]
+    long ldb;
+};
+
+#if CUPPEN_CUDA
+// ------------------------------------------------------------------------------------------------
+struct WarpLanes {
+    CUPPEN_D int lane() const { return threadIdx.x & 31; }
+    CUPPEN_D int lanes() const { return 32; }
+    CUPPEN_D double sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+};
+
+// K0: one warp per leaf, lane r owns row r of Q (kept in shared memory), the scalar QL recurrence
+// is executed redundantly by all lanes (no divergence), lane 0 owns the d/e updates.
+__global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict__ leaves, int nleaves,
+                                                      const double* __restrict__ Dm, const double* __restrict__ E,
+                                                      double* __restrict__ lam, double* __restrict__ frow,
+                                                      double* __restrict__ lrow, double* __restrict__ Q, long ldq,
+                                                      int R0, int* __restrict__ fail) {
+    __shared__ double sq[4][LEAF_MAX][LEAF_MAX + 1];
+    __shared__ double sd[4][LEAF_MAX];
+    __shared__ double se[4][LEAF_MAX + 1];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int leaf = blockIdx.x * 4 + w;
+    if (leaf >= nleaves) return;
+    const int off = leaves[leaf].off, nl = leaves[leaf].n;
+    double (*q)[LEAF_MAX + 1] = sq[w];
+    double* d = sd[w];
+    double* e = se[w];
+    for (int c = 0; c < nl; ++c) q[lane][c] = (lane == c) ? 1.0 : 0.0;
+    if (lane < nl) d[lane] = Dm[off + lane];
+    if (lane < nl) e[lane] = (lane < nl - 1) ? E[off + lane] : 0.0;
+    __syncwarp();
+    const double eps = 2.220446049250313e-16;
+    for (int l = 0; l < nl; ++l) {
+        int iter = 0, m;
+        do {
+            for (m = l; m < nl - 1; ++m) {
+                double dd = fabs(d[m]) + fabs(d[m + 1]);
+                if (fabs(e[m]) <= eps * dd) break;
+            }
+            if (m != l) {
+                if (iter++ == 90) { if (lane == 0) atomicExch(fail, 1 + off + l); break; }
+                double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+                double r = sqrt(g * g + 1.0);
+                g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
+                double s = 1.0, c = 1.0, p = 0.0;
+                int i;
+                bool early = false;
+                for (i = m - 1; i >= l; --i) {
+                    double f = s * e[i];
+                    double b = c * e[i];
+                    r = hypot(f, g);
+                    __syncwarp();
+                    if (lane == 0) e[i + 1] = r;
+                    if (r == 0.0) {
+                        if (lane == 0) { d[i + 1] -= p; e[m] = 0.0; }
+                        early = true;
+                        break;
+                    }
+                    s = f / r;
+                    c = g / r;
+                    g = d[i + 1] - p;
+                    r = (d[i] - g) * s + 2.0 * c * b;
+                    p = s * r;
+                    __syncwarp();
+                    if (lane == 0) d[i + 1] = g + p;
+                    g = c * r - b;
+                    double f2 = q[lane][i + 1];
+                    double q0 = q[lane][i];
+                    q[lane][i + 1] = s * q0 + c * f2;
+                    q[lane][i] = c * q0 - s * f2;
+                }
+                __syncwarp();
+                if (!early) {
+                    if (lane == 0) { d[l] -= p; e[l] = g; e[m] = 0.0; }
+                }
+                __syncwarp();
+            }
+        } while (m != l);
+    }
+    __syncwarp();
+    // ascending order (selection sort; swaps are per-row so every lane swaps its own entries)
+    for (int i = 0; i < nl - 1; ++i) {
+        int kmin = i;
+        double p = d[i];
+        for (int k2 = i + 1; k2 < nl; ++k2) if (d[k2] < p) { kmin = k2; p = d[k2]; }
+        __syncwarp();
+        if (kmin != i) {
+            if (lane == 0) { d[kmin] = d[i]; d[i] = p; }
+            double t = q[lane][i]; q[lane][i] = q[lane][kmin]; q[lane][kmin] = t;
+        }
+        __syncwarp();
+    }
+    if (lane < nl) {
+        lam[off + lane] = d[lane];
+        frow[off + lane] = q[0][lane];
+        lrow[off + lane] = q[nl - 1][lane];
+    }
+    const int grow = off + lane;          // global row of this lane
+    if (Q != nullptr && lane < nl)
+        for (int c = 0; c < nl; ++c) Q[(long)(grow - R0) + (long)(off + c) * ldq] = q[lane][c];
+}
+
+// K3: one warp per secular root; poles and weights of the merge staged in shared memory when
+// they fit (k <= SEC_SMEM_K), otherwise read through L1/L2.
+enum { SEC_SMEM_K = 6144, SEC_WARPS = 16 };
+__global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int kcap, int part, int nparts) {
+    extern __shared__ double sec_smem[];
+    const int id = blockIdx.y;
+    const MergeDesc& D = c.desc[id];
+    const int k = D.k;
+    // roots of this merge handled by this rank: contiguous range [i0,i1) (multi-GPU root split)
+    const int per = (k + nparts - 1) / nparts;
+    const int i0 = part * per, i1 = min(k, i0 + per);
+    const int i = i0 + blockIdx.x * SEC_WARPS + (threadIdx.x >> 5);
+    if (i0 + (int)blockIdx.x * SEC_WARPS >= i1) return;
+    const double* dl = c.dl + D.off;
+    const double* wl = c.wl + D.off;
+    if (k <= kcap) {
+        for (int t = threadIdx.x; t < k; t += blockDim.x) { sec_smem[t] = dl[t]; sec_smem[kcap + t] = wl[t]; }
+        __syncthreads();
+        dl = sec_smem;
+        wl = sec_smem + kcap;
+    }
+    if (i >= i1) return;
+    WarpLanes L;
+    SecularRoot r = secular_solve(L, k, dl, wl, fabs(D.rho), D.sumw, i);
+    if (L.lane() == 0) { c.org[D.off + i] = r.origin; c.tau[D.off + i] = r.tau; }
+}
+
+// K5a: walk every rotation chain once per row.  grid.x = global column, grid.y = row chunk.
+enum { PACK_THREADS = 128, PACK_ROWS = 4 };
+__global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M) {
+    const int g = blockIdx.x;
+    const int id = c.node_of[g];
+    if (id < 0) return;
+    const MergeDesc& D = c.desc[id];
+    const int off = D.off, e = g - off;
+    const int Gg = c.G[g];
+    const bool zdefl = (Gg == -2);
+    if (!zdefl && !c.head[g]) return;
+    const int rlo = max(off, M.R0), rhi = min(off + D.m, M.R1);   // global rows of this block held here
+    const int split = off + D.n1;
+    for (int t = 0; t < PACK_ROWS; ++t) {
+        const int r = rlo + (blockIdx.y * PACK_ROWS + t) * PACK_THREADS + threadIdx.x;
+        if (r >= rhi) return;
+        const long rl = r - M.R0;
+        const bool rtop = r < split;
+        if (zdefl) {
+            const bool mine = (e < D.n1) == rtop;
+            M.Qnew[rl + (long)g * M.ldq] = mine ? M.Qold[rl + (long)g * M.ldq] : 0.0;
+            continue;
+        }
+        int a = e;
+        double carry = ((a < D.n1) == rtop) ? M.Qold[rl + (long)(off + a) * M.ldq] : 0.0;
+        int b;
+        while ((b = c.G[off + a]) >= 0) {
+            const double cs = c.gc[off + a], sn = c.gs[off + a];
+            const double x = ((b < D.n1) == rtop) ? M.Qold[rl + (long)(off + b) * M.ldq] : 0.0;
+            M.Qnew[rl + (long)(off + a) * M.ldq] = cs * carry - sn * x;
+            carry = sn * carry + cs * x;
+            a = b;
+        }
+        const int pos = rtop ? c.tpos[off + a] : c.bpos[off + a];
+        if (pos >= 0) M.Apack[rl + (long)(off + pos) * M.ldq] = carry;
+    }
+}
+
+// zero the K tail of Apack: columns [kh, round_up(kh,K_PAD)) of each half.  grid.x = descriptor,
+// grid.y = row chunk.
+__global__ void __launch_bounds__(128) pack_tail_kernel(LevelCtx c, MatCtx M) {
+    const MergeDesc& D = c.desc[blockIdx.x];
+    const int rlo = max(D.off, M.R0), rhi = min(D.off + D.m, M.R1);
+    const int r = rlo + blockIdx.y * 128 + threadIdx.x;
+    if (r >= rhi) return;
+    const bool rtop = r < D.off + D.n1;
+    const int kh = rtop ? D.ktop : D.kbot;
+    const int kend = (kh + K_PAD - 1) / K_PAD * K_PAD;
+    for (int kk = kh; kk < kend; ++kk) M.Apack[(long)(r - M.R0) + (long)(D.off + kk) * M.ldq] = 0.0;
+}
+
+// K5b: B[row = arena row of pole j][col = root i - p0] = zhat_j / (((d_j - d_org(i)) - tau_i) N_i)
+// grid.x = arena row (global index), grid.y = column chunk of 256.
+__global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width) {
+    const int row = blockIdx.x;
+    const int id = c.node_of[row];
+    if (id < 0) return;
+    const MergeDesc& D = c.desc[id];
+    const bool top = row < D.off + D.n1;
+    const int jj = row - (top ? D.off : D.off + D.n1);
+    const int kh = top ? D.ktop : D.kbot;
+    if (jj >= kh) return;
+    const int i = p0 + blockIdx.y * 256 + threadIdx.x;
+    if (i >= D.k || i >= p0 + width) return;
+    const int j = top ? c.toplist[row] : c.botlist[row];
+    const double* dl = c.dl + D.off;
+    const double dj = dl[j], zj = c.zhat[D.off + j];
+    double den = ((dj - dl[c.org[D.off + i]]) - c.tau[D.off + i]) * c.nrm[D.off + i];
+    if (den == 0.0) den = 4.9e-324;
+    double v = zj / den;
+    if (!(fabs(v) < 1.7e308)) v = (v > 0) ? 1.7e308 : -1.7e308;
+    M.B[(long)row * M.ldb + (i - p0)] = v;
+}
+
+// K8: one block per output column; V holds the columns already in ascending-lambda order
+__global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ V, long ldq, int n, int R0, int R1,
+                                                       const double* __restrict__ OD, const double* __restrict__ OE,
+                                                       const double* __restrict__ lam_sorted,
+                                                       const double* __restrict__ halo_lo, const double* __restrict__ halo_hi,
+                                                       double* __restrict__ res2) {
+    const int col = blockIdx.x;
+    const double* x = V + (long)col * ldq;
+    const double lambda = lam_sorted[col];
+    double acc = 0;
+    for (int r = R0 + threadIdx.x; r < R1; r += blockDim.x) {
+        const double xc = x[r - R0];
+        double y = OD[r] * xc - lambda * xc;
+        if (r > 0) y += OE[r - 1] * ((r > R0) ? x[r - 1 - R0] : halo_lo[col]);
+        if (r < n - 1) y += OE[r] * ((r + 1 < R1) ? x[r + 1 - R0] : halo_hi[col]);
+        acc += y * y;
+    }
+    __shared__ double red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int w = 0; w < 8; ++w) s += red[w];
+        res2[col] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) gather_cols_kernel(const double* __restrict__ src, double* __restrict__ dst,
+                                                          long ldq, int rows, const int* __restrict__ perm) {
+    const int cidx = blockIdx.x;
+    const double* s = src + (long)perm[cidx] * ldq;
+    double* d = dst + (long)cidx * ldq;
+    for (int r = blockIdx.y * 256 + threadIdx.x; r < rows; r += gridDim.y * 256) d[r] = s[r];
+}
+#endif  // CUPPEN_CUDA
+
+}  // namespace cuppen
+#endif

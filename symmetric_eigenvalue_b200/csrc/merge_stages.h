@@ -1,0 +1,440 @@
+// The O(m) / O(m^2) "vector" stages of one level of merges (z assembly, deflation, Loewner
+// vector, normalisation, new eigenvalues).  Every stage is a one-thread-per-item functor run by
+// launch_items() over the global index range [0,n): all merges of a level own disjoint index
+// ranges, `node_of[g]` says which MergeDesc (if any) index g belongs to.
+//
+// What they replace in the reference (paths under /root/reference):
+//   ZAssemble      computeZ                         src/helper.c:36-50, D copy src/main.c:534-538
+//   FlagDeflate    z-deflation                      src/eigenvalues.c:58-81
+//   RankLive       qsort of {D[i],i}                src/eigenvalues.c:83-88 (+ src/helper.c:95-103)
+//   GivensSweep    sequential Givens chain          src/eigenvalues.c:98-135
+//   Compact        (implicit: G[] tests everywhere) src/eigenvalues.c:166-208
+//   Loewner        -- absent in the reference (Gu/Eisenstat z-hat; SURVEY.md finding 4)
+//   Norms          computeNormalizationFactors      src/eigenvalues.c:257-289
+//   NewLambda      L[ind] = ...                     src/eigenvalues.c:170-171,244
+#ifndef CUPPEN_MERGE_STAGES_H
+#define CUPPEN_MERGE_STAGES_H
+
+#include <math.h>
+#include "platform.h"
+
+namespace cuppen {
+
+enum { MODE_ACCURATE = 0, MODE_REFERENCE = 1 };
+enum { SUP_TOP = 1, SUP_BOT = 2 };
+
+// One merge node of the current level (host fills the first block, device the second).
+struct MergeDesc {
+    int off, n1, n2, m;
+    int mode;
+    int pad0;
+    double rho;      // rank-one weight as seen by the solver: beta*theta (reference rule) or 2*beta
+    double theta;    // z = [last row of Q1 ; first row of Q2 / theta]
+    double zscale;   // 1 (reference rule) or 1/sqrt(2) (accurate rule, LAPACK dlaed2 convention)
+    // ---- written by the device ----
+    int nlive1;      // entries that survive z-deflation
+    int k;           // live entries after the Givens sweep = number of secular roots
+    int ktop, kbot;  // live columns with support in the upper / lower half
+    double tol;      // accurate rule: 8 eps max(|d|max,|z|max)
+    double sumw;     // sum of z^2 over the live entries
+};
+
+struct LevelCtx {
+    int n;                 // global problem size
+    MergeDesc* desc;       // descriptors of this level
+    const int* node_of;    // [n] descriptor id or -1
+    double* lam;           // [n] eigenvalues of the current nodes (children in, parents out)
+    const double* frow;    // [n] first row of each current node's Q
+    const double* lrow;    // [n] last row
+    double* d;             // [n] poles in child order
+    double* z;             // [n]
+    double* dn;            // [n] poles after the Givens sweep
+    double* zn;            // [n] z after the sweep
+    int* G;                // [n] -1 live, -2 z-deflated, >=0 local index of the rotation partner
+    double* gc;            // [n] Givens cosine, keyed by the deflated index
+    double* gs;            // [n] Givens sine
+    int* lsort;            // [n] off+p -> local index of the p-th z-live entry in ascending d
+    int* head;             // [n] 1 if the element starts a rotation chain (singletons included)
+    int* sup;              // [n] support bits of the chain ending at this element
+    int* tpos;             // [n] per element: position in the top K-list or -1
+    int* bpos;             // [n] per element: position in the bottom K-list or -1
+    // canonical live problem (rho>0, poles ascending), indexed off+ci
+    double* dl;            // poles
+    double* wl;            // z^2
+    double* zl;            // z (signed)
+    int* lidx;             // local index of the element
+    int* org;              // secular root: origin pole (canonical index)
+    double* tau;           // secular root: lambda = dl[org] + tau
+    double* zhat;          // Loewner vector
+    double* nrm;           // column norms
+    int* toplist;          // [n] off+t        -> canonical index of the t-th top-supported live column
+    int* botlist;          // [n] off+n1+t     -> canonical index of the t-th bottom-supported one
+};
+
+CUPPEN_HD bool before(double da, int ia, double db, int ib) {
+    return (da < db) || (da == db && ia < ib);
+}
+
+struct ZAssemble {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        int j = (int)g - D.off;
+        c.d[g] = c.lam[g];
+        double zv = (j < D.n1) ? c.lrow[g] : c.frow[g] / D.theta;
+        c.z[g] = zv * D.zscale;
+        c.G[g] = -1;
+        c.head[g] = 0;
+        c.sup[g] = 0;
+        c.tpos[g] = -1;
+        c.bpos[g] = -1;
+    }
+};
+
+// z-deflation flags (+ the accurate rule's tolerance, which needs the maxima of the merge)
+struct FlagDeflate {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        MergeDesc& D = c.desc[id];
+        int j = (int)g - D.off;
+        double zg = c.z[g];
+        bool defl;
+        if (D.mode == MODE_REFERENCE) {
+            defl = fabs(zg) < 1e-6;                       // src/eigenvalues.c:72,77
+        } else {
+            double dmax = 0, zmax = 0;
+            const double* dd = c.d + D.off;
+            const double* zz = c.z + D.off;
+            for (int t = 0; t < D.m; ++t) {
+                dmax = fmax(dmax, fabs(dd[t]));
+                zmax = fmax(zmax, fabs(zz[t]));
+            }
+            double tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, zmax);
+            if (j == 0) D.tol = tol;
+            defl = fabs(D.rho) * fabs(zg) <= tol;
+        }
+        if (defl) {
+            c.G[g] = -2;
+            c.dn[g] = c.d[g];
+            c.zn[g] = zg;
+        }
+    }
+};
+
+// stable enumeration sort of the z-live entries by (d, index)
+struct RankLive {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        MergeDesc& D = c.desc[id];
+        int j = (int)g - D.off;
+        const double* dd = c.d + D.off;
+        const int* GG = c.G + D.off;
+        double dj = dd[j];
+        bool live = GG[j] != -2;
+        int cnt = 0, tot = 0;
+        if (live || j == 0) {
+            for (int t = 0; t < D.m; ++t) {
+                if (GG[t] == -2) continue;
+                tot++;
+                if (before(dd[t], t, dj, j)) cnt++;
+            }
+        }
+        if (live) c.lsort[D.off + cnt] = j;
+        if (j == 0) D.nlive1 = tot;
+    }
+};
+
+// can the rotation step (p-1 -> p) fire, whatever chain state p-1 is in?  false = certified no.
+CUPPEN_HD bool step_may_fire(const MergeDesc& D, double dprev, double zprev, double dq, double zq) {
+    if (D.mode == MODE_REFERENCE) return fabs(dq - dprev) < 1e-5;     // src/eigenvalues.c:109
+    double t = dq - dprev;
+    double y = fabs(zq), x1 = fabs(zprev), x2 = 1.0 + 1e-9;
+    double g1 = x1 * y / (x1 * x1 + y * y), g2 = x2 * y / (x2 * x2 + y * y);
+    return !(t * fmin(g1, g2) > D.tol * (1.0 + 1e-9));
+}
+
+struct GivensSweep {
+    LevelCtx c;
+    CUPPEN_HD void finalize(int off, int e, double dc, double zc, int sp) const {
+        c.dn[off + e] = dc;
+        c.zn[off + e] = zc;
+        c.sup[off + e] = sp;
+    }
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        int p = (int)g - D.off;
+        if (p >= D.nlive1) return;
+        const int off = D.off;
+        const int* ls = c.lsort + off;
+        const double* dd = c.d + off;
+        const double* zz = c.z + off;
+        int e = ls[p];
+        if (p > 0) {
+            int ep = ls[p - 1];
+            if (step_may_fire(D, dd[ep], zz[ep], dd[e], zz[e])) return;      // not a segment head
+        }
+        double dc = dd[e], zc = zz[e];
+        int sp = (e < D.n1) ? SUP_TOP : SUP_BOT;
+        c.head[off + e] = 1;
+        int eprev = e;
+        for (int q = p + 1; q < D.nlive1; ++q) {
+            int eq = ls[q];
+            double dq = dd[eq], zq = zz[eq];
+            if (!step_may_fire(D, dd[eprev], zz[eprev], dq, zq)) break;    // q heads the next segment
+            bool fire;
+            double r = sqrt(zc * zc + zq * zq);                             // src/eigenvalues.c:113
+            double cs = zq / r, sn = zc / r;
+            if (D.mode == MODE_REFERENCE) fire = fabs(dq - dc) < 1e-5;
+            else fire = fabs((dq - dc) * cs * sn) <= D.tol;
+            if (fire) {
+                c.G[off + e] = eq;
+                c.gc[off + e] = cs;
+                c.gs[off + e] = sn;
+                double ti = cs * cs * dc + sn * sn * dq;                    // :126-127
+                double tj = sn * sn * dc + cs * cs * dq;
+                c.dn[off + e] = ti;
+                c.zn[off + e] = 0.0;
+                dc = tj;
+                zc = r;
+                sp |= (eq < D.n1) ? SUP_TOP : SUP_BOT;
+            } else {
+                finalize(off, e, dc, zc, sp);
+                dc = dq;
+                zc = zq;
+                sp = (eq < D.n1) ? SUP_TOP : SUP_BOT;
+                c.head[off + eq] = 1;
+            }
+            e = eq;
+            eprev = eq;
+        }
+        finalize(off, e, dc, zc, sp);
+    }
+};
+
+// build the canonical live problem (rho>0, ascending poles) and the per-half K lists
+struct Compact {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        MergeDesc& D = c.desc[id];
+        int p = (int)g - D.off;
+        if (p >= D.nlive1) return;
+        const int off = D.off;
+        const int* ls = c.lsort + off;
+        int e = ls[p];
+        if (c.G[off + e] != -1) return;
+        int cnt = 0, k = 0, tcnt = 0, bcnt = 0, kt = 0, kb = 0;
+        for (int q = 0; q < D.nlive1; ++q) {
+            int eq = ls[q];
+            if (c.G[off + eq] != -1) continue;
+            int s = c.sup[off + eq];
+            k++;
+            kt += (s & SUP_TOP) ? 1 : 0;
+            kb += (s & SUP_BOT) ? 1 : 0;
+            if (q < p) {
+                cnt++;
+                tcnt += (s & SUP_TOP) ? 1 : 0;
+                bcnt += (s & SUP_BOT) ? 1 : 0;
+            }
+        }
+        const bool neg = D.rho < 0;
+        int ci = neg ? (k - 1 - cnt) : cnt;
+        double dv = c.dn[off + e], zv = c.zn[off + e];
+        c.dl[off + ci] = neg ? -dv : dv;
+        c.zl[off + ci] = zv;
+        c.wl[off + ci] = zv * zv;
+        c.lidx[off + ci] = e;
+        int s = c.sup[off + e];
+        if (s & SUP_TOP) { c.tpos[off + e] = tcnt; c.toplist[off + tcnt] = ci; }
+        if (s & SUP_BOT) { c.bpos[off + e] = bcnt; c.botlist[off + D.n1 + bcnt] = ci; }
+        if (cnt == 0) {
+            double sw = 0;
+            for (int q = 0; q < D.nlive1; ++q) {
+                int eq = ls[q];
+                if (c.G[off + eq] == -1) { double zq = c.zn[off + eq]; sw += zq * zq; }
+            }
+            D.k = k; D.ktop = kt; D.kbot = kb; D.sumw = sw;
+        }
+    }
+};
+
+// Gu/Eisenstat: z-hat such that the computed roots are the exact eigenvalues of D + rho zhat zhat^T
+struct Loewner {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        int j = (int)g - D.off;
+        if (j >= D.k) return;
+        const double* dl = c.dl + D.off;
+        const double* tau = c.tau + D.off;
+        const int* org = c.org + D.off;
+        const double dj = dl[j];
+        double prod = (dl[org[j]] - dj) + tau[j];
+        for (int i = 0; i < D.k; ++i) {
+            if (i == j) continue;
+            prod *= ((dl[org[i]] - dj) + tau[i]) / (dl[i] - dj);
+        }
+        double zh = sqrt(fabs(prod) / fabs(D.rho));
+        c.zhat[g] = (c.zl[g] < 0) ? -zh : zh;
+    }
+};
+
+struct Norms {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        int i = (int)g - D.off;
+        if (i >= D.k) return;
+        const double* dl = c.dl + D.off;
+        const double* zh = c.zhat + D.off;
+        const double dorg = dl[c.org[g]], t = c.tau[g];
+        double s = 0;
+        for (int j = 0; j < D.k; ++j) {
+            double u = zh[j] / ((dl[j] - dorg) - t);
+            s += u * u;
+        }
+        c.nrm[g] = sqrt(s);
+    }
+};
+
+struct NewLambda {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        int j = (int)g - D.off;
+        if (c.G[g] != -1) c.lam[g] = c.dn[g];             // deflated: src/eigenvalues.c:170-171
+        if (j < D.k) {
+            double v = c.dl[D.off + c.org[g]] + c.tau[g];
+            c.lam[D.off + c.lidx[g]] = (D.rho < 0) ? -v : v;
+        }
+    }
+};
+
+// ---- K7: boundary-row propagation for the eigenvalue-only mode -------------------------------------
+// The reference never forms Q above the leaves while computing eigenvalues: it carries only the
+// first and last row of every node, Wf = Q1f U[0:n1,:], Wl = Q2l U[n1:,:] (src/main.c:613-639).
+struct RowCtx {
+    const double* frow_old;
+    const double* lrow_old;
+    double* frow_new;
+    double* lrow_new;
+    double* fpack;     // [n] off+t      : rotated first-row entries of the top-supported live columns
+    double* lpack;     // [n] off+n1+t   : rotated last-row entries of the bottom-supported live columns
+};
+
+struct RowPack {
+    LevelCtx c;
+    RowCtx r;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        const int off = D.off, e = (int)g - off, n1 = D.n1;
+        if (c.G[g] == -2) {
+            r.frow_new[g] = (e < n1) ? r.frow_old[g] : 0.0;
+            r.lrow_new[g] = (e >= n1) ? r.lrow_old[g] : 0.0;
+            return;
+        }
+        if (!c.head[g]) return;
+        int a = e, b;
+        double cf = (a < n1) ? r.frow_old[off + a] : 0.0;
+        double cl = (a >= n1) ? r.lrow_old[off + a] : 0.0;
+        while ((b = c.G[off + a]) >= 0) {
+            const double cs = c.gc[off + a], sn = c.gs[off + a];
+            const double xf = (b < n1) ? r.frow_old[off + b] : 0.0;
+            const double xl = (b >= n1) ? r.lrow_old[off + b] : 0.0;
+            r.frow_new[off + a] = cs * cf - sn * xf;
+            r.lrow_new[off + a] = cs * cl - sn * xl;
+            cf = sn * cf + cs * xf;
+            cl = sn * cl + cs * xl;
+            a = b;
+        }
+        if (c.tpos[off + a] >= 0) r.fpack[off + c.tpos[off + a]] = cf;
+        if (c.bpos[off + a] >= 0) r.lpack[off + n1 + c.bpos[off + a]] = cl;
+    }
+};
+
+struct RowGemv {
+    LevelCtx c;
+    RowCtx r;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        const int off = D.off, i = (int)g - off;
+        if (i >= D.k) return;
+        const double* dl = c.dl + off;
+        const double* zh = c.zhat + off;
+        const double dorg = dl[c.org[g]], t = c.tau[g], nn = c.nrm[g];
+        double sf = 0, sl = 0;
+        for (int q = 0; q < D.ktop; ++q) {
+            int j = c.toplist[off + q];
+            sf += r.fpack[off + q] * (zh[j] / (((dl[j] - dorg) - t) * nn));
+        }
+        for (int q = 0; q < D.kbot; ++q) {
+            int j = c.botlist[off + D.n1 + q];
+            sl += r.lpack[off + D.n1 + q] * (zh[j] / (((dl[j] - dorg) - t) * nn));
+        }
+        r.frow_new[off + c.lidx[g]] = sf;
+        r.lrow_new[off + c.lidx[g]] = sl;
+    }
+};
+
+// boundary rows of the freshly merged nodes, read back from the materialised Q (vector mode)
+struct ExtractRows {
+    LevelCtx c;
+    const double* Q;
+    long ldq;
+    int R0, R1;
+    double* frow;
+    double* lrow;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        const int first = D.off, last = D.off + D.m - 1;
+        if (first >= R0 && first < R1) frow[g] = Q[(long)(first - R0) + g * ldq];
+        if (last >= R0 && last < R1) lrow[g] = Q[(long)(last - R0) + g * ldq];
+    }
+};
+
+// final ordering: stable enumeration sort of all n eigenvalues (src/filehandling.c:315-321)
+struct FinalRank {
+    int n;
+    const double* lam;
+    int* perm;
+    double* lam_sorted;
+    CUPPEN_HD void operator()(long g) const {
+        const double v = lam[g];
+        int cnt = 0;
+        for (int j = 0; j < n; ++j) cnt += before(lam[j], j, v, (int)g) ? 1 : 0;
+        perm[cnt] = (int)g;
+        lam_sorted[cnt] = v;
+    }
+};
+
+struct ExtractRowVec {
+    const double* Q;
+    long ldq;
+    long rowlocal;
+    double* out;
+    CUPPEN_HD void operator()(long c) const { out[c] = Q[rowlocal + c * ldq]; }
+};
+
+}  // namespace cuppen
+#endif

@@ -1,0 +1,172 @@
+// Device plumbing for libcuppen_b200: error checks, device buffers and the generic
+// one-thread-per-item launcher used by the O(m) "vector" stages of a merge.
+//
+// The product is compiled by nvcc for sm_100a only.  CUPPEN_HOST_EMULATION is a TEST-ONLY build
+// mode (tests/host/Makefile, g++): the same sources run the per-item functors in a serial loop on
+// the host so the tree planning, index bookkeeping and numerics can be unit-tested in a container
+// without a GPU.  It is never compiled into libcuppen_b200.so and there is no runtime switch:
+// the shipped library has no CPU path.
+#ifndef CUPPEN_PLATFORM_H
+#define CUPPEN_PLATFORM_H
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#if defined(__CUDACC__) && !defined(CUPPEN_HOST_EMULATION)
+#define CUPPEN_CUDA 1
+#include <cuda_runtime.h>
+#else
+#ifndef CUPPEN_HOST_EMULATION
+#error "libcuppen_b200 must be compiled with nvcc (sm_100a); the host build is test-only (-DCUPPEN_HOST_EMULATION)"
+#endif
+#define CUPPEN_CUDA 0
+#endif
+
+#if CUPPEN_CUDA
+#define CUPPEN_HD __host__ __device__ __forceinline__
+#define CUPPEN_D __device__ __forceinline__
+#else
+#define CUPPEN_HD inline
+#define CUPPEN_D inline
+#endif
+
+namespace cuppen {
+
+struct Error {
+    int code;
+    std::string msg;
+};
+
+#define CUPPEN_THROW(code_, ...)                                   \
+    do {                                                           \
+        char buf_[512];                                            \
+        snprintf(buf_, sizeof buf_, __VA_ARGS__);                  \
+        throw ::cuppen::Error{(code_), std::string(buf_)};         \
+    } while (0)
+
+#if CUPPEN_CUDA
+#define CUDA_CHECK(expr)                                                                        \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            CUPPEN_THROW(-10, "CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__,      \
+                         __LINE__, cudaGetErrorString(e_));                                     \
+    } while (0)
+typedef cudaStream_t Stream;
+#else
+typedef int Stream;
+#endif
+
+// ---- device memory ---------------------------------------------------------------------------
+inline void* dev_alloc_bytes(size_t bytes) {
+    if (bytes == 0) bytes = 8;
+#if CUPPEN_CUDA
+    void* p = nullptr;
+    CUDA_CHECK(cudaMalloc(&p, bytes));
+    return p;
+#else
+    void* p = malloc(bytes);
+    if (!p) CUPPEN_THROW(-11, "host emulation: out of memory (%zu bytes)", bytes);
+    memset(p, 0xff, bytes);   // poison (NaN pattern) so that reads of unwritten memory show up
+    return p;
+#endif
+}
+inline void dev_free(void* p) {
+    if (!p) return;
+#if CUPPEN_CUDA
+    cudaFree(p);
+#else
+    free(p);
+#endif
+}
+inline void dev_h2d(void* d, const void* h, size_t bytes, Stream s) {
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, s));
+#else
+    (void)s; memcpy(d, h, bytes);
+#endif
+}
+inline void dev_d2h(void* h, const void* d, size_t bytes, Stream s) {
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, s));
+#else
+    (void)s; memcpy(h, d, bytes);
+#endif
+}
+inline void dev_d2d(void* dst, const void* src, size_t bytes, Stream s) {
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+#else
+    (void)s; memmove(dst, src, bytes);
+#endif
+}
+inline void dev_zero(void* d, size_t bytes, Stream s) {
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaMemsetAsync(d, 0, bytes, s));
+#else
+    (void)s; memset(d, 0, bytes);
+#endif
+}
+inline void dev_sync(Stream s) {
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaStreamSynchronize(s));
+#else
+    (void)s;
+#endif
+}
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { dev_free(p); }
+    void alloc(size_t count) {
+        dev_free(p);
+        p = nullptr;
+        n = count;
+        p = static_cast<T*>(dev_alloc_bytes(count * sizeof(T)));
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// ---- generic per-item launcher -----------------------------------------------------------------
+// Functor F: `CUPPEN_HD void operator()(long i) const`.  Kernel names in profiles read
+// cuppen::per_item_kernel<cuppen::ZAssemble> etc.
+#if CUPPEN_CUDA
+template <class F>
+__global__ void __launch_bounds__(256) per_item_kernel(long n, F f) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) f(i);
+}
+#endif
+
+struct LaunchCounter {
+    long launches = 0;
+};
+extern LaunchCounter g_launches;
+
+template <class F>
+inline void launch_items(Stream s, long n, const F& f) {
+    if (n <= 0) return;
+#if CUPPEN_CUDA
+    long blocks = (n + 255) / 256;
+    per_item_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(n, f);
+    CUDA_CHECK(cudaGetLastError());
+#else
+    (void)s;
+    for (long i = 0; i < n; ++i) f(i);
+#endif
+    g_launches.launches++;
+}
+
+static inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
+
+}  // namespace cuppen
+#endif

@@ -1,0 +1,170 @@
+// Secular-equation root finder shared by the warp-per-root CUDA kernel (secular_kernel in
+// cuppen_kernels.cu) and the host-side unit tests (tests/ compile this header with g++ to
+// check the numerics without a GPU).  It replaces the bisection loop of the reference,
+// /root/reference/src/eigenvalues.c:161-247 (secularEquation :8-17), with a rational
+// interpolation ("middle way", Li 1994 / LAPACK working note 89) iteration that is safeguarded
+// by a bracket, and returns the root as (origin pole, tau) so that consumers can form
+// d_j - lambda_i = (d_j - d_origin) - tau without cancellation.
+//
+// Canonical problem (the caller reflects rho<0 problems):  rho > 0,
+//   d[0] < d[1] < ... < d[k-1],  w[j] = z_j^2 > 0,
+//   g(lambda) = 1/rho + sum_j w[j] / (d[j] - lambda),   root i in (d[i], d[i+1]),
+//   last root in (d[k-1], d[k-1] + rho*sum(w)].
+#ifndef CUPPEN_SECULAR_CORE_H
+#define CUPPEN_SECULAR_CORE_H
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define CUPPEN_HD __host__ __device__ __forceinline__
+#else
+#define CUPPEN_HD inline
+#endif
+
+namespace cuppen {
+
+struct SecularSums {
+    double psi, dpsi, phi, dphi, err;
+};
+
+// Lanes policy for the host: one lane, no reduction.
+struct SerialLanes {
+    CUPPEN_HD int lane() const { return 0; }
+    CUPPEN_HD int lanes() const { return 1; }
+    CUPPEN_HD double sum(double v) const { return v; }
+};
+
+// psi = sum_{j<=split} w_j/(delta_j - tau), phi = sum_{j>split}; derivatives likewise.
+// `skip0`, `skip1` (pole indices or -1) are left out (used for the initial guess).
+template <class Lanes>
+CUPPEN_HD SecularSums secular_eval(const Lanes& L, int k, const double* __restrict__ d,
+                                   const double* __restrict__ w, double dorg, double tau, int split,
+                                   int skip0, int skip1) {
+    double psi = 0, dpsi = 0, phi = 0, dphi = 0, err = 0;
+    for (int j = L.lane(); j < k; j += L.lanes()) {
+        if (j == skip0 || j == skip1) continue;
+        double t = (d[j] - dorg) - tau;
+        double inv = 1.0 / t;
+        double r = w[j] * inv;
+        if (j <= split) { psi += r; dpsi += r * inv; }
+        else { phi += r; dphi += r * inv; }
+        err += fabs(r);
+    }
+    SecularSums s;
+    s.psi = L.sum(psi); s.dpsi = L.sum(dpsi); s.phi = L.sum(phi); s.dphi = L.sum(dphi); s.err = L.sum(err);
+    return s;
+}
+
+struct SecularRoot {
+    int origin;     // index of the pole tau is measured from
+    double tau;     // lambda = d[origin] + tau
+    int iters;      // function evaluations spent
+};
+
+// Solve for root i.  sumw = sum_j w[j] (only needed for the last root).
+template <class Lanes>
+CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restrict__ d,
+                                    const double* __restrict__ w, double rho, double sumw, int i) {
+    const double eps = 2.220446049250313e-16;
+    const double rhoinv = 1.0 / rho;
+    SecularRoot out;
+    out.iters = 0;
+    if (k == 1) { out.origin = 0; out.tau = rho * w[0]; return out; }
+
+    const bool last = (i == k - 1);
+    // interpolation poles: (ip0, ip1) = (i, i+1) for interior roots, (k-2, k-1) for the last one
+    const int ip0 = last ? k - 2 : i;
+    const int ip1 = ip0 + 1;
+    int org;
+    double lo, hi, tau;
+    const double gap = d[ip1] - d[ip0];
+
+    if (!last) {
+        // decide the origin from the sign of g at the midpoint (evaluated relative to pole i)
+        const double half = 0.5 * gap;
+        SecularSums s = secular_eval(L, k, d, w, d[i], half, i, ip0, ip1);
+        out.iters++;
+        const double c = rhoinv + s.psi + s.phi;                 // all poles except ip0, ip1
+        const double gmid = c + w[ip0] / (-half) + w[ip1] / half;
+        const double a_ = c * gap, w0 = w[ip0], w1 = w[ip1];
+        if (gmid >= 0.0) {            // root in the left half: origin i, tau in (0, gap/2]
+            org = i; lo = 0.0; hi = half;
+            const double a = a_ + w0 + w1, b = w0 * gap;
+            const double disc = sqrt(fabs(a * a - 4.0 * b * c));
+            tau = (a > 0.0) ? 2.0 * b / (a + disc) : (a - disc) / (2.0 * c);
+        } else {                      // origin i+1, tau in [-gap/2, 0)
+            org = i + 1; lo = -half; hi = 0.0;
+            const double a = a_ - w0 - w1, b = w1 * gap;
+            const double disc = sqrt(fabs(a * a + 4.0 * b * c));
+            tau = (a < 0.0) ? 2.0 * b / (a - disc) : -(a + disc) / (2.0 * c);
+        }
+        if (!(tau > lo && tau < hi)) tau = 0.5 * (lo + hi);
+    } else {
+        org = k - 1;
+        const double R = rho * sumw;
+        const double mid = 0.5 * R;
+        SecularSums s = secular_eval(L, k, d, w, d[org], mid, k, ip0, ip1);
+        out.iters++;
+        const double c = rhoinv + s.psi;                         // poles 0..k-3
+        const double w0 = w[ip0], w1 = w[ip1];
+        const double gmid = c + w0 / (-gap - mid) + w1 / (-mid);
+        const double a = -c * gap + w0 + w1, b = w1 * gap;
+        const double disc = sqrt(fabs(a * a + 4.0 * b * c));
+        if (gmid <= 0.0) {            // root above the midpoint
+            lo = mid; hi = R;
+            const double temp = w0 / (gap + R) + w1 / R;
+            if (c <= temp) tau = R;
+            else tau = (a < 0.0) ? 2.0 * b / (disc - a) : (a + disc) / (2.0 * c);
+        } else {
+            lo = 0.0; hi = mid;
+            tau = (a < 0.0) ? 2.0 * b / (disc - a) : (a + disc) / (2.0 * c);
+        }
+        if (!(tau > lo && tau <= hi)) tau = 0.5 * (lo + hi);
+    }
+
+    const double dorg = d[org];
+    const int split = last ? k - 2 : i;     // psi covers poles <= split
+    double prevabs = INFINITY;
+    int slow = 0;
+    for (int it = 0; it < 80; ++it) {
+        SecularSums s = secular_eval(L, k, d, w, dorg, tau, split, -1, -1);
+        out.iters++;
+        const double h = rhoinv + s.psi + s.phi;
+        const double errb = eps * (8.0 * s.err + fabs(rhoinv) + fabs(tau) * (s.dpsi + s.dphi));
+        if (fabs(h) <= errb) break;
+        if (h < 0.0) lo = tau; else hi = tau;                    // g is increasing in tau
+        if (hi - lo <= 2.0 * eps * fmax(fabs(lo), fabs(hi))) { tau = 0.5 * (lo + hi); break; }
+        // middle-way step: match psi, psi' with a pole at ip0 and phi, phi' with a pole at ip1
+        const double DL = (d[ip0] - dorg) - tau, DR = (d[ip1] - dorg) - tau;
+        const double c = h - DL * s.dpsi - DR * s.dphi;
+        const double a = (DL + DR) * h - DL * DR * (s.dpsi + s.dphi);
+        const double b = DL * DR * h;
+        double eta;
+        if (c == 0.0) {
+            eta = (a != 0.0) ? b / a : 0.5 * (lo + hi) - tau;
+        } else {
+            const double disc = sqrt(fabs(a * a - 4.0 * b * c));
+            if (!last) eta = (a <= 0.0) ? (a - disc) / (2.0 * c) : 2.0 * b / (a + disc);
+            else       eta = (a >= 0.0) ? (a + disc) / (2.0 * c) : 2.0 * b / (a - disc);
+        }
+        if (h * eta >= 0.0) eta = -h / (s.dpsi + s.dphi);        // wrong direction: Newton step
+        double nt = tau + eta;
+        const double ah = fabs(h);
+        if (ah > 0.5 * prevabs) slow++;
+        prevabs = ah;
+        if (!(nt > lo && nt < hi) || slow >= 2) {
+            // safeguard: bisect the bracket (geometrically when it spans many binades)
+            if (lo > 0.0 && hi > 16.0 * lo) nt = sqrt(lo) * sqrt(hi);
+            else if (hi < 0.0 && lo < 16.0 * hi) nt = -sqrt(-lo) * sqrt(-hi);
+            else nt = 0.5 * (lo + hi);
+            slow = 0;
+        }
+        tau = nt;
+    }
+    out.origin = org;
+    out.tau = tau;
+    return out;
+}
+
+}  // namespace cuppen
+#endif

@@ -1,0 +1,736 @@
+// libcuppen_b200: host orchestration of the divide-and-conquer tree and the C ABI
+// (include/cuppen_b200.h).  Replaces the conquer loop of the reference's main()
+// (/root/reference/src/main.c:495-664) and the back-transformation of writeResults
+// (/root/reference/src/filehandling.c:332-548): one process drives one B200; all merges of a
+// tree level are batched into the same launches.
+#include <math.h>
+#include <algorithm>
+#include <chrono>
+#include <map>
+
+#include "../../include/cuppen_b200.h"
+#include "platform.h"
+#include "plan.h"
+#include "merge_stages.h"
+#include "matrix_stages.h"
+#include "gemm_dmma.h"
+#include "host_twins.h"
+#include "comm.h"
+
+namespace cuppen {
+
+LaunchCounter g_launches;
+static thread_local std::string g_last_error;
+
+static double wall_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---- per-category device timers (CUDA events on the solver's stream) ---------------------------
+enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_NCAT };
+struct PhaseTimers {
+    double acc[T_NCAT] = {0};
+#if CUPPEN_CUDA
+    struct Span { int cat; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+    cudaEvent_t get() {
+        if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+        cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); return e;
+    }
+    void begin(int cat, Stream s) { Span sp{cat, get(), get()}; CUDA_CHECK(cudaEventRecord(sp.a, s)); spans.push_back(sp); }
+    void end(Stream s) { CUDA_CHECK(cudaEventRecord(spans.back().b, s)); }
+    void collect() {
+        for (auto& sp : spans) {
+            float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b);
+            acc[sp.cat] += ms * 1e-3;
+            pool.push_back(sp.a); pool.push_back(sp.b);
+        }
+        spans.clear();
+    }
+    ~PhaseTimers() { for (auto e : pool) cudaEventDestroy(e); for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);} }
+#else
+    int cur = -1; double t0 = 0;
+    void begin(int cat, Stream) { cur = cat; t0 = wall_now(); }
+    void end(Stream) { acc[cur] += wall_now() - t0; }
+    void collect() {}
+#endif
+    void reset() { for (double& a : acc) a = 0; }
+};
+
+struct Solver {
+    int n = 0, P = 1, flags = 0, device = 0;
+    bool want_vectors = false;
+    Comm comm;
+    Plan plan;
+    bool have_matrix = false, solved = false;
+    int R0 = 0, R1 = 0, nloc = 0;
+    long ldq = 0, ldb = 0;
+    int W = 0;                    // panel width of the U arena
+    Stream stream = 0;
+
+    std::vector<double> hD, hE;   // original matrix (host)
+    DevBuf<double> dDm, dE, dOD, dOE;
+    DevBuf<double> lam, lam_sorted, frow, lrow, frow2, lrow2, fpack, lpack;
+    DevBuf<double> d, z, dn, zn, gc, gs, dl, wl, zl, tau, zhat, nrm, res2, halo, halo_all;
+    DevBuf<int> node_of, G, lsort, head, sup, tpos, bpos, lidx, org, toplist, botlist, perm, fail;
+    DevBuf<double> Qa, Qb, Apack, B;
+    DevBuf<MergeDesc> desc;
+    DevBuf<LeafDesc> leaves;
+    DevBuf<GemmProblem> probs;
+    DevBuf<GemmTile> tiles;
+    double* Qcur = nullptr;       // children / final
+    double* Qnext = nullptr;
+    bool final_sorted_in_next = false;
+
+    std::vector<double> h_lam_sorted, h_resid;
+    std::vector<cuppen_merge_stat> stats;
+    PhaseTimers pt;
+    cuppen_timers timers;
+    // rank layout
+    std::vector<int> rank_lo, rank_hi;       // row range per rank
+    std::vector<int> parent_of;              // plan node -> parent node id
+
+    void init_layout();
+    void allocate();
+    void set_matrix(const double* D, const double* E);
+    void solve();
+    void run_leaves();
+    void run_level(int h);
+    void finish();
+    LevelCtx level_ctx();
+    MatCtx mat_ctx();
+};
+
+// ---- layout --------------------------------------------------------------------------------------
+void Solver::init_layout() {
+    const int world = comm.world;
+    rank_lo.assign(world, 0);
+    rank_hi.assign(world, n);
+    if (world > 1) {
+        int g = 0;
+        while ((1 << g) < world) ++g;
+        if ((1 << g) != world) CUPPEN_THROW(CUPPEN_ERR_ARG, "world size %d is not a power of two", world);
+        std::vector<std::pair<int, int>> ranges;
+        for (const PlanNode& nd : plan.nodes)
+            if (nd.depth == g) ranges.push_back({nd.off, nd.off + nd.n});
+        std::sort(ranges.begin(), ranges.end());
+        long covered = 0;
+        for (auto& r : ranges) covered += r.second - r.first;
+        if ((int)ranges.size() != world || covered != n)
+            CUPPEN_THROW(CUPPEN_ERR_ARG, "the divide tree of n=%d (reference leaves %d) has no level with %d subtrees", n, P, world);
+        for (int r = 0; r < world; ++r) { rank_lo[r] = ranges[r].first; rank_hi[r] = ranges[r].second; }
+    }
+    parent_of.assign(plan.nodes.size(), -1);
+    for (size_t id = 0; id < plan.nodes.size(); ++id)
+        if (plan.nodes[id].left >= 0) { parent_of[plan.nodes[id].left] = (int)id; parent_of[plan.nodes[id].right] = (int)id; }
+    R0 = rank_lo[comm.rank];
+    R1 = rank_hi[comm.rank];
+    nloc = R1 - R0;
+    ldq = round_up(nloc, 16);
+}
+
+void Solver::allocate() {
+    const size_t N = (size_t)n;
+    for (DevBuf<double>* b : {&dDm, &dE, &dOD, &dOE, &lam, &lam_sorted, &frow, &lrow, &frow2, &lrow2, &fpack, &lpack, &d, &z,
+                              &dn, &zn, &gc, &gs, &dl, &wl, &zl, &tau, &zhat, &nrm, &res2})
+        b->alloc(N + 64);
+    for (DevBuf<int>* b : {&node_of, &G, &lsort, &head, &sup, &tpos, &bpos, &lidx, &org, &toplist, &botlist, &perm})
+        b->alloc(N + 64);
+    fail.alloc(4);
+    halo.alloc(2 * N + 64);
+    halo_all.alloc(2 * N * (size_t)comm.world + 64);
+    size_t maxdesc = 1;
+    for (auto& v : plan.by_height) maxdesc = std::max(maxdesc, v.size());
+    desc.alloc(maxdesc);
+    leaves.alloc(std::max<size_t>(1, plan.leaves.size()));
+    if (want_vectors) {
+        const size_t qelems = (size_t)ldq * (N + K_PAD + 2) + 4096;
+        Qa.alloc(qelems);
+        Qb.alloc(qelems);
+        Apack.alloc(qelems);
+        // U arena: rows indexed by global pole index, W columns per panel (<= 2 GiB)
+        const size_t cap = (size_t)1 << 28;
+        W = (int)std::min<size_t>(N, std::max<size_t>(256, cap / N));
+        ldb = round_up(W, 16) + 16;
+        B.alloc((N + 2 * K_PAD + 8) * (size_t)ldb + 4096);
+        dev_zero(B.p, B.bytes(), stream);
+        dev_zero(Apack.p, Apack.bytes(), stream);
+        dev_zero(Qa.p, Qa.bytes(), stream);
+        dev_zero(Qb.p, Qb.bytes(), stream);
+        probs.alloc(2 * maxdesc + 2);
+    }
+    dev_zero(halo.p, halo.bytes(), stream);
+    dev_sync(stream);
+}
+
+void Solver::set_matrix(const double* D, const double* E) {
+    hD.assign(D, D + n);
+    hE.assign(E, E + std::max(0, n - 1));
+    for (int i = 0; i < n - 1; ++i)
+        if (hE[i] == 0.0 && P > 1) {
+            // only the reference-rule splits need beta != 0 (assert at src/main.c:196-200, src/eigenvalues.c:68)
+            for (const PlanNode& nd : plan.nodes)
+                if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.off + nd.n1 - 1 == i)
+                    CUPPEN_THROW(CUPPEN_ERR_ZERO, "zero off-diagonal entry E[%d] at a reference split", i);
+        }
+    Plan fresh;
+    int rc = build_plan(fresh, n, hD.data(), hE.data(), P, LEAF_MAX);
+    if (rc != 0) CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
+    plan = fresh;
+    for (const PlanNode& nd : plan.nodes)
+        if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.rho == 0.0)
+            CUPPEN_THROW(CUPPEN_ERR_ZERO, "zero off-diagonal entry at a reference split (row %d)", nd.off + nd.n1);
+    dev_h2d(dDm.p, plan.D.data(), sizeof(double) * n, stream);
+    dev_h2d(dOD.p, hD.data(), sizeof(double) * n, stream);
+    if (n > 1) {
+        dev_h2d(dE.p, hE.data(), sizeof(double) * (n - 1), stream);
+        dev_h2d(dOE.p, hE.data(), sizeof(double) * (n - 1), stream);
+    }
+    dev_sync(stream);
+    have_matrix = true;
+    solved = false;
+}
+
+LevelCtx Solver::level_ctx() {
+    LevelCtx c;
+    c.n = n; c.desc = desc.p; c.node_of = node_of.p; c.lam = lam.p; c.frow = frow.p; c.lrow = lrow.p;
+    c.d = d.p; c.z = z.p; c.dn = dn.p; c.zn = zn.p; c.G = G.p; c.gc = gc.p; c.gs = gs.p; c.lsort = lsort.p;
+    c.head = head.p; c.sup = sup.p; c.tpos = tpos.p; c.bpos = bpos.p; c.dl = dl.p; c.wl = wl.p; c.zl = zl.p;
+    c.lidx = lidx.p; c.org = org.p; c.tau = tau.p; c.zhat = zhat.p; c.nrm = nrm.p; c.toplist = toplist.p;
+    c.botlist = botlist.p;
+    return c;
+}
+
+MatCtx Solver::mat_ctx() {
+    MatCtx M;
+    M.n = n; M.R0 = R0; M.R1 = R1; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qnext; M.Apack = Apack.p; M.B = B.p; M.ldb = ldb;
+    return M;
+}
+
+// ---- leaves ---------------------------------------------------------------------------------------
+void Solver::run_leaves() {
+    std::vector<LeafDesc> hl;
+    for (int id : plan.leaves) {
+        const PlanNode& nd = plan.nodes[id];
+        if (nd.off >= R0 && nd.off + nd.n <= R1) hl.push_back(LeafDesc{nd.off, nd.n});
+        else if (nd.off < R1 && nd.off + nd.n > R0) CUPPEN_THROW(CUPPEN_ERR_STATE, "leaf straddles a rank boundary");
+    }
+    if (hl.empty()) return;
+    dev_h2d(leaves.p, hl.data(), sizeof(LeafDesc) * hl.size(), stream);
+    dev_zero(fail.p, sizeof(int) * 4, stream);
+    pt.begin(T_LEAF, stream);
+    double* Q = want_vectors ? Qcur : nullptr;
+#if CUPPEN_CUDA
+    leaf_ql_kernel<<<(unsigned)((hl.size() + 3) / 4), 128, 0, stream>>>(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p,
+                                                                       lrow.p, Q, ldq, R0, fail.p);
+    CUDA_CHECK(cudaGetLastError());
+#else
+    leaf_ql_host(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p, lrow.p, Q, ldq, R0, fail.p);
+#endif
+    g_launches.launches++;
+    pt.end(stream);
+}
+
+// ---- one tree level ---------------------------------------------------------------------------------
+template <int BM, int BN, int BK, int WMs, int WNs, int STAGES>
+static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tiles, int ntiles) {
+#if CUPPEN_CUDA
+    using Cfg = DmmaCfg<BM, BN, BK, WMs, WNs, STAGES>;
+    auto kern = dgemm_dmma_kernel<BM, BN, BK, WMs, WNs, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
+        attr_set = true;
+    }
+    int grid = std::min(ntiles, 148 * 8);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(probs, tiles, ntiles);
+    CUDA_CHECK(cudaGetLastError());
+#else
+    (void)s; (void)probs; (void)tiles; (void)ntiles;
+#endif
+}
+
+void Solver::run_level(int h) {
+    // nodes of this height that intersect my rows
+    std::vector<int> ids;
+    for (int id : plan.by_height[h]) {
+        const PlanNode& nd = plan.nodes[id];
+        if (nd.off < R1 && nd.off + nd.n > R0) ids.push_back(id);
+    }
+    if (ids.empty()) return;
+    const int nd_cnt = (int)ids.size();
+    std::vector<MergeDesc> hd(nd_cnt);
+    std::vector<int> hnode(n, -1);
+    int glo = comm.rank, gcnt = 1;           // rank group of a cooperative node
+    for (int t = 0; t < nd_cnt; ++t) {
+        const PlanNode& nd = plan.nodes[ids[t]];
+        MergeDesc& D = hd[t];
+        memset(&D, 0, sizeof D);
+        D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
+        D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale;
+        for (int g = nd.off; g < nd.off + nd.n; ++g) hnode[g] = t;
+        if (nd.off < R0 || nd.off + nd.n > R1) {       // spans several ranks
+            if (nd_cnt != 1) CUPPEN_THROW(CUPPEN_ERR_STATE, "cooperative node is not alone on its level");
+            glo = 0;
+            while (rank_lo[glo] < nd.off) ++glo;
+            int ghi = glo;
+            while (ghi < comm.world && rank_hi[ghi] <= nd.off + nd.n) ++ghi;
+            gcnt = ghi - glo;
+        }
+    }
+    dev_h2d(desc.p, hd.data(), sizeof(MergeDesc) * nd_cnt, stream);
+    dev_h2d(node_of.p, hnode.data(), sizeof(int) * n, stream);
+    LevelCtx c = level_ctx();
+
+    if (gcnt > 1) {
+        // children's eigenvalues and boundary rows from their owners (src/main.c:501-517,530-542)
+        const MergeDesc& D = hd[0];
+        int gmid = glo;
+        while (rank_lo[gmid] < D.off + D.n1) ++gmid;                 // first rank of the right child
+        comm.group_bcast(lam.p + D.off, sizeof(double) * D.n1, gmid - 1, glo, gcnt, stream);
+        comm.group_bcast(lrow.p + D.off, sizeof(double) * D.n1, gmid - 1, glo, gcnt, stream);
+        comm.group_bcast(lam.p + D.off + D.n1, sizeof(double) * D.n2, gmid, glo, gcnt, stream);
+        comm.group_bcast(frow.p + D.off + D.n1, sizeof(double) * D.n2, gmid, glo, gcnt, stream);
+    }
+
+    pt.begin(T_DEFL, stream);
+    launch_items(stream, n, ZAssemble{c});
+    launch_items(stream, n, FlagDeflate{c});
+    launch_items(stream, n, RankLive{c});
+    launch_items(stream, n, GivensSweep{c});
+    launch_items(stream, n, Compact{c});
+    pt.end(stream);
+    dev_d2h(hd.data(), desc.p, sizeof(MergeDesc) * nd_cnt, stream);
+    dev_sync(stream);
+
+    int maxk = 0, maxm_rows = 0;
+    for (int t = 0; t < nd_cnt; ++t) {
+        const MergeDesc& D = hd[t];
+        maxk = std::max(maxk, D.k);
+        maxm_rows = std::max(maxm_rows, std::min(D.off + D.m, R1) - std::max(D.off, R0));
+        cuppen_merge_stat st;
+        st.offset = D.off; st.m = D.m; st.n1 = D.n1; st.mode = D.mode; st.zdefl = D.m - D.nlive1;
+        st.givens = D.nlive1 - D.k; st.k = D.k; st.height = h; st.rho = plan.nodes[ids[t]].beta * plan.nodes[ids[t]].theta;
+        stats.push_back(st);
+    }
+
+    if (maxk > 0) {
+        pt.begin(T_ROOT, stream);
+        const int part = comm.rank - glo;
+        const int per = (maxk + gcnt - 1) / gcnt;
+#if CUPPEN_CUDA
+        {
+            int kcap = std::min((int)round_up(maxk, 32), (int)SEC_SMEM_K);
+            size_t smem = (size_t)2 * kcap * sizeof(double);
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(2 * SEC_SMEM_K * sizeof(double))));
+                attr_set = true;
+            }
+            dim3 grid((unsigned)((per + SEC_WARPS - 1) / SEC_WARPS), (unsigned)nd_cnt);
+            secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, gcnt);
+            CUDA_CHECK(cudaGetLastError());
+        }
+#else
+        secular_host(c, nd_cnt, part, gcnt);
+#endif
+        g_launches.launches++;
+        pt.end(stream);
+        if (gcnt > 1) {
+            const MergeDesc& D = hd[0];
+            const int per1 = (D.k + gcnt - 1) / gcnt;
+            for (int r = 0; r < gcnt; ++r) {
+                int i0 = r * per1, i1 = std::min(D.k, i0 + per1);
+                if (i1 <= i0) continue;
+                comm.group_bcast(tau.p + D.off + i0, sizeof(double) * (i1 - i0), glo + r, glo, gcnt, stream);
+                comm.group_bcast(org.p + D.off + i0, sizeof(int) * (i1 - i0), glo + r, glo, gcnt, stream);
+            }
+        }
+        pt.begin(T_EVX, stream);
+        launch_items(stream, n, Loewner{c});
+        launch_items(stream, n, Norms{c});
+        pt.end(stream);
+    }
+    pt.begin(T_EVX, stream);
+    launch_items(stream, n, NewLambda{c});
+    pt.end(stream);
+
+    if (!want_vectors) {
+        RowCtx r{frow.p, lrow.p, frow2.p, lrow2.p, fpack.p, lpack.p};
+        pt.begin(T_EVX, stream);
+        launch_items(stream, n, RowPack{c, r});
+        if (maxk > 0) launch_items(stream, n, RowGemv{c, r});
+        pt.end(stream);
+        // copy the new rows of this level's nodes back (other index ranges keep their values)
+        for (int t = 0; t < nd_cnt; ++t) {
+            dev_d2d(frow.p + hd[t].off, frow2.p + hd[t].off, sizeof(double) * hd[t].m, stream);
+            dev_d2d(lrow.p + hd[t].off, lrow2.p + hd[t].off, sizeof(double) * hd[t].m, stream);
+        }
+        return;
+    }
+
+    MatCtx M = mat_ctx();
+    pt.begin(T_PACK, stream);
+#if CUPPEN_CUDA
+    {
+        dim3 grid((unsigned)n, (unsigned)((maxm_rows + PACK_THREADS * PACK_ROWS - 1) / (PACK_THREADS * PACK_ROWS)));
+        pack_kernel<<<grid, PACK_THREADS, 0, stream>>>(c, M);
+        CUDA_CHECK(cudaGetLastError());
+        dim3 grid2((unsigned)nd_cnt, (unsigned)((maxm_rows + 127) / 128));
+        pack_tail_kernel<<<grid2, 128, 0, stream>>>(c, M);
+        CUDA_CHECK(cudaGetLastError());
+    }
+#else
+    pack_host(c, M);
+    pack_tail_host(c, M, nd_cnt);
+#endif
+    g_launches.launches += 2;
+    pt.end(stream);
+
+    // panels of W root columns: U generation, then one GEMM launch over all (merge, half) problems
+    const bool small_tiles = (maxm_rows <= 256);
+    for (int p0 = 0; p0 < maxk; p0 += W) {
+        const int width = std::min(W, maxk - p0);
+        pt.begin(T_UGEN, stream);
+#if CUPPEN_CUDA
+        {
+            dim3 grid((unsigned)n, (unsigned)((width + 255) / 256));
+            ugen_kernel<<<grid, 256, 0, stream>>>(c, M, p0, width);
+            CUDA_CHECK(cudaGetLastError());
+        }
+#else
+        ugen_host(c, M, p0, width);
+#endif
+        g_launches.launches++;
+        pt.end(stream);
+
+        std::vector<GemmProblem> hp;
+        std::vector<GemmTile> ht;
+        const int BM = small_tiles ? 64 : 128, BN = small_tiles ? 64 : 128;
+        for (int t = 0; t < nd_cnt; ++t) {
+            const MergeDesc& D = hd[t];
+            if (D.k <= p0) continue;
+            const int N = std::min(width, D.k - p0);
+            for (int half = 0; half < 2; ++half) {
+                const int hs = half ? D.off + D.n1 : D.off;             // first global row of the half
+                const int he = half ? D.off + D.m : D.off + D.n1;
+                const int rs = std::max(hs, R0), re = std::min(he, R1);
+                if (re <= rs) continue;
+                GemmProblem Pb;
+                Pb.M = re - rs; Pb.N = N; Pb.K = half ? D.kbot : D.ktop;
+                Pb.A = Apack.p + (rs - R0) + (long)D.off * ldq; Pb.lda = ldq;
+                Pb.B = B.p + (long)hs * ldb; Pb.ldb = ldb;
+                Pb.C = Qnext + (rs - R0) + (long)D.off * ldq; Pb.ldc = ldq;
+                Pb.colidx = lidx.p + D.off + p0;
+                const int pi = (int)hp.size();
+                hp.push_back(Pb);
+                for (int m0 = 0; m0 < Pb.M; m0 += BM)
+                    for (int n0 = 0; n0 < Pb.N; n0 += BN) ht.push_back(GemmTile{pi, m0, n0});
+                timers.gemm_flop += 2.0 * Pb.M * (double)Pb.N * Pb.K;
+            }
+        }
+        if (hp.empty()) continue;
+        if (probs.n < hp.size()) probs.alloc(hp.size());
+        if (tiles.n < ht.size()) tiles.alloc(ht.size() + ht.size() / 2);
+        dev_h2d(probs.p, hp.data(), sizeof(GemmProblem) * hp.size(), stream);
+        dev_h2d(tiles.p, ht.data(), sizeof(GemmTile) * ht.size(), stream);
+        pt.begin(T_GEMM, stream);
+#if CUPPEN_CUDA
+        if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, (int)ht.size());
+        else launch_gemm<128, 128, 16, 2, 4, 3>(stream, probs.p, tiles.p, (int)ht.size());
+#else
+        gemm_host(hp.data(), (int)hp.size());
+#endif
+        g_launches.launches++;
+        pt.end(stream);
+        dev_sync(stream);      // hp/ht are host vectors reused per panel; also bounds the event list
+    }
+
+    launch_items(stream, n, ExtractRows{c, Qnext, ldq, R0, R1, frow.p, lrow.p});
+    // blocks that are produced below this level but consumed above it (unbalanced trees only)
+    // must follow into the new buffer
+    for (size_t id = 0; id < plan.nodes.size(); ++id) {
+        const PlanNode& nd = plan.nodes[id];
+        if (nd.off >= R1 || nd.off + nd.n <= R0) continue;
+        const int par = parent_of[id];
+        if (nd.height < h && par >= 0 && plan.nodes[par].height > h) {
+            const int rs = std::max(nd.off, R0), re = std::min(nd.off + nd.n, R1);
+            for (int col = nd.off; col < nd.off + nd.n; ++col)
+                dev_d2d(Qnext + (long)col * ldq + (rs - R0), Qcur + (long)col * ldq + (rs - R0), sizeof(double) * (re - rs), stream);
+        }
+    }
+    std::swap(Qcur, Qnext);
+}
+
+// ---- final ordering, eigenvector gather, residuals -------------------------------------------------
+void Solver::finish() {
+    launch_items(stream, n, FinalRank{n, lam.p, perm.p, lam_sorted.p});
+    h_lam_sorted.resize(n);
+    dev_d2h(h_lam_sorted.data(), lam_sorted.p, sizeof(double) * n, stream);
+    h_resid.clear();
+    if (want_vectors) {
+        pt.begin(T_RESID, stream);
+#if CUPPEN_CUDA
+        {
+            dim3 grid((unsigned)n, (unsigned)std::min(64, (nloc + 255) / 256));
+            gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Qnext, ldq, nloc, perm.p);
+            CUDA_CHECK(cudaGetLastError());
+        }
+#else
+        gather_cols_host(Qcur, Qnext, ldq, nloc, perm.p, n);
+#endif
+        g_launches.launches++;
+        std::swap(Qcur, Qnext);           // Qcur: V with columns in ascending-lambda order
+        if (!(flags & CUPPEN_FLAG_NO_RESIDUALS)) {
+            double* halo_lo = halo.p;
+            double* halo_hi = halo.p + n;
+            if (comm.world > 1) {
+                // first and last local row of every rank -> neighbours' halos
+                launch_items(stream, n, ExtractRowVec{Qcur, ldq, 0, halo.p});
+                launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)nloc - 1, halo.p + n});
+                comm.allgather(halo.p, halo_all.p, sizeof(double) * 2 * n, stream);
+                halo_lo = (comm.rank > 0) ? halo_all.p + (size_t)(comm.rank - 1) * 2 * n + n : halo.p;
+                halo_hi = (comm.rank + 1 < comm.world) ? halo_all.p + (size_t)(comm.rank + 1) * 2 * n : halo.p;
+            }
+#if CUPPEN_CUDA
+            residual_kernel<<<(unsigned)n, 256, 0, stream>>>(Qcur, ldq, n, R0, R1, dOD.p, dOE.p, lam_sorted.p, halo_lo, halo_hi, res2.p);
+            CUDA_CHECK(cudaGetLastError());
+#else
+            residual_host(Qcur, ldq, n, R0, R1, dOD.p, dOE.p, lam_sorted.p, halo_lo, halo_hi, res2.p);
+#endif
+            g_launches.launches++;
+            comm.allreduce_sum(res2.p, n, stream);
+            h_resid.resize(n);
+            dev_d2h(h_resid.data(), res2.p, sizeof(double) * n, stream);
+        }
+        pt.end(stream);
+    }
+    dev_sync(stream);
+    for (double& r : h_resid) r = sqrt(r);
+}
+
+void Solver::solve() {
+    if (!have_matrix) CUPPEN_THROW(CUPPEN_ERR_STATE, "cuppen_set_tridiagonal has not been called");
+    const double t0 = wall_now();
+    const long l0 = g_launches.launches;
+    stats.clear();
+    pt.reset();
+    memset(&timers, 0, sizeof timers);
+    Qcur = Qa.p; Qnext = Qb.p;
+    run_leaves();
+    for (int h = 1; h < (int)plan.by_height.size(); ++h) run_level(h);
+    const double t1 = wall_now();
+    finish();
+    int hfail[4] = {0, 0, 0, 0};
+    dev_d2h(hfail, fail.p, sizeof(int), stream);
+    dev_sync(stream);
+    pt.collect();
+    const double t2 = wall_now();
+    timers.total_s = t1 - t0;
+    timers.root_finding_s = pt.acc[T_ROOT];
+    timers.ev_extract_s = pt.acc[T_EVX] + pt.acc[T_UGEN];
+    timers.backtransform_s = pt.acc[T_PACK] + pt.acc[T_GEMM] + pt.acc[T_UGEN] + (t2 - t1);
+    timers.backtransform_ev_s = pt.acc[T_UGEN];
+    timers.gemm_s = pt.acc[T_GEMM];
+    timers.leaf_s = pt.acc[T_LEAF];
+    timers.deflation_s = pt.acc[T_DEFL];
+    timers.pack_s = pt.acc[T_PACK];
+    timers.residual_s = pt.acc[T_RESID];
+    timers.kernel_launches = g_launches.launches - l0;
+    if (hfail[0] != 0) CUPPEN_THROW(CUPPEN_ERR_CONVERGENCE, "leaf QL iteration did not converge (row %d)", hfail[0] - 1);
+    solved = true;
+}
+
+}  // namespace cuppen
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+using namespace cuppen;
+
+struct cuppen_handle_s {
+    Solver s;
+};
+
+#define CUPPEN_API_BEGIN try {
+#define CUPPEN_API_END                                                     \
+    }                                                                      \
+    catch (const cuppen::Error& e) { g_last_error = e.msg; return e.code; } \
+    catch (const std::bad_alloc&) { g_last_error = "out of host memory"; return CUPPEN_ERR_NOMEM; } \
+    catch (...) { g_last_error = "unknown error"; return CUPPEN_ERR_ARG; }   \
+    return CUPPEN_OK;
+
+static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int device, Comm comm) {
+    CUPPEN_API_BEGIN
+    if (!h || n < 1 || ref_leaves < 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument (n=%d, ref_leaves=%d)", n, ref_leaves);
+    if (n / ref_leaves == 0) CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
+#if CUPPEN_CUDA
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        CUPPEN_THROW(CUPPEN_ERR_CUDA, "no CUDA device available (%s); libcuppen_b200 has no CPU path", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) CUPPEN_THROW(CUPPEN_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CUDA_CHECK(cudaSetDevice(device));
+#endif
+    cuppen_handle_s* hs = new cuppen_handle_s();
+    Solver& s = hs->s;
+    s.n = n; s.P = ref_leaves; s.flags = flags; s.device = device; s.want_vectors = (flags & CUPPEN_FLAG_VECTORS) != 0;
+    s.comm = comm;
+    try {
+#if CUPPEN_CUDA
+        CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+#endif
+        // the tree shape depends only on (n, P): plan with a dummy matrix to size the buffers
+        std::vector<double> D0(n, 1.0), E0(std::max(1, n - 1), 1.0);
+        if (build_plan(s.plan, n, D0.data(), E0.data(), ref_leaves, LEAF_MAX) != 0)
+            CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
+        s.init_layout();
+        s.allocate();
+    } catch (...) { delete hs; throw; }
+    *h = hs;
+    CUPPEN_API_END
+}
+
+extern "C" {
+
+int cuppen_create(cuppen_handle* h, int n, int ref_leaves, int flags, int device) {
+    return create_common(h, n, ref_leaves, flags, device, Comm());
+}
+
+int cuppen_create_callbacks(cuppen_handle* h, int n, int ref_leaves, int flags, int device, int rank, int world,
+                            const cuppen_comm_callbacks* cb) {
+    CUPPEN_API_BEGIN
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !cb)) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad rank/world");
+    Comm c;
+    c.rank = rank; c.world = world;
+    if (cb) { c.cb = *cb; c.use_cb = true; }
+    int rc = create_common(h, n, ref_leaves, flags, device, c);
+    if (rc != 0) return rc;
+    CUPPEN_API_END
+}
+
+int cuppen_nccl_unique_id(unsigned char id[CUPPEN_NCCL_ID_BYTES]) {
+    CUPPEN_API_BEGIN
+    nccl_unique_id(id);
+    CUPPEN_API_END
+}
+
+int cuppen_create_nccl(cuppen_handle* h, int n, int ref_leaves, int flags, int device, int rank, int world,
+                       const unsigned char id[CUPPEN_NCCL_ID_BYTES]) {
+    CUPPEN_API_BEGIN
+    if (world < 1 || rank < 0 || rank >= world) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad rank/world");
+    Comm c;
+    c.rank = rank; c.world = world;
+    if (world > 1) {
+#if CUPPEN_CUDA
+        CUDA_CHECK(cudaSetDevice(device));
+#endif
+        c.init_nccl(id);
+    }
+    int rc = create_common(h, n, ref_leaves, flags, device, c);
+    if (rc != 0) return rc;
+    CUPPEN_API_END
+}
+
+int cuppen_destroy(cuppen_handle h) {
+    CUPPEN_API_BEGIN
+    if (h) {
+        h->s.comm.destroy();
+#if CUPPEN_CUDA
+        if (h->s.stream) cudaStreamDestroy(h->s.stream);
+#endif
+        delete h;
+    }
+    CUPPEN_API_END
+}
+
+int cuppen_set_tridiagonal(cuppen_handle h, const double* D, const double* E) {
+    CUPPEN_API_BEGIN
+    if (!h || !D || (!E && h->s.n > 1)) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(h->s.device));
+#endif
+    h->s.set_matrix(D, E);
+    CUPPEN_API_END
+}
+
+int cuppen_solve(cuppen_handle h) {
+    CUPPEN_API_BEGIN
+    if (!h) CUPPEN_THROW(CUPPEN_ERR_ARG, "null handle");
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(h->s.device));
+#endif
+    h->s.solve();
+    CUPPEN_API_END
+}
+
+int cuppen_resolve(cuppen_handle h) { return cuppen_solve(h); }
+
+int cuppen_get_eigenvalues(cuppen_handle h, double* out) {
+    CUPPEN_API_BEGIN
+    if (!h || !out) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    if (!h->s.solved) CUPPEN_THROW(CUPPEN_ERR_STATE, "not solved");
+    memcpy(out, h->s.h_lam_sorted.data(), sizeof(double) * h->s.n);
+    CUPPEN_API_END
+}
+
+int cuppen_get_residuals(cuppen_handle h, const int* idx, int cnt, double* out) {
+    CUPPEN_API_BEGIN
+    if (!h || !out) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    Solver& s = h->s;
+    if (!s.solved) CUPPEN_THROW(CUPPEN_ERR_STATE, "not solved");
+    if ((int)s.h_resid.size() != s.n) CUPPEN_THROW(CUPPEN_ERR_STATE, "residuals need CUPPEN_FLAG_VECTORS");
+    if (!idx) { memcpy(out, s.h_resid.data(), sizeof(double) * s.n); }
+    else
+        for (int i = 0; i < cnt; ++i) {
+            if (idx[i] < 0 || idx[i] >= s.n) CUPPEN_THROW(CUPPEN_ERR_ARG, "eigenvector index %d out of range", idx[i]);
+            out[i] = s.h_resid[idx[i]];
+        }
+    CUPPEN_API_END
+}
+
+int cuppen_get_merge_stats(cuppen_handle h, cuppen_merge_stat* out, int capacity, int* count) {
+    CUPPEN_API_BEGIN
+    if (!h || !count) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    *count = (int)h->s.stats.size();
+    if (out)
+        for (int i = 0; i < *count && i < capacity; ++i) out[i] = h->s.stats[i];
+    CUPPEN_API_END
+}
+
+int cuppen_get_timers(cuppen_handle h, cuppen_timers* out) {
+    CUPPEN_API_BEGIN
+    if (!h || !out) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    *out = h->s.timers;
+    CUPPEN_API_END
+}
+
+int cuppen_local_rows(cuppen_handle h, int* row0, int* rows) {
+    CUPPEN_API_BEGIN
+    if (!h || !row0 || !rows) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    *row0 = h->s.R0; *rows = h->s.nloc;
+    CUPPEN_API_END
+}
+
+int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld) {
+    CUPPEN_API_BEGIN
+    if (!h || !V) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    Solver& s = h->s;
+    if (!s.solved || !s.want_vectors) CUPPEN_THROW(CUPPEN_ERR_STATE, "no eigenvectors (solve with CUPPEN_FLAG_VECTORS)");
+    if (ld < s.nloc) CUPPEN_THROW(CUPPEN_ERR_ARG, "ld too small");
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(s.device));
+    CUDA_CHECK(cudaMemcpy2DAsync(V, sizeof(double) * ld, s.Qcur, sizeof(double) * s.ldq, sizeof(double) * s.nloc, s.n,
+                                 cudaMemcpyDeviceToHost, s.stream));
+    dev_sync(s.stream);
+#else
+    for (int c = 0; c < s.n; ++c) memcpy(V + (long)c * ld, s.Qcur + (long)c * s.ldq, sizeof(double) * s.nloc);
+#endif
+    CUPPEN_API_END
+}
+
+const char* cuppen_last_error(void) { return g_last_error.c_str(); }
+
+}  // extern "C"
