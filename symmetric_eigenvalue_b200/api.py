@@ -100,7 +100,7 @@ def load_library(path=None):
     p = path or library_path()
     if not os.path.exists(p):
         raise CuppenError(-10, "CUDA library %s is missing: run `make` (there is no CPU fallback)" % p)
-    lib = _declare(ctypes.CDLL(p, mode=ctypes.RTLD_GLOBAL))
+    lib = _declare(ctypes.CDLL(p))
     if path is None:
         _LIB = lib
     return lib

@@ -1,0 +1,125 @@
+"""Parity tests proper: the CUDA path (through the C ABI of libcuppen_b200.so) against the reference's
+golden outputs, the CPU oracle on the same seeded inputs, and size-independent properties at the
+BASELINE sizes.  Tolerances are BASELINE.json's: eigenvalues within 1e-12*||T||, residual and
+orthogonality at or below the reference's, identical deflation counts per merge."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import symmetric_eigenvalue_b200 as se
+from conftest import ROOT, check_against_golden, golden_cases, load_golden, norm_T, ref_stats
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib(product_lib):
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return product_lib
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_matches_reference_goldens(lib, name):
+    g = load_golden(name)
+    vec = bool(np.isfinite(g["resid"]).any())
+    out = se.cuppens(g["D"], g["E"], ref_leaves=g["P"], vectors=vec, lib=lib)
+    check_against_golden(g, out, vec)
+    # the same run with eigenvectors: deflation bookkeeping and eigenvalues must not depend on the mode
+    out2 = se.cuppens(g["D"], g["E"], ref_leaves=g["P"], vectors=not vec, lib=lib)
+    assert np.abs(out2["lam"] - out["lam"]).max() <= 1e-13 * norm_T(g["D"], g["E"])
+    assert ref_stats(out2["stats"]) == ref_stats(out["stats"])
+
+
+@pytest.mark.parametrize("gen,n,P", [("goe", 700, 4), ("rand_u", 512, 8), ("wilk", 600, 4), ("s1", 777, 3), ("s2", 512, 8),
+                                     ("goe", 300, 2), ("s2", 96, 6)])
+def test_against_oracle_seeded(lib, oracle, gen, n, P):
+    D, E = {"goe": oracle.goe, "rand_u": oracle.rand_u, "wilk": lambda k: oracle.wilkinson(k, norm=64.0),
+            "s1": lambda k: oracle.scheme(1, k), "s2": lambda k: oracle.scheme(2, k)}[gen](n)
+    o = oracle.solve(D, E, P, vectors=True)
+    out = se.cuppens(D, E, ref_leaves=P, lib=lib)
+    nT = norm_T(D, E)
+    assert np.abs(out["lam"] - o["lam"]).max() <= 1e-12 * nT
+    assert ref_stats(out["stats"]) == sorted((int(m), int(off), int(zd), int(gv)) for (off, m, zd, gv) in o["stats"].tolist())
+    assert out["resid"].max() <= o["resid"].max() * 1.05 + 4 * 2.2e-16 * nT
+    mine = np.abs(out["V"].T @ out["V"] - np.eye(n)).max()
+    ref = np.abs(o["V"].T @ o["V"] - np.eye(n)).max()
+    assert mine <= max(ref, 1e-13)
+
+
+@pytest.mark.parametrize("gen,n", [("goe", 2048), ("rand_u", 1500), ("wilk", 1001), ("s1", 4096), ("s2", 3000), ("s2", 33), ("s1", 2)])
+def test_accurate_mode_against_lapack(lib, oracle, gen, n):
+    from scipy.linalg import eigvalsh_tridiagonal
+    D, E = {"goe": oracle.goe, "rand_u": oracle.rand_u, "wilk": oracle.wilkinson,
+            "s1": lambda k: oracle.scheme(1, k), "s2": lambda k: oracle.scheme(2, k)}[gen](n)
+    out = se.cuppens(D, E, ref_leaves=1, lib=lib)
+    nT = norm_T(D, E)
+    assert np.abs(out["lam"] - eigvalsh_tridiagonal(D, E)).max() < 3e-14 * nT
+    assert out["resid"].max() < 1e-14 * nT
+    V = out["V"]
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-13
+
+
+def test_baseline_config_properties(lib, oracle):
+    """BASELINE configs[1]: -s 1 -n 4096 with eigenvectors (reference tree P=8): properties that
+    need no oracle -- T V = V Lambda, V^T V = I, trace, ordering."""
+    n = 4096
+    D, E = se.createMatrixScheme1(n, lib=lib)
+    out = se.cuppens(D, E, ref_leaves=8, lib=lib)
+    lam, V = out["lam"], out["V"]
+    assert (np.diff(lam) >= 0).all()
+    assert abs(lam.sum() - D.sum()) < 1e-9 * abs(D.sum())
+    TV = D[:, None] * V
+    TV[1:] += E[:, None] * V[:-1]
+    TV[:-1] += E[:, None] * V[1:]
+    r = np.linalg.norm(TV - V * lam[None, :], axis=0)
+    assert np.allclose(r, out["resid"], rtol=1e-6, atol=1e-12)
+    assert r.max() < 2e-6          # set by the reference's 1e-6 z-deflation (golden: 1.3e-6 at n=1024)
+    assert np.abs(V.T @ V - np.eye(n)).max() < 1e-12
+    g = load_golden("s1_n4096_p8")
+    assert np.abs(lam - g["lam"]).max() <= 1e-12 * norm_T(D, E)
+
+
+def test_cli_drop_in(lib, tmp_path):
+    """The `cuppens` executable: same stdout lines and output file format as the reference
+    (SURVEY.md Appendix B.2 / B.5)."""
+    exe = os.path.join(ROOT, "cuppens")
+    out = tmp_path / "out.txt"
+    r = subprocess.run([exe, "-p", "2", "-i", os.path.join(ROOT, "tests", "golden", "tinyL.mtx"), "-e", str(out)],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    for line in ("Input file: ", "Program will compute all eigenvectors", "Output file: ", "Number of MPI tasks is: 2",
+                 "Start divide phase ...", "Average leaf size will be 2.0", "Apply QR algorithm on leaves ...",
+                 "Start Conquer Phase ...", "Required time to compute all eigenvalues: ", "Required time for root finding: ",
+                 "Required time for eigenvector extraction from U_i's: ", "Write results to file ...",
+                 "Required time for backtransformation: ", "Program finished successfully!"):
+        assert line in r.stdout, line
+    g = load_golden("tinyL_p2")
+    rows = [l.split() for l in out.read_text().splitlines()]
+    assert len(rows) == 4 and all(len(x) == 2 for x in rows)
+    assert np.abs(np.array([float(x[0]) for x in rows]) - g["lam"]).max() <= 4e-12
+    assert max(float(x[1]) for x in rows) <= g["resid"].max() * 1.05 + 4e-15
+    # eigenvalues only, scheme input, -eFILE selection
+    r = subprocess.run([exe, "-p", "4", "-s", "2", "-n", "256", str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Use a matrix of scheme 2 with dimension 256" in r.stdout
+    lam = np.array([float(l) for l in out.read_text().splitlines()])
+    assert np.abs(lam - load_golden("s2_n256_p4")["lam"]).max() <= 4e-12
+    ev = tmp_path / "ev.txt"
+    ev.write_text("1\n3\nfoo\n999\n")
+    r = subprocess.run([exe, "-p", "4", "-s", "2", "-n", "256", "-e" + str(ev), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.count("WARNING: Line") == 2
+    rows = [l.split() for l in out.read_text().splitlines()]
+    assert [len(x) for x in rows[:4]] == [2, 1, 2, 1] and all(len(x) == 1 for x in rows[4:])
+
+
+def test_resolve_is_repeatable(lib, oracle):
+    D, E = oracle.goe(900)
+    s = se.CuppenSolver(900, ref_leaves=4, lib=lib)
+    s.set_tridiagonal(D, E)
+    s.solve()
+    a = s.eigenvalues().copy(); ra = s.residuals().copy()
+    s.solve()
+    assert np.array_equal(a, s.eigenvalues()) and np.array_equal(ra, s.residuals())
+    s.close()

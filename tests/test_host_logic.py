@@ -1,0 +1,165 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every declared symbol, the host
+I/O mirrors the reference, the CLI's option handling / exit codes, and -- through the TEST-ONLY host
+build of the product sources -- the tree planning, deflation bookkeeping and numerics against the
+oracle and the reference's golden outputs."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import symmetric_eigenvalue_b200 as se
+from symmetric_eigenvalue_b200 import api
+from conftest import ROOT, check_against_golden, golden_cases, load_golden, norm_T, ref_stats
+
+
+# ---- the shipped library -----------------------------------------------------------------------------
+def test_library_exports_every_declared_symbol(product_lib):
+    hdr = open(os.path.join(ROOT, "include", "cuppen_b200.h")).read()
+    declared = set(re.findall(r"\b(cuppen_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"cuppen_handle_s"}
+    assert declared == set(api.EXPORTED_SYMBOLS), declared ^ set(api.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(product_lib, name), name
+
+
+def test_no_cpu_fallback_in_product(product_lib):
+    """Without a GPU the product must fail loudly, not compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(se.CuppenError) as ei:
+        se.CuppenSolver(16, lib=product_lib)
+    assert ei.value.code == -10
+    syms = subprocess.run(["nm", "-D", "--defined-only", api.library_path()], capture_output=True, text=True).stdout
+    assert "host_leaf_ql" not in syms and "gemm_host" not in syms and "oracle" not in syms
+
+
+def test_schemes(product_lib):
+    D, E = se.createMatrixScheme1(5, lib=product_lib)
+    assert np.allclose(D, 1 + np.arange(5) * 99 / 4) and (E == -1).all()
+    D, E = se.createMatrixScheme2(5, lib=product_lib)
+    assert (D == 2).all() and (E == -1).all()
+
+
+def test_mtx_reader(product_lib, tmp_path, capfd):
+    p = tmp_path / "t.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate real general\n%c\n3 3 7\n1 1 2\n2 1 -1\n1 2 -1\n2 2 3\n3 2 -4\n2 3 -4\n3 3 5\n")
+    D, E = se.readSymmTriadiagonalMatrixFromSparseMTX(str(p), lib=product_lib)
+    assert D.tolist() == [2, 3, 5] and E.tolist() == [-1, -4]
+    bad = {
+        "%%MatrixMarket matrix coordinate real symmetric\n2 2 1\n1 1 1\n": "does not support",
+        "%MatrixMarket matrix coordinate real general\n2 2 1\n1 1 1\n": "Could not process Matrix Market banner",
+        "%%MatrixMarket matrix coordinate real general\n2 3 1\n1 1 1\n": "Matrix is not square",
+        "%%MatrixMarket matrix coordinate real general\n3 3 1\n1 3 1\n": "Matrix is not tridiagonal",
+        "%%MatrixMarket matrix coordinate real general\n2 2 4\n1 1 1\n2 1 5\n1 2 6\n2 2 1\n": "Matrix is not symmetric",
+        "%%MatrixMarket matrix coordinate real general\n2 2 4\n1 1 1\n1 2 5\n2 1 5\n2 2 1\n": "Matrix is not symmetric",
+    }
+    for text, msg in bad.items():
+        p.write_text(text)
+        with pytest.raises(se.CuppenError) as ei:
+            se.readSymmTriadiagonalMatrixFromSparseMTX(str(p), lib=product_lib)
+        assert ei.value.code == -2
+        assert msg in capfd.readouterr().out
+    with pytest.raises(se.CuppenError):
+        se.readSymmTriadiagonalMatrixFromSparseMTX(str(tmp_path / "missing.mtx"), lib=product_lib)
+
+
+def test_ev_file_and_writer(product_lib, tmp_path, capfd):
+    ev = tmp_path / "ev.txt"
+    ev.write_text("3\n1\nfoo\n9\n1\n")
+    idx = se.determineEigenvectorsToCompute(str(ev), 4, lib=product_lib)
+    assert idx.tolist() == [0, 0, 2]
+    assert capfd.readouterr().out.count("WARNING: Line") == 2
+    out = tmp_path / "o.txt"
+    lam = np.array([0.3819660112501050975, 1.38196601125010532, 2.5, 3.5])
+    res = np.array([2.92423134397388715e-16, 1e-15, 2e-15, 3e-15])
+    se.writeResults(str(out), lam, res, indices=idx, lib=product_lib)
+    lines = out.read_text().splitlines()
+    assert lines[0] == "0.3819660112501050975 2.92423134397388715e-16"
+    assert lines[1] == " 1.38196601125010532"
+    assert len(lines[2].split()) == 2 and len(lines[3].split()) == 1
+    se.writeResults(str(out), lam, lib=product_lib)
+    assert all(len(l.split()) == 1 for l in out.read_text().splitlines())
+
+
+def test_cli_usage_and_exit_codes(product_lib, tmp_path):
+    exe = os.path.join(ROOT, "cuppens")
+    assert os.path.exists(exe)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "USAGE cuppens [options] [outputfile]" in r.stdout
+    r = subprocess.run([exe, "-h"], capture_output=True, text=True)
+    assert r.returncode == 0 and " -e(FILENAME)" in r.stdout
+    for args, msg in ((["-s", "3"], "Invalid argument for option -s. See help."),
+                      (["-n", "0"], "Invalid argument for option -n. See help."),
+                      (["-x"], "Unknown option `-x'."),
+                      (["a", "b"], "Invalid number of positional arguments. See help.")):
+        r = subprocess.run([exe] + args, capture_output=True, text=True)
+        assert r.returncode == 1 and msg in r.stderr, (args, r.returncode, r.stderr)
+    r = subprocess.run([exe, "-i", str(tmp_path / "nope.mtx")], capture_output=True, text=True)
+    assert r.returncode == 2 and "Could not open file" in r.stderr
+    r = subprocess.run([exe, "-p", "8", "-n", "4", "-s", "2"], capture_output=True, text=True)
+    assert r.returncode == 4 and "Leaf Size is too small! Reduce number of tasks." in r.stderr
+
+
+# ---- product sources on the host (TEST-ONLY build): orchestration + numerics vs oracle / goldens -------
+@pytest.mark.parametrize("name", [c for c in golden_cases() if "4096" not in c])
+def test_hostemu_matches_reference_goldens(hostemu, name):
+    g = load_golden(name)
+    vec = bool(np.isfinite(g["resid"]).any())
+    out = se.cuppens(g["D"], g["E"], ref_leaves=g["P"], vectors=vec, lib=hostemu)
+    check_against_golden(g, out, vec)
+
+
+@pytest.mark.parametrize("vectors", [True, False])
+def test_hostemu_eigenvalue_only_mode_agrees(hostemu, oracle, vectors):
+    D, E = oracle.goe(300)
+    a = se.cuppens(D, E, ref_leaves=4, vectors=vectors, lib=hostemu)
+    b = se.cuppens(D, E, ref_leaves=4, vectors=True, lib=hostemu)
+    assert np.abs(a["lam"] - b["lam"]).max() < 1e-14
+    assert ref_stats(a["stats"]) == ref_stats(b["stats"])
+
+
+@pytest.mark.parametrize("gen,n", [("goe", 500), ("rand_u", 333), ("wilkinson", 257), ("s1", 1000), ("s2", 640)])
+def test_hostemu_accurate_mode(hostemu, oracle, gen, n):
+    """ref_leaves=1: LAPACK-grade tolerances on every level (stands in for dsteqr)."""
+    from scipy.linalg import eigvalsh_tridiagonal
+    D, E = {"goe": oracle.goe, "rand_u": oracle.rand_u, "wilkinson": oracle.wilkinson,
+            "s1": lambda k: oracle.scheme(1, k), "s2": lambda k: oracle.scheme(2, k)}[gen](n)
+    out = se.cuppens(D, E, ref_leaves=1, lib=hostemu)
+    nT = norm_T(D, E)
+    assert np.abs(out["lam"] - eigvalsh_tridiagonal(D, E)).max() < 2e-14 * nT
+    assert out["resid"].max() < 5e-15 * nT
+    V = out["V"]
+    assert np.abs(V.T @ V - np.eye(n)).max() < 5e-14
+
+
+def test_hostemu_orthogonality_beats_reference(hostemu, oracle):
+    D, E = oracle.goe(256)
+    o = oracle.solve(D, E, 4, vectors=True)
+    out = se.cuppens(D, E, ref_leaves=4, lib=hostemu)
+    mine = np.abs(out["V"].T @ out["V"] - np.eye(256)).max()
+    ref = np.abs(o["V"].T @ o["V"] - np.eye(256)).max()
+    assert mine <= ref and mine < 1e-13
+    assert out["resid"].max() <= o["resid"].max() * 1.05
+
+
+def test_hostemu_edge_cases(hostemu):
+    out = se.cuppens(np.array([3.0]), np.zeros(0), lib=hostemu)
+    assert out["lam"].tolist() == [3.0]
+    out = se.cuppens(np.array([2.0, 2.0]), np.array([-1.0]), ref_leaves=2, lib=hostemu)
+    assert np.allclose(out["lam"], [1.0, 3.0], atol=1e-14)
+    with pytest.raises(se.CuppenError) as ei:
+        se.CuppenSolver(3, ref_leaves=4, lib=hostemu)
+    assert ei.value.code == -4
+    # zero off-diagonal away from the reference splits is fine (accurate rule), at a reference split it is an error
+    D = np.arange(1.0, 65.0); E = np.ones(63); E[10] = 0.0
+    out = se.cuppens(D, E, ref_leaves=1, lib=hostemu)
+    from scipy.linalg import eigvalsh_tridiagonal
+    assert np.abs(out["lam"] - eigvalsh_tridiagonal(D, E)).max() < 1e-12
+    E = np.ones(63); E[31] = 0.0
+    s = se.CuppenSolver(64, ref_leaves=2, lib=hostemu)
+    with pytest.raises(se.CuppenError) as ei:
+        s.set_tridiagonal(D, E)
+    assert ei.value.code == -3
