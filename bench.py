@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Cuppen hot path (BASELINE.json: eigenpairs wall time and
+FP64 TFLOP/s of the full eigendecomposition of a synthetic symmetric tridiagonal matrix).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA, libcuppen_b200.so)
+  python bench.py --impl reference --steps K --warmup W    the reference's own CPU implementation
+                                                           (oracle/_ref/cuppens_ref, else the oracle port)
+
+A "step" is one complete decomposition (leaves, all merges, back-transformation GEMMs, residuals) of
+the workload: at N=1 BASELINE configs[1] `-s 1 -n 4096 -e` with the reference tree of `mpirun -n 8`;
+at N>1 the same decomposition sharded by eigenvector row blocks (strong scaling).  `--n/--matrix/
+--ref-leaves` select the other BASELINE configurations.  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def make_matrix(kind, n):
+    """Synthetic inputs of BASELINE.json configs (generated here, never read from /root/reference)."""
+    if kind in ("s1", "s2"):
+        D = np.empty(n); E = np.full(max(n - 1, 0), -1.0)
+        if kind == "s1":
+            D[:] = 1.0 + np.arange(n) * ((100.0 - 1.0) / (n - 1))      # helper.c:7-20
+        else:
+            D[:] = 2.0                                                # helper.c:22-33
+        return D, E
+    if kind == "goe":
+        rng = np.random.default_rng(7)
+        d = rng.normal(0.0, np.sqrt(2.0), n)
+        e = np.sqrt(rng.chisquare(np.arange(n - 1, 0, -1)))
+        s = 1.0 / np.sqrt(n)
+        return d * s, e * s
+    if kind == "randu":
+        rng = np.random.default_rng(1234)
+        d = rng.uniform(-1, 1, n); e = rng.uniform(-1, 1, n - 1)
+        d[d == 0] = 0.5; e[e == 0] = 0.5
+        return d, e
+    if kind == "wilk":
+        d = np.abs(np.arange(n) - (n - 1) / 2.0); e = np.ones(n - 1)
+        s = 64.0 / (d.max() + 2.0)
+        return d * s, e * s
+    raise SystemExit("unknown --matrix " + kind)
+
+
+def workload_name(a):
+    flag = {"s1": "-s 1", "s2": "-s 2"}.get(a.matrix, "-i %s(seeded)" % a.matrix)
+    return "cuppens %s -n %d -e (eigenvalues+eigenvectors+residuals), reference tree mpirun -n %d" % (flag, a.n, a.ref_leaves)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+        self.proc = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    import symmetric_eigenvalue_b200 as se
+    from symmetric_eigenvalue_b200 import api
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % a.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local)
+    nccl_id = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        idt = torch.zeros(api.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(se.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    D, E = make_matrix(a.matrix, a.n)
+    solver = se.CuppenSolver(a.n, ref_leaves=a.ref_leaves, vectors=True, device=local, rank=rank, world=world, nccl_id=nccl_id)
+    solver.set_tridiagonal(D, E)                         # inputs resident in HBM before the timed region
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for _ in range(a.warmup):
+        solver.solve()
+    barrier()
+    if sampler:
+        sampler.start()
+    dev_ms, wall_ms, tsum = [], [], None
+    for _ in range(a.steps):
+        flush.zero_()                                    # L2 flush between timed iterations (untimed)
+        barrier()
+        t0 = time.perf_counter()
+        solver.solve()                                   # returns after the stream is drained
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = solver.timers()
+        pair = torch.tensor([t["device_s"] * 1e3, wall], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(pair, op=dist.ReduceOp.MAX)  # max over ranks
+        dev_ms.append(float(pair[0])); wall_ms.append(float(pair[1]))
+        tsum = t if tsum is None else {k: tsum[k] + t[k] for k in t}
+    barrier()
+    clocks = sampler.finish() if sampler else None
+    tavg = {k: v / a.steps for k, v in tsum.items()}
+    lam = solver.eigenvalues(); res = solver.residuals()
+
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    hD = torch.from_numpy(D).pin_memory(); hE = torch.from_numpy(E).pin_memory()
+    e2e = []
+    for it in range(max(2, min(a.steps, 5)) + 1):
+        barrier()
+        t0 = time.perf_counter()
+        solver.set_tridiagonal(hD.numpy(), hE.numpy())
+        solver.solve()
+        out_l = solver.eigenvalues(); out_r = solver.residuals()
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        if it > 0:
+            e2e.append(float(dt[0]))
+    e2e_s = float(np.mean(e2e))
+
+    if rank != 0:
+        solver.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms = float(np.mean(dev_ms))
+    peaks, peak_src = measured_peaks()
+    # dominant kernel class of the step, by CUDA-event time inside the library
+    cats = {"gemm": tavg["gemm_s"], "pack": tavg["pack_s"], "ugen": tavg["backtransform_ev_s"], "secular": tavg["root_finding_s"],
+            "deflation": tavg["deflation_s"], "leaf": tavg["leaf_s"], "residual": tavg["residual_s"]}
+    dom = max(cats, key=cats.get)
+    dmma_tf, dfma_tf = se.api.measure_fp64_peak(local, 200)
+    dgemm_tf = None
+    try:
+        A = torch.randn(8192, 8192, dtype=torch.float64, device="cuda"); B = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+        best = 1e9
+        for _ in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(A, B); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        dgemm_tf = 2 * 8192.0 ** 3 / (best * 1e-3) * 1e-12
+        del A, B
+    except Exception:
+        pass
+    fp64_peak = max(x for x in (dmma_tf, dgemm_tf) if x)
+    gemm_tflops = tavg["gemm_flop"] / tavg["gemm_s"] * 1e-12 if tavg["gemm_s"] > 0 else 0.0
+    if dom in ("gemm", "secular", "deflation", "leaf"):
+        roof = {"kernel": "dgemm_dmma_kernel", "bound": "tensor", "achieved": gemm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": gemm_tflops / fp64_peak if fp64_peak else None, "traffic": None,
+                "peak_source": "measured in this run: DMMA.8x8x4 issue loop %.1f TF/s, cuBLAS Dgemm 8192^3 %s TF/s (no FP64 entry in MEASURED_PEAKS.json)"
+                               % (dmma_tf, "%.1f" % dgemm_tf if dgemm_tf else "n/a"),
+                "dominant_by_time": dom}
+    else:
+        nbytes = tavg["pack_bytes"] if dom == "pack" else tavg["ugen_bytes"] if dom == "ugen" else 8.0 * a.n * a.n
+        sec = cats[dom]
+        ach = nbytes / sec * 1e-9
+        roof = {"kernel": {"pack": "pack_kernel", "ugen": "ugen_kernel", "residual": "residual_kernel"}[dom], "bound": "hbm",
+                "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                "peak_source": peak_src, "dominant_by_time": dom,
+                "gemm": {"achieved_tflops": gemm_tflops, "fp64_peak_tflops": fp64_peak,
+                         "frac": gemm_tflops / fp64_peak if fp64_peak else None}}
+    line = {
+        "metric": "eigenpairs wall-time (s), full eigendecomposition (eigenvalues + eigenvectors + residuals)",
+        "value": ms * 1e-3, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
+        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "n": a.n, "matrix": a.matrix, "ref_leaves": a.ref_leaves,
+                   "l2": "256 MiB buffer zeroed between timed steps (untimed); Q working set 3x%.0f MB" % (8e-6 * a.n * a.n / world),
+                   "sharding": "eigenvector row blocks, %d rank(s)" % world},
+        "wall_ms_per_step": float(np.mean(wall_ms)),
+        "eigenpairs_per_s": a.n / (ms * 1e-3),
+        "tflops_fp64_nominal_4n3_over_3": (4.0 / 3.0) * a.n ** 3 / (ms * 1e-3) * 1e-12,
+        "gemm_tflops_executed": gemm_tflops,
+        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(8 * (4 * a.n - 2)), "d2h_bytes_per_step": int(8 * 2 * a.n)},
+        "gpu_launches": int(tsum["kernel_launches"]),
+        "phase_ms": {k: v * 1e3 for k, v in cats.items()},
+        "roofline": roof,
+        "fp64_yardsticks_tflops": {"dmma_issue_loop": dmma_tf, "dfma_issue_loop": dfma_tf, "cublas_dgemm_8192": dgemm_tf},
+        "clocks": clocks,
+        "check": {"max_residual": float(res.max()), "lambda_min": float(lam[0]), "lambda_max": float(lam[-1])},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(a, bounded_s=25.0)
+    print(json.dumps(line), flush=True)
+    solver.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------------------
+_BT_CACHE = {}
+
+
+def cpu_reference(a, bounded_s=25.0):
+    """The reference's own CPU path on this box's host cores, on a bounded sample of the workload:
+    the complete eigenvalue phase (`cuppens -s .. -n ..`, mpirun -n P x OMP threads) plus the
+    back-transformation of `nvec` sampled eigenvectors (-eFILE), extrapolated to all n vectors
+    (the reference's back-transformation is O(n^3)..O(n^4), SURVEY.md finding 5)."""
+    import oracle
+    cores = os.cpu_count() or 1
+    P = a.ref_leaves
+    T = max(1, cores // P)
+    D, E = make_matrix(a.matrix, a.n)
+    have_ref = os.path.exists(oracle.ref_binary())
+    if not have_ref:
+        t0 = time.perf_counter()
+        oracle.solve(D, E, P, vectors=False, residuals=False)
+        dt = time.perf_counter() - t0
+        return {"value": None, "unit": "s", "cores": cores, "kind": "port", "eigenvalues_only_s": dt,
+                "sample": "oracle port (oracle/cuppen_oracle.c), eigenvalue phase only, OpenMP %d threads" % cores}
+    with tempfile.TemporaryDirectory() as td:
+        mtx = os.path.join(td, "in.mtx")
+        if a.matrix in ("s1", "s2"):
+            args = ["-s", a.matrix[1], "-n", str(a.n)]
+        else:
+            oracle.write_mtx(mtx, D, E)
+            args = ["-i", mtx]
+        out = os.path.join(td, "out.txt")
+        t0 = time.perf_counter()
+        r = oracle.run_reference(args + [out], P=P, threads=T, timeout=3600, stats=False)
+        t_eval_wall = time.perf_counter() - t0
+        txt = r["stdout"]
+        t_eval = _grab(txt, "Required time to compute all eigenvalues:")
+        # sampled eigenvectors: time one, then as many as fit the budget (measured once per process:
+        # later steps of the same run re-time the eigenvalue phase and reuse the per-vector cost)
+        nvec, per_vec, t_bt = 0, None, None
+        budget = max(0.0, bounded_s - t_eval_wall)
+        ev = os.path.join(td, "ev.txt")
+        trial = 1
+        key = (a.matrix, a.n, P)
+        if key in _BT_CACHE:
+            nvec, per_vec = _BT_CACHE[key]
+        while key not in _BT_CACHE:
+            idx = np.unique(np.linspace(1, a.n, trial).astype(int))
+            open(ev, "w").write("".join("%d\n" % i for i in idx))
+            t0 = time.perf_counter()
+            r2 = oracle.run_reference(args + ["-e" + ev, out], P=P, threads=T, timeout=3600, stats=False)
+            dt = time.perf_counter() - t0
+            bt = _grab(r2["stdout"], "Required time for backtransformation:")
+            if bt is not None:
+                nvec, per_vec, t_bt = len(idx), bt / len(idx), bt
+            budget -= dt
+            if per_vec is None or budget < 2 * dt or trial >= 64:
+                if per_vec is not None:
+                    _BT_CACHE[key] = (nvec, per_vec)
+                break
+            trial = min(64, max(trial + 1, int(trial * min(4.0, budget / max(dt, 1e-3) / 2))))
+    value = None if (t_eval is None or per_vec is None) else t_eval + per_vec * a.n
+    return {"value": value, "unit": "s", "cores": P * T, "kind": "reference",
+            "eigenvalue_phase_s": t_eval, "backtransform_s_per_eigenvector": per_vec, "sampled_eigenvectors": nvec,
+            "sample": "unmodified reference (oracle/_ref/cuppens_ref, MPI shim ranks P=%d x OMP_NUM_THREADS=%d): full eigenvalue "
+                      "phase + back-transformation of %d sampled eigenvectors (-eFILE), extrapolated x n=%d" % (P, T, nvec, a.n)}
+
+
+def _grab(txt, key):
+    for line in txt.splitlines():
+        if key in line:
+            try:
+                return float(line.split(key)[1].split()[0])
+            except Exception:
+                return None
+    return None
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, info = [], None
+    for it in range(a.warmup + a.steps):
+        info = cpu_reference(a, bounded_s=a.ref_budget)
+        if it >= a.warmup and info["value"] is not None:
+            vals.append(info["value"])
+    v = float(np.mean(vals)) if vals else None
+    info["value"] = v
+    line = {"impl": "reference",
+            "metric": "eigenpairs wall-time (s), full eigendecomposition (eigenvalues + eigenvectors + residuals)",
+            "value": v, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": None if v is None else v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a), "n": a.n, "matrix": a.matrix, "ref_leaves": a.ref_leaves},
+            "cpu_baseline": info,
+            "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--matrix", default="s1", choices=["s1", "s2", "goe", "randu", "wilk"])
+    ap.add_argument("--ref-leaves", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=25.0, help="seconds of CPU work per reference step")
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference_arm(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -86,6 +86,10 @@ typedef struct {
     double gemm_s;           /* device time of the DMMA GEMM launches */
     double gemm_flop;        /* executed flop: sum 2*M*N*K over GEMM problems */
     double leaf_s, deflation_s, pack_s, residual_s;
+    double device_s;         /* CUDA-event time from the first to the last launch of cuppen_solve */
+    double pack_bytes;       /* algorithmic bytes of pack_kernel: 8*rows*(columns read + columns written) */
+    double ugen_bytes;       /* algorithmic bytes of ugen_kernel: 8*K*N written */
+    double secular_root_iters; /* reserved */
     long   kernel_launches;
 } cuppen_timers;
 
@@ -132,6 +136,10 @@ int cuppen_get_timers(cuppen_handle h, cuppen_timers* out);
 int cuppen_local_rows(cuppen_handle h, int* row0, int* rows);
 int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld);
 const char* cuppen_last_error(void);
+
+/* FP64 yardsticks measured on the device: register-resident DMMA.8x8x4 issue loop and DFMA loop,
+ * TFLOP/s with all SMs busy for ~`ms` milliseconds each (the FP64 peak is not in MEASURED_PEAKS.json). */
+int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* dfma_tflops);
 
 /* ---- host-side helpers of the CLI (no GPU involved) ------------------------------------------- */
 int cuppen_scheme(int scheme, int n, double* D, double* E);

@@ -28,7 +28,8 @@ class _MergeStat(ctypes.Structure):
 class _Timers(ctypes.Structure):
     _fields_ = [(k, ctypes.c_double) for k in (
         "total_s", "root_finding_s", "ev_extract_s", "backtransform_s", "backtransform_ev_s", "gemm_s",
-        "gemm_flop", "leaf_s", "deflation_s", "pack_s", "residual_s")] + [("kernel_launches", ctypes.c_long)]
+        "gemm_flop", "leaf_s", "deflation_s", "pack_s", "residual_s", "device_s", "pack_bytes", "ugen_bytes",
+        "secular_root_iters")] + [("kernel_launches", ctypes.c_long)]
 
 
 _BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
@@ -70,6 +71,7 @@ def _declare(lib):
         "cuppen_get_timers": [H, ctypes.POINTER(_Timers)],
         "cuppen_local_rows": [H, ip, ip],
         "cuppen_copy_eigenvectors": [H, dp, ctypes.c_long],
+        "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_read_mtx": [ctypes.c_char_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ip],
         "cuppen_read_ev_file": [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ip), ip],
@@ -88,7 +90,7 @@ EXPORTED_SYMBOLS = (
     "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_copy_eigenvectors",
-    "cuppen_last_error", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
+    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
 
@@ -120,6 +122,14 @@ def nccl_unique_id(lib=None):
     buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
     _chk(lib, lib.cuppen_nccl_unique_id(buf))
     return buf.raw
+
+
+def measure_fp64_peak(device=0, ms=200, lib=None):
+    """(DMMA TFLOP/s, DFMA TFLOP/s) of register-resident issue loops on `device`."""
+    lib = lib or load_library()
+    a, b = ctypes.c_double(0), ctypes.c_double(0)
+    _chk(lib, lib.cuppen_measure_fp64_peak(device, ms, ctypes.byref(a), ctypes.byref(b)))
+    return a.value, b.value
 
 
 class CuppenSolver:

@@ -41,6 +41,36 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" :: "n"(N)); }
 
+// FP64 yardsticks: register-resident issue loops (no memory traffic)
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double acc[16][2];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j][0] = acc[j][1] = 0.0;
+    const double a = 1e-9 * threadIdx.x, b = 1.0 + 1e-9 * blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) dmma884(acc[j][0], acc[j][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) s += acc[j][0] + acc[j][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 1e-3 * j;
+    const double a = 1.0 + 1e-12 * threadIdx.x, b = 1e-9 * blockIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = fma(acc[j], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) s += acc[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // CTA tile BM x BN x BK, WARPS_M x WARPS_N warps, each warp (BM/WARPS_M) x (BN/WARPS_N).
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 struct DmmaCfg {

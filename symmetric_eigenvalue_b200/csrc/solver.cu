@@ -87,6 +87,10 @@ struct Solver {
     std::vector<cuppen_merge_stat> stats;
     PhaseTimers pt;
     cuppen_timers timers;
+    double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
+#if CUPPEN_CUDA
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+#endif
     // rank layout
     std::vector<int> rank_lo, rank_hi;       // row range per rank
     std::vector<int> parent_of;              // plan node -> parent node id
@@ -372,6 +376,12 @@ void Solver::run_level(int h) {
     }
 
     MatCtx M = mat_ctx();
+    for (int t = 0; t < nd_cnt; ++t) {
+        const MergeDesc& D = hd[t];
+        const double rows = std::min(D.off + D.m, R1) - std::max(D.off, R0);
+        acc_pack_bytes += 8.0 * rows * D.m          // every column of the parent block is written once (Q' or Apack)
+                        + 8.0 * (rows / 2) * D.m;   // every child column is read over its own half
+    }
     pt.begin(T_PACK, stream);
 #if CUPPEN_CUDA
     {
@@ -428,7 +438,8 @@ void Solver::run_level(int h) {
                 hp.push_back(Pb);
                 for (int m0 = 0; m0 < Pb.M; m0 += BM)
                     for (int n0 = 0; n0 < Pb.N; n0 += BN) ht.push_back(GemmTile{pi, m0, n0});
-                timers.gemm_flop += 2.0 * Pb.M * (double)Pb.N * Pb.K;
+                acc_gemm_flop += 2.0 * Pb.M * (double)Pb.N * Pb.K;
+                acc_ugen_bytes += 8.0 * Pb.K * (double)Pb.N;
             }
         }
         if (hp.empty()) continue;
@@ -515,9 +526,14 @@ void Solver::solve() {
     if (!have_matrix) CUPPEN_THROW(CUPPEN_ERR_STATE, "cuppen_set_tridiagonal has not been called");
     const double t0 = wall_now();
     const long l0 = g_launches.launches;
+#if CUPPEN_CUDA
+    if (!ev_begin) { CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end)); }
+    CUDA_CHECK(cudaEventRecord(ev_begin, stream));
+#endif
     stats.clear();
     pt.reset();
     memset(&timers, 0, sizeof timers);
+    acc_pack_bytes = acc_ugen_bytes = acc_gemm_flop = 0;
     Qcur = Qa.p; Qnext = Qb.p;
     run_leaves();
     for (int h = 1; h < (int)plan.by_height.size(); ++h) run_level(h);
@@ -525,6 +541,9 @@ void Solver::solve() {
     finish();
     int hfail[4] = {0, 0, 0, 0};
     dev_d2h(hfail, fail.p, sizeof(int), stream);
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaEventRecord(ev_end, stream));
+#endif
     dev_sync(stream);
     pt.collect();
     const double t2 = wall_now();
@@ -539,6 +558,14 @@ void Solver::solve() {
     timers.pack_s = pt.acc[T_PACK];
     timers.residual_s = pt.acc[T_RESID];
     timers.kernel_launches = g_launches.launches - l0;
+    timers.pack_bytes = acc_pack_bytes;
+    timers.ugen_bytes = acc_ugen_bytes;
+    timers.gemm_flop = acc_gemm_flop;
+#if CUPPEN_CUDA
+    { float ms = 0; cudaEventElapsedTime(&ms, ev_begin, ev_end); timers.device_s = ms * 1e-3; }
+#else
+    timers.device_s = t2 - t0;
+#endif
     if (hfail[0] != 0) CUPPEN_THROW(CUPPEN_ERR_CONVERGENCE, "leaf QL iteration did not converge (row %d)", hfail[0] - 1);
     solved = true;
 }
@@ -732,5 +759,42 @@ int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld) {
 }
 
 const char* cuppen_last_error(void) { return g_last_error.c_str(); }
+
+int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* dfma_tflops) {
+    CUPPEN_API_BEGIN
+#if CUPPEN_CUDA
+    if (!dmma_tflops || !dfma_tflops) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 2, threads = 256;
+    double* out = nullptr;
+    CUDA_CHECK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    for (int which = 0; which < 2; ++which) {
+        int iters = 2000;
+        double best = 0;
+        for (int rep = 0; rep < 6; ++rep) {
+            CUDA_CHECK(cudaEventRecord(a));
+            if (which == 0) dmma_peak_kernel<<<blocks, threads>>>(out, iters);
+            else dfma_peak_kernel<<<blocks, threads>>>(out, iters);
+            CUDA_CHECK(cudaEventRecord(b));
+            CUDA_CHECK(cudaEventSynchronize(b));
+            float t = 0; cudaEventElapsedTime(&t, a, b);
+            const double per_thread_iter = which == 0 ? 16.0 * 512.0 / 32.0 : 32.0 * 2.0;
+            const double fl = (double)blocks * threads * iters * per_thread_iter;
+            best = std::max(best, fl / (t * 1e-3) * 1e-12);
+            if (t < ms && rep < 3) iters = (int)std::min(2.0e8, iters * std::max(2.0, (double)ms / std::max(t, 0.01f)));
+        }
+        *(which == 0 ? dmma_tflops : dfma_tflops) = best;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+#else
+    (void)device; (void)ms; (void)dmma_tflops; (void)dfma_tflops;
+    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
+#endif
+    CUPPEN_API_END
+}
 
 }  // extern "C"
