@@ -8,7 +8,7 @@ FP64 TFLOP/s of the full eigendecomposition of a synthetic symmetric tridiagonal
 
 A "step" is one complete decomposition (leaves, all merges, back-transformation GEMMs, residuals) of
 the workload: at N=1 BASELINE configs[1] `-s 1 -n 4096 -e` with the reference tree of `mpirun -n 8`;
-at N>1 the same decomposition sharded by eigenvector row blocks (strong scaling).  `--n/--matrix/
+at N>1 the same decomposition sharded by eigenvector row blocks (strong scaling).  `--size/--matrix/
 --ref-leaves` select the other BASELINE configurations.  One JSON line is printed by rank 0.
 """
 import argparse
@@ -358,7 +358,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=4096)
+    ap.add_argument("--size", dest="n", type=int, default=4096)
     ap.add_argument("--matrix", default="s1", choices=["s1", "s2", "goe", "randu", "wilk"])
     ap.add_argument("--ref-leaves", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -36,16 +36,6 @@ struct MatCtx {
 
 #if CUPPEN_CUDA
 // ------------------------------------------------------------------------------------------------
-struct WarpLanes {
-    CUPPEN_D int lane() const { return threadIdx.x & 31; }
-    CUPPEN_D int lanes() const { return 32; }
-    CUPPEN_D double sum(double v) const {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    }
-};
-
 // K0: one warp per leaf, lane r owns row r of Q (kept in shared memory), the scalar QL recurrence
 // is executed redundantly by all lanes (no divergence), lane 0 owns the d/e updates.
 __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict__ leaves, int nleaves,

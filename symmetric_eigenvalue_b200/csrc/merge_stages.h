@@ -93,30 +93,37 @@ struct ZAssemble {
     }
 };
 
-// z-deflation flags (+ the accurate rule's tolerance, which needs the maxima of the merge)
+// accurate rule: deflation tolerance 8 eps max(|d|max,|z|max) of every merge (one warp per merge)
+struct MergeTol {
+    LevelCtx c;
+    template <class L>
+    CUPPEN_HD void operator()(long id, const L& lanes) const {
+        MergeDesc& D = c.desc[id];
+        if (D.mode == MODE_REFERENCE) return;
+        double dmax = 0, zmax = 0;
+        const double* dd = c.d + D.off;
+        const double* zz = c.z + D.off;
+        for (int t = lanes.lane(); t < D.m; t += lanes.lanes()) {
+            dmax = fmax(dmax, fabs(dd[t]));
+            zmax = fmax(zmax, fabs(zz[t]));
+        }
+        dmax = lanes.max(dmax);
+        zmax = lanes.max(zmax);
+        if (lanes.lane() == 0) D.tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, zmax);
+    }
+};
+
+// z-deflation flags
 struct FlagDeflate {
     LevelCtx c;
     CUPPEN_HD void operator()(long g) const {
         int id = c.node_of[g];
         if (id < 0) return;
-        MergeDesc& D = c.desc[id];
-        int j = (int)g - D.off;
+        const MergeDesc& D = c.desc[id];
         double zg = c.z[g];
         bool defl;
-        if (D.mode == MODE_REFERENCE) {
-            defl = fabs(zg) < 1e-6;                       // src/eigenvalues.c:72,77
-        } else {
-            double dmax = 0, zmax = 0;
-            const double* dd = c.d + D.off;
-            const double* zz = c.z + D.off;
-            for (int t = 0; t < D.m; ++t) {
-                dmax = fmax(dmax, fabs(dd[t]));
-                zmax = fmax(zmax, fabs(zz[t]));
-            }
-            double tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, zmax);
-            if (j == 0) D.tol = tol;
-            defl = fabs(D.rho) * fabs(zg) <= tol;
-        }
+        if (D.mode == MODE_REFERENCE) defl = fabs(zg) < 1e-6;                       // src/eigenvalues.c:72,77
+        else defl = fabs(D.rho) * fabs(zg) <= D.tol;
         if (defl) {
             c.G[g] = -2;
             c.dn[g] = c.d[g];
@@ -125,10 +132,11 @@ struct FlagDeflate {
     }
 };
 
-// stable enumeration sort of the z-live entries by (d, index)
+// stable enumeration sort of the z-live entries by (d, index); one warp per element
 struct RankLive {
     LevelCtx c;
-    CUPPEN_HD void operator()(long g) const {
+    template <class L>
+    CUPPEN_HD void operator()(long g, const L& lanes) const {
         int id = c.node_of[g];
         if (id < 0) return;
         MergeDesc& D = c.desc[id];
@@ -137,16 +145,19 @@ struct RankLive {
         const int* GG = c.G + D.off;
         double dj = dd[j];
         bool live = GG[j] != -2;
+        if (!live && j != 0) return;
         int cnt = 0, tot = 0;
-        if (live || j == 0) {
-            for (int t = 0; t < D.m; ++t) {
-                if (GG[t] == -2) continue;
-                tot++;
-                if (before(dd[t], t, dj, j)) cnt++;
-            }
+        for (int t = lanes.lane(); t < D.m; t += lanes.lanes()) {
+            if (GG[t] == -2) continue;
+            tot++;
+            if (before(dd[t], t, dj, j)) cnt++;
         }
-        if (live) c.lsort[D.off + cnt] = j;
-        if (j == 0) D.nlive1 = tot;
+        cnt = lanes.isum(cnt);
+        tot = lanes.isum(tot);
+        if (lanes.lane() == 0) {
+            if (live) c.lsort[D.off + cnt] = j;
+            if (j == 0) D.nlive1 = tot;
+        }
     }
 };
 
@@ -219,10 +230,12 @@ struct GivensSweep {
     }
 };
 
-// build the canonical live problem (rho>0, ascending poles) and the per-half K lists
+// build the canonical live problem (rho>0, ascending poles) and the per-half K lists; one warp per
+// position of the z-live sorted list
 struct Compact {
     LevelCtx c;
-    CUPPEN_HD void operator()(long g) const {
+    template <class L>
+    CUPPEN_HD void operator()(long g, const L& lanes) const {
         int id = c.node_of[g];
         if (id < 0) return;
         MergeDesc& D = c.desc[id];
@@ -233,10 +246,13 @@ struct Compact {
         int e = ls[p];
         if (c.G[off + e] != -1) return;
         int cnt = 0, k = 0, tcnt = 0, bcnt = 0, kt = 0, kb = 0;
-        for (int q = 0; q < D.nlive1; ++q) {
+        double sw = 0;
+        for (int q = lanes.lane(); q < D.nlive1; q += lanes.lanes()) {
             int eq = ls[q];
             if (c.G[off + eq] != -1) continue;
             int s = c.sup[off + eq];
+            double zq = c.zn[off + eq];
+            sw += zq * zq;
             k++;
             kt += (s & SUP_TOP) ? 1 : 0;
             kb += (s & SUP_BOT) ? 1 : 0;
@@ -246,6 +262,10 @@ struct Compact {
                 bcnt += (s & SUP_BOT) ? 1 : 0;
             }
         }
+        cnt = lanes.isum(cnt); k = lanes.isum(k); tcnt = lanes.isum(tcnt); bcnt = lanes.isum(bcnt);
+        kt = lanes.isum(kt); kb = lanes.isum(kb);
+        if (cnt == 0) sw = lanes.sum(sw);
+        if (lanes.lane() != 0) return;
         const bool neg = D.rho < 0;
         int ci = neg ? (k - 1 - cnt) : cnt;
         double dv = c.dn[off + e], zv = c.zn[off + e];
@@ -256,21 +276,16 @@ struct Compact {
         int s = c.sup[off + e];
         if (s & SUP_TOP) { c.tpos[off + e] = tcnt; c.toplist[off + tcnt] = ci; }
         if (s & SUP_BOT) { c.bpos[off + e] = bcnt; c.botlist[off + D.n1 + bcnt] = ci; }
-        if (cnt == 0) {
-            double sw = 0;
-            for (int q = 0; q < D.nlive1; ++q) {
-                int eq = ls[q];
-                if (c.G[off + eq] == -1) { double zq = c.zn[off + eq]; sw += zq * zq; }
-            }
-            D.k = k; D.ktop = kt; D.kbot = kb; D.sumw = sw;
-        }
+        if (cnt == 0) { D.k = k; D.ktop = kt; D.kbot = kb; D.sumw = sw; }
     }
 };
 
 // Gu/Eisenstat: z-hat such that the computed roots are the exact eigenvalues of D + rho zhat zhat^T
+// (one warp per pole, the product over the roots is split across the lanes)
 struct Loewner {
     LevelCtx c;
-    CUPPEN_HD void operator()(long g) const {
+    template <class L>
+    CUPPEN_HD void operator()(long g, const L& lanes) const {
         int id = c.node_of[g];
         if (id < 0) return;
         const MergeDesc& D = c.desc[id];
@@ -280,19 +295,21 @@ struct Loewner {
         const double* tau = c.tau + D.off;
         const int* org = c.org + D.off;
         const double dj = dl[j];
-        double prod = (dl[org[j]] - dj) + tau[j];
-        for (int i = 0; i < D.k; ++i) {
+        double prod = 1.0;
+        for (int i = lanes.lane(); i < D.k; i += lanes.lanes()) {
             if (i == j) continue;
             prod *= ((dl[org[i]] - dj) + tau[i]) / (dl[i] - dj);
         }
+        prod = lanes.prod(prod) * ((dl[org[j]] - dj) + tau[j]);
         double zh = sqrt(fabs(prod) / fabs(D.rho));
-        c.zhat[g] = (c.zl[g] < 0) ? -zh : zh;
+        if (lanes.lane() == 0) c.zhat[g] = (c.zl[g] < 0) ? -zh : zh;
     }
 };
 
 struct Norms {
     LevelCtx c;
-    CUPPEN_HD void operator()(long g) const {
+    template <class L>
+    CUPPEN_HD void operator()(long g, const L& lanes) const {
         int id = c.node_of[g];
         if (id < 0) return;
         const MergeDesc& D = c.desc[id];
@@ -302,11 +319,12 @@ struct Norms {
         const double* zh = c.zhat + D.off;
         const double dorg = dl[c.org[g]], t = c.tau[g];
         double s = 0;
-        for (int j = 0; j < D.k; ++j) {
+        for (int j = lanes.lane(); j < D.k; j += lanes.lanes()) {
             double u = zh[j] / ((dl[j] - dorg) - t);
             s += u * u;
         }
-        c.nrm[g] = sqrt(s);
+        s = lanes.sum(s);
+        if (lanes.lane() == 0) c.nrm[g] = sqrt(s);
     }
 };
 
@@ -372,7 +390,8 @@ struct RowPack {
 struct RowGemv {
     LevelCtx c;
     RowCtx r;
-    CUPPEN_HD void operator()(long g) const {
+    template <class L>
+    CUPPEN_HD void operator()(long g, const L& lanes) const {
         int id = c.node_of[g];
         if (id < 0) return;
         const MergeDesc& D = c.desc[id];
@@ -382,16 +401,20 @@ struct RowGemv {
         const double* zh = c.zhat + off;
         const double dorg = dl[c.org[g]], t = c.tau[g], nn = c.nrm[g];
         double sf = 0, sl = 0;
-        for (int q = 0; q < D.ktop; ++q) {
+        for (int q = lanes.lane(); q < D.ktop; q += lanes.lanes()) {
             int j = c.toplist[off + q];
             sf += r.fpack[off + q] * (zh[j] / (((dl[j] - dorg) - t) * nn));
         }
-        for (int q = 0; q < D.kbot; ++q) {
+        for (int q = lanes.lane(); q < D.kbot; q += lanes.lanes()) {
             int j = c.botlist[off + D.n1 + q];
             sl += r.lpack[off + D.n1 + q] * (zh[j] / (((dl[j] - dorg) - t) * nn));
         }
-        r.frow_new[off + c.lidx[g]] = sf;
-        r.lrow_new[off + c.lidx[g]] = sl;
+        sf = lanes.sum(sf);
+        sl = lanes.sum(sl);
+        if (lanes.lane() == 0) {
+            r.frow_new[off + c.lidx[g]] = sf;
+            r.lrow_new[off + c.lidx[g]] = sl;
+        }
     }
 };
 
@@ -419,12 +442,13 @@ struct FinalRank {
     const double* lam;
     int* perm;
     double* lam_sorted;
-    CUPPEN_HD void operator()(long g) const {
+    template <class L>
+    CUPPEN_HD void operator()(long g, const L& lanes) const {
         const double v = lam[g];
         int cnt = 0;
-        for (int j = 0; j < n; ++j) cnt += before(lam[j], j, v, (int)g) ? 1 : 0;
-        perm[cnt] = (int)g;
-        lam_sorted[cnt] = v;
+        for (int j = lanes.lane(); j < n; j += lanes.lanes()) cnt += before(lam[j], j, v, (int)g) ? 1 : 0;
+        cnt = lanes.isum(cnt);
+        if (lanes.lane() == 0) { perm[cnt] = (int)g; lam_sorted[cnt] = v; }
     }
 };
 

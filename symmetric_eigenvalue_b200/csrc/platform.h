@@ -166,6 +166,59 @@ inline void launch_items(Stream s, long n, const F& f) {
     g_launches.launches++;
 }
 
+// ---- one-warp-per-item launcher ------------------------------------------------------------------
+// Functor F: `template <class L> CUPPEN_HD void operator()(long i, const L& lanes) const`; the
+// inner loops stride over lanes.lane()/lanes.lanes() and combine with lanes.sum/isum/max/prod.
+struct SerialLanes {
+    CUPPEN_HD int lane() const { return 0; }
+    CUPPEN_HD int lanes() const { return 1; }
+    CUPPEN_HD double sum(double v) const { return v; }
+    CUPPEN_HD double max(double v) const { return v; }
+    CUPPEN_HD double prod(double v) const { return v; }
+    CUPPEN_HD int isum(int v) const { return v; }
+};
+#if CUPPEN_CUDA
+struct WarpLanes {
+    CUPPEN_D int lane() const { return threadIdx.x & 31; }
+    CUPPEN_D int lanes() const { return 32; }
+    CUPPEN_D double sum(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    CUPPEN_D double max(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        return v;
+    }
+    CUPPEN_D double prod(double v) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    }
+    CUPPEN_D int isum(int v) const { return __reduce_add_sync(0xffffffffu, v); }
+};
+template <class F>
+__global__ void __launch_bounds__(256) per_warp_kernel(long n, F f) {
+    long i = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i < n) f(i, WarpLanes());
+}
+#endif
+
+template <class F>
+inline void launch_warps(Stream s, long n, const F& f) {
+    if (n <= 0) return;
+#if CUPPEN_CUDA
+    long blocks = (n + 7) / 8;
+    per_warp_kernel<F><<<(unsigned)blocks, 256, 0, s>>>(n, f);
+    CUDA_CHECK(cudaGetLastError());
+#else
+    (void)s;
+    for (long i = 0; i < n; ++i) f(i, SerialLanes());
+#endif
+    g_launches.launches++;
+}
+
 static inline long round_up(long a, long b) { return (a + b - 1) / b * b; }
 
 }  // namespace cuppen

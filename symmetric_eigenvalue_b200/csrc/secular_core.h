@@ -15,10 +15,12 @@
 
 #include <math.h>
 
+#ifndef CUPPEN_HD
 #if defined(__CUDACC__)
 #define CUPPEN_HD __host__ __device__ __forceinline__
 #else
 #define CUPPEN_HD inline
+#endif
 #endif
 
 namespace cuppen {
@@ -27,12 +29,14 @@ struct SecularSums {
     double psi, dpsi, phi, dphi, err;
 };
 
-// Lanes policy for the host: one lane, no reduction.
+#ifndef CUPPEN_PLATFORM_H
+// Lanes policy for the host: one lane, no reduction (platform.h has the full version).
 struct SerialLanes {
     CUPPEN_HD int lane() const { return 0; }
     CUPPEN_HD int lanes() const { return 1; }
     CUPPEN_HD double sum(double v) const { return v; }
 };
+#endif
 
 // psi = sum_{j<=split} w_j/(delta_j - tau), phi = sum_{j>split}; derivatives likewise.
 // `skip0`, `skip1` (pole indices or -1) are left out (used for the initial guess).

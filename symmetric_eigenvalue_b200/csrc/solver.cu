@@ -267,12 +267,14 @@ void Solver::run_level(int h) {
     std::vector<MergeDesc> hd(nd_cnt);
     std::vector<int> hnode(n, -1);
     int glo = comm.rank, gcnt = 1;           // rank group of a cooperative node
+    bool any_accurate = false;
     for (int t = 0; t < nd_cnt; ++t) {
         const PlanNode& nd = plan.nodes[ids[t]];
         MergeDesc& D = hd[t];
         memset(&D, 0, sizeof D);
         D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
         D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale;
+        any_accurate = any_accurate || nd.mode == MODE_ACCURATE;
         for (int g = nd.off; g < nd.off + nd.n; ++g) hnode[g] = t;
         if (nd.off < R0 || nd.off + nd.n > R1) {       // spans several ranks
             if (nd_cnt != 1) CUPPEN_THROW(CUPPEN_ERR_STATE, "cooperative node is not alone on its level");
@@ -300,10 +302,11 @@ void Solver::run_level(int h) {
 
     pt.begin(T_DEFL, stream);
     launch_items(stream, n, ZAssemble{c});
+    if (any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
     launch_items(stream, n, FlagDeflate{c});
-    launch_items(stream, n, RankLive{c});
+    launch_warps(stream, n, RankLive{c});
     launch_items(stream, n, GivensSweep{c});
-    launch_items(stream, n, Compact{c});
+    launch_warps(stream, n, Compact{c});
     pt.end(stream);
     dev_d2h(hd.data(), desc.p, sizeof(MergeDesc) * nd_cnt, stream);
     dev_sync(stream);
@@ -353,8 +356,8 @@ void Solver::run_level(int h) {
             }
         }
         pt.begin(T_EVX, stream);
-        launch_items(stream, n, Loewner{c});
-        launch_items(stream, n, Norms{c});
+        launch_warps(stream, n, Loewner{c});
+        launch_warps(stream, n, Norms{c});
         pt.end(stream);
     }
     pt.begin(T_EVX, stream);
@@ -365,7 +368,7 @@ void Solver::run_level(int h) {
         RowCtx r{frow.p, lrow.p, frow2.p, lrow2.p, fpack.p, lpack.p};
         pt.begin(T_EVX, stream);
         launch_items(stream, n, RowPack{c, r});
-        if (maxk > 0) launch_items(stream, n, RowGemv{c, r});
+        if (maxk > 0) launch_warps(stream, n, RowGemv{c, r});
         pt.end(stream);
         // copy the new rows of this level's nodes back (other index ranges keep their values)
         for (int t = 0; t < nd_cnt; ++t) {
@@ -477,7 +480,7 @@ void Solver::run_level(int h) {
 
 // ---- final ordering, eigenvector gather, residuals -------------------------------------------------
 void Solver::finish() {
-    launch_items(stream, n, FinalRank{n, lam.p, perm.p, lam_sorted.p});
+    launch_warps(stream, n, FinalRank{n, lam.p, perm.p, lam_sorted.p});
     h_lam_sorted.resize(n);
     dev_d2h(h_lam_sorted.data(), lam_sorted.p, sizeof(double) * n, stream);
     h_resid.clear();
