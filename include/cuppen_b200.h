@@ -141,6 +141,11 @@ const char* cuppen_last_error(void);
  * TFLOP/s with all SMs busy for ~`ms` milliseconds each (the FP64 peak is not in MEASURED_PEAKS.json). */
 int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* dfma_tflops);
 
+/* GEMM self-test / micro-benchmark of the back-transformation kernels on random data:
+ * variant 0 = cp.async DMMA kernel 128x128, 1 = TMA DMMA kernel 128x128, 2 = cp.async 64x64.
+ * max_abs_err: against an fp64 FMA dot product on 8192 sampled entries; tflops: best of `reps`. */
+int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps, double* max_abs_err, double* tflops);
+
 /* ---- host-side helpers of the CLI (no GPU involved) ------------------------------------------- */
 int cuppen_scheme(int scheme, int n, double* D, double* E);
 int cuppen_read_mtx(const char* filename, double** D, double** E, int* n);   /* callee allocates (malloc) */

@@ -72,6 +72,7 @@ def _declare(lib):
         "cuppen_local_rows": [H, ip, ip],
         "cuppen_copy_eigenvectors": [H, dp, ctypes.c_long],
         "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
+        "cuppen_selftest_gemm": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_read_mtx": [ctypes.c_char_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ip],
         "cuppen_read_ev_file": [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ip), ip],
@@ -90,7 +91,7 @@ EXPORTED_SYMBOLS = (
     "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_copy_eigenvectors",
-    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
+    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_selftest_gemm", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
 
@@ -130,6 +131,14 @@ def measure_fp64_peak(device=0, ms=200, lib=None):
     a, b = ctypes.c_double(0), ctypes.c_double(0)
     _chk(lib, lib.cuppen_measure_fp64_peak(device, ms, ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value
+
+
+def selftest_gemm(variant, M, N, K, reps=3, device=0, lib=None):
+    """(max abs error on sampled entries, TFLOP/s) of one back-transformation GEMM kernel variant."""
+    lib = lib or load_library()
+    e, t = ctypes.c_double(0), ctypes.c_double(0)
+    _chk(lib, lib.cuppen_selftest_gemm(device, variant, M, N, K, reps, ctypes.byref(e), ctypes.byref(t)))
+    return e.value, t.value
 
 
 class CuppenSolver:

@@ -23,6 +23,8 @@ struct GemmProblem {
     const int* colidx;    // N entries
     int M, N, K;
     long lda, ldb, ldc;
+    // coordinates of the same operands inside the Apack / U-arena tensors (TMA version)
+    int a_row0, a_col0, b_row0, b_col0;
 };
 
 struct GemmTile { int prob, m0, n0; };

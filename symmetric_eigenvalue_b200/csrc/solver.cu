@@ -14,6 +14,7 @@
 #include "merge_stages.h"
 #include "matrix_stages.h"
 #include "gemm_dmma.h"
+#include "gemm_tma.h"
 #include "host_twins.h"
 #include "comm.h"
 
@@ -88,8 +89,11 @@ struct Solver {
     PhaseTimers pt;
     cuppen_timers timers;
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
+    int gemm_variant = 1;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA kernel (gemm_tma.h); env CUPPEN_GEMM
+    int num_sms = 148;
 #if CUPPEN_CUDA
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    CUtensorMap mapA, mapB;
 #endif
     // rank layout
     std::vector<int> rank_lo, rank_hi;       // row range per rank
@@ -163,6 +167,16 @@ void Solver::allocate() {
         dev_zero(Qa.p, Qa.bytes(), stream);
         dev_zero(Qb.p, Qb.bytes(), stream);
         probs.alloc(2 * maxdesc + 2);
+#if CUPPEN_CUDA
+        const char* gv = getenv("CUPPEN_GEMM");
+        if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
+        cudaDeviceProp prop;
+        CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+        num_sms = prop.multiProcessorCount;
+        // Apack: ldq rows (contiguous) x (n + K_PAD) columns; U arena: ldb columns (contiguous) x (n + 2 K_PAD) rows
+        mapA = make_tma_map(Apack.p, (uint64_t)ldq, (uint64_t)(N + K_PAD), (uint64_t)ldq);
+        mapB = make_tma_map(B.p, (uint64_t)ldb, (uint64_t)(N + 2 * K_PAD), (uint64_t)ldb);
+#endif
     }
     dev_zero(halo.p, halo.bytes(), stream);
     dev_sync(stream);
@@ -437,6 +451,7 @@ void Solver::run_level(int h) {
                 Pb.B = B.p + (long)hs * ldb; Pb.ldb = ldb;
                 Pb.C = Qnext + (rs - R0) + (long)D.off * ldq; Pb.ldc = ldq;
                 Pb.colidx = lidx.p + D.off + p0;
+                Pb.a_row0 = rs - R0; Pb.a_col0 = D.off; Pb.b_row0 = hs; Pb.b_col0 = 0;
                 const int pi = (int)hp.size();
                 hp.push_back(Pb);
                 for (int m0 = 0; m0 < Pb.M; m0 += BM)
@@ -453,6 +468,7 @@ void Solver::run_level(int h) {
         pt.begin(T_GEMM, stream);
 #if CUPPEN_CUDA
         if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, (int)ht.size());
+        else if (gemm_variant == 1) launch_gemm_tma(stream, mapA, mapB, probs.p, tiles.p, (int)ht.size(), num_sms);
         else launch_gemm<128, 128, 16, 2, 4, 3>(stream, probs.p, tiles.p, (int)ht.size());
 #else
         gemm_host(hp.data(), (int)hp.size());
@@ -762,6 +778,91 @@ int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld) {
 }
 
 const char* cuppen_last_error(void) { return g_last_error.c_str(); }
+
+#if CUPPEN_CUDA
+namespace cuppen {
+__global__ void fill_kernel(double* p, long count, unsigned seed) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long x = (unsigned long long)i * 6364136223846793005ull + seed * 1442695040888963407ull + 1013904223ull;
+    x ^= x >> 29; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 32;
+    p[i] = (double)(x & 0xfffff) / 524288.0 - 1.0;
+}
+__global__ void sample_check_kernel(const GemmProblem P, int samples, double* err) {
+    int sidx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= samples) return;
+    int m = (int)(((unsigned long long)sidx * 2654435761ull) % (unsigned)P.M);
+    int nn = (int)(((unsigned long long)sidx * 40503ull + 17) % (unsigned)P.N);
+    double s = 0;
+    for (int k = 0; k < P.K; ++k) s = fma(P.A[(long)k * P.lda + m], P.B[(long)k * P.ldb + nn], s);
+    double got = P.C[(long)P.colidx[nn] * P.ldc + m];
+    atomicMax((unsigned long long*)err, (unsigned long long)__double_as_longlong(fabs(got - s)));
+}
+__global__ void iota_rev_kernel(int* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = n - 1 - i; }
+}  // namespace cuppen
+#endif
+
+int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps, double* max_abs_err, double* tflops) {
+    CUPPEN_API_BEGIN
+#if CUPPEN_CUDA
+    if (M < 1 || N < 1 || K < 0 || !max_abs_err || !tflops) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    const int row0 = 3;                                      // odd row offset, like the lower half of an odd split
+    const long lda = round_up(M + row0 + 128, 16), ldb = round_up(N, 16) + 16, ldc = lda;
+    const long Kp = round_up(K, K_PAD);
+    DevBuf<double> A, Bm, C, err;
+    DevBuf<int> colidx;
+    DevBuf<GemmProblem> dprob;
+    DevBuf<GemmTile> dtiles;
+    A.alloc((size_t)lda * (Kp + K_PAD + 1) + 4096); Bm.alloc((size_t)ldb * (Kp + 2 * K_PAD + 2) + 4096);
+    C.alloc((size_t)ldc * (N + 1) + 4096); err.alloc(1); colidx.alloc(N);
+    Stream s = 0;
+    fill_kernel<<<(unsigned)((A.n + 255) / 256), 256>>>(A.p, (long)A.n, 1u);
+    fill_kernel<<<(unsigned)((Bm.n + 255) / 256), 256>>>(Bm.p, (long)Bm.n, 2u);
+    // zero the K tail of A (columns K..Kp) as pack_tail_kernel does
+    if (Kp > K) CUDA_CHECK(cudaMemset(A.p + (size_t)K * lda, 0, sizeof(double) * (size_t)(Kp - K) * lda));
+    CUDA_CHECK(cudaMemset(C.p, 0, C.bytes()));
+    CUDA_CHECK(cudaMemset(err.p, 0, sizeof(double)));
+    iota_rev_kernel<<<(N + 255) / 256, 256>>>(colidx.p, N);
+    GemmProblem P;
+    P.A = A.p + row0; P.B = Bm.p; P.C = C.p + row0; P.colidx = colidx.p; P.M = M; P.N = N; P.K = K;
+    P.lda = lda; P.ldb = ldb; P.ldc = ldc; P.a_row0 = row0; P.a_col0 = 0; P.b_row0 = 0; P.b_col0 = 0;
+    std::vector<GemmTile> ht;
+    const int BM = variant == 2 ? 64 : 128, BN = BM;
+    for (int m0 = 0; m0 < M; m0 += BM)
+        for (int n0 = 0; n0 < N; n0 += BN) ht.push_back(GemmTile{0, m0, n0});
+    dprob.alloc(1); dtiles.alloc(ht.size());
+    CUDA_CHECK(cudaMemcpy(dprob.p, &P, sizeof P, cudaMemcpyHostToDevice));
+    CUDA_CHECK(cudaMemcpy(dtiles.p, ht.data(), sizeof(GemmTile) * ht.size(), cudaMemcpyHostToDevice));
+    CUtensorMap mA = make_tma_map(A.p, (uint64_t)lda, (uint64_t)(Kp + K_PAD), (uint64_t)lda);
+    CUtensorMap mB = make_tma_map(Bm.p, (uint64_t)ldb, (uint64_t)(Kp + 2 * K_PAD), (uint64_t)ldb);
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int r = 0; r < std::max(1, reps) + 1; ++r) {
+        CUDA_CHECK(cudaEventRecord(e0, s));
+        if (variant == 1) launch_gemm_tma(s, mA, mB, dprob.p, dtiles.p, (int)ht.size(), prop.multiProcessorCount);
+        else if (variant == 2) launch_gemm<64, 64, 16, 2, 2, 3>(s, dprob.p, dtiles.p, (int)ht.size());
+        else launch_gemm<128, 128, 16, 2, 4, 3>(s, dprob.p, dtiles.p, (int)ht.size());
+        CUDA_CHECK(cudaEventRecord(e1, s));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (r > 0 || reps <= 0) best = std::min(best, ms);
+    }
+    const int samples = 8192;
+    sample_check_kernel<<<(samples + 127) / 128, 128>>>(P, samples, err.p);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(max_abs_err, err.p, sizeof(double), cudaMemcpyDeviceToHost));
+    *tflops = 2.0 * M * (double)N * K / (best * 1e-3) * 1e-12;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+#else
+    (void)device; (void)variant; (void)M; (void)N; (void)K; (void)reps; (void)max_abs_err; (void)tflops;
+    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
+#endif
+    CUPPEN_API_END
+}
 
 int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* dfma_tflops) {
     CUPPEN_API_BEGIN
