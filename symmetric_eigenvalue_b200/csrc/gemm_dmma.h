@@ -101,7 +101,8 @@ __device__ __forceinline__ void gemm_load_stage(double* sA, double* sB, const Ge
 
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 __global__ void __launch_bounds__(WARPS_M * WARPS_N * 32)
-dgemm_dmma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles, int ntiles) {
+dgemm_dmma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles, const int* __restrict__ ntiles_ptr) {
+    const int ntiles = *ntiles_ptr;
     using Cfg = DmmaCfg<BM, BN, BK, WARPS_M, WARPS_N, STAGES>;
     extern __shared__ __align__(16) double gemm_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

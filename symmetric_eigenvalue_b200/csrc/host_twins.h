@@ -7,7 +7,6 @@
 
 #include <algorithm>
 #include "matrix_stages.h"
-#include "gemm_dmma.h"
 
 namespace cuppen {
 
@@ -161,17 +160,38 @@ inline void ugen_host(LevelCtx c, MatCtx M, int p0, int width) {
     }
 }
 
-inline void gemm_host(const GemmProblem* probs, int nprobs) {
-    for (int p = 0; p < nprobs; ++p) {
-        const GemmProblem& P = probs[p];
+inline void build_gemm_work_host(WorkCtx w) {
+    int run = 0, mis = 0;
+    for (int p = 0; p < 2 * w.nd; ++p) {
+        GemmProblem Pb;
+        work_fill_problem(w, p, Pb);
+        w.probs[p] = Pb;
+        if (Pb.M == 0) continue;
+        if (Pb.a_row0 & 1) mis++;
+        for (int m0 = 0; m0 < Pb.M; m0 += w.BM)
+            for (int n0 = 0; n0 < Pb.N; n0 += w.BN) {
+                if (run < w.tile_cap) w.tiles[run] = GemmTile{p, m0, n0};
+                ++run;
+            }
+    }
+    w.ntiles[0] = run < w.tile_cap ? run : w.tile_cap;
+    w.ntiles[1] = mis;
+}
+
+// consumes the same (problem, tile) list as the device kernels
+inline void gemm_host(const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, int BM, int BN) {
+    for (int t = 0; t < ntiles_ptr[0]; ++t) {
+        const GemmProblem& P = probs[tiles[t].prob];
+        const int m0 = tiles[t].m0, n0 = tiles[t].n0;
+        const int m1 = std::min(P.M, m0 + BM), n1 = std::min(P.N, n0 + BN);
         const int Kpad = (P.K + K_PAD - 1) / K_PAD * K_PAD;     // read the padded K like the device kernel
-        for (int nn = 0; nn < P.N; ++nn) {
+        for (int nn = n0; nn < n1; ++nn) {
             double* ccol = P.C + (long)P.colidx[nn] * P.ldc;
-            for (int mm = 0; mm < P.M; ++mm) ccol[mm] = 0.0;
+            for (int mm = m0; mm < m1; ++mm) ccol[mm] = 0.0;
             for (int kk = 0; kk < Kpad; ++kk) {
                 const double b = P.B[(long)kk * P.ldb + nn];
                 const double* acol = P.A + (long)kk * P.lda;
-                for (int mm = 0; mm < P.M; ++mm) ccol[mm] += acol[mm] * b;
+                for (int mm = m0; mm < m1; ++mm) ccol[mm] += acol[mm] * b;
             }
         }
     }

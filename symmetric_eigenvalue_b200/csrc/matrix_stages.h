@@ -15,6 +15,7 @@
 
 #include "merge_stages.h"
 #include "secular_core.h"
+#include "gemm_dmma.h"
 
 namespace cuppen {
 
@@ -33,6 +34,80 @@ struct MatCtx {
     double* B;            // U arena, row-major [n + pad][ldb]
     long ldb;
 };
+
+// GEMM work list of one level and one panel, built on the device from the merge descriptors so that
+// the host never has to read the deflation counts back between the stages of a level.
+struct WorkCtx {
+    const MergeDesc* desc;
+    int nd;                 // merges of this level
+    int p0, width;          // panel of root columns [p0, p0+width)
+    int BM, BN;             // CTA tile of the GEMM kernel that will consume the list
+    int R0, R1;
+    long ldq, ldb;
+    double* Apack;
+    double* B;
+    double* Qnext;
+    const int* lidx;
+    GemmProblem* probs;     // [2*nd]
+    GemmTile* tiles;
+    int* ntiles;            // [0] tile count, [1] number of problems whose lines are not 16-byte aligned
+    int tile_cap;
+};
+
+CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
+    const MergeDesc& D = w.desc[p >> 1];
+    const int half = p & 1;
+    Pb.M = 0; Pb.N = 0; Pb.K = 0;
+    if (D.k <= w.p0) return 0;
+    const int hs = half ? D.off + D.n1 : D.off;
+    const int he = half ? D.off + D.m : D.off + D.n1;
+    const int rs = hs > w.R0 ? hs : w.R0, re = he < w.R1 ? he : w.R1;
+    if (re <= rs) return 0;
+    Pb.M = re - rs;
+    Pb.N = (D.k - w.p0) < w.width ? (D.k - w.p0) : w.width;
+    Pb.K = half ? D.kbot : D.ktop;
+    Pb.A = w.Apack + (rs - w.R0) + (long)D.off * w.ldq; Pb.lda = w.ldq;
+    Pb.B = w.B + (long)hs * w.ldb; Pb.ldb = w.ldb;
+    Pb.C = w.Qnext + (rs - w.R0) + (long)D.off * w.ldq; Pb.ldc = w.ldq;
+    Pb.colidx = w.lidx + D.off + w.p0;
+    Pb.a_row0 = rs - w.R0; Pb.a_col0 = D.off; Pb.b_row0 = hs; Pb.b_col0 = 0;
+    return ((Pb.M + w.BM - 1) / w.BM) * ((Pb.N + w.BN - 1) / w.BN);
+}
+
+#if CUPPEN_CUDA
+// one block; shared memory: 2*nd ints (tile offsets)
+__global__ void __launch_bounds__(256) build_gemm_work_kernel(WorkCtx w) {
+    extern __shared__ int work_off[];
+    __shared__ int misaligned;
+    const int np = 2 * w.nd;
+    if (threadIdx.x == 0) misaligned = 0;
+    __syncthreads();
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        GemmProblem Pb;
+        work_off[p] = work_fill_problem(w, p, Pb);
+        w.probs[p] = Pb;
+        if (Pb.M > 0 && (Pb.a_row0 & 1)) atomicAdd(&misaligned, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int p = 0; p < np; ++p) { int c = work_off[p]; work_off[p] = run; run += c; }
+        w.ntiles[0] = run < w.tile_cap ? run : w.tile_cap;
+        w.ntiles[1] = misaligned;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+        const GemmProblem Pb = w.probs[p];
+        if (Pb.M == 0) continue;
+        int t = work_off[p];
+        for (int m0 = 0; m0 < Pb.M; m0 += w.BM)
+            for (int n0 = 0; n0 < Pb.N; n0 += w.BN) {
+                if (t < w.tile_cap) w.tiles[t] = GemmTile{p, m0, n0};
+                ++t;
+            }
+    }
+}
+#endif
 
 #if CUPPEN_CUDA
 // ------------------------------------------------------------------------------------------------

@@ -82,6 +82,10 @@ struct ZAssemble {
         if (id < 0) return;
         const MergeDesc& D = c.desc[id];
         int j = (int)g - D.off;
+        if (j == 0) {       // device-written fields of the descriptor start from zero on every solve
+            MergeDesc& W = c.desc[id];
+            W.nlive1 = 0; W.k = 0; W.ktop = 0; W.kbot = 0; W.sumw = 0.0;
+        }
         c.d[g] = c.lam[g];
         double zv = (j < D.n1) ? c.lrow[g] : c.frow[g] / D.theta;
         c.z[g] = zv * D.zscale;
@@ -415,6 +419,19 @@ struct RowGemv {
             r.frow_new[off + c.lidx[g]] = sf;
             r.lrow_new[off + c.lidx[g]] = sl;
         }
+    }
+};
+
+// copy the new boundary rows of this level's nodes over the old ones (other index ranges keep theirs)
+struct RowCommit {
+    LevelCtx c;
+    RowCtx r;
+    double* frow;
+    double* lrow;
+    CUPPEN_HD void operator()(long g) const {
+        if (c.node_of[g] < 0) return;
+        frow[g] = r.frow_new[g];
+        lrow[g] = r.lrow_new[g];
     }
 };
 

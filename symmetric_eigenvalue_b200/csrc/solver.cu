@@ -93,11 +93,25 @@ struct Solver {
     int num_sms = 148;
 #if CUPPEN_CUDA
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
-    CUtensorMap mapA, mapB;
 #endif
     // rank layout
     std::vector<int> rank_lo, rank_hi;       // row range per rank
     std::vector<int> parent_of;              // plan node -> parent node id
+    // per-level data prepared once per matrix (descriptors and index maps live on the device)
+    struct LevelInfo {
+        std::vector<int> ids;                // plan nodes of this height that touch my rows
+        size_t desc_off = 0;                 // offset into desc_all
+        int maxm = 0, maxm_rows = 0;
+        int glo = 0, gcnt = 1;               // rank group of a cooperative node
+        bool any_accurate = false, aligned = true;
+        long worst_tiles_big = 0, worst_tiles_small = 0;
+    };
+    std::vector<LevelInfo> levels;
+    std::vector<MergeDesc> h_desc_all;
+    DevBuf<MergeDesc> desc_all;
+    DevBuf<int> node_of_all;                 // [levels][n]
+    DevBuf<int> ntiles_dev;
+    void prepare_levels();
 
     void init_layout();
     void allocate();
@@ -106,7 +120,7 @@ struct Solver {
     void run_leaves();
     void run_level(int h);
     void finish();
-    LevelCtx level_ctx();
+    LevelCtx level_ctx(int h);
     MatCtx mat_ctx();
 };
 
@@ -148,9 +162,6 @@ void Solver::allocate() {
     fail.alloc(4);
     halo.alloc(2 * N + 64);
     halo_all.alloc(2 * N * (size_t)comm.world + 64);
-    size_t maxdesc = 1;
-    for (auto& v : plan.by_height) maxdesc = std::max(maxdesc, v.size());
-    desc.alloc(maxdesc);
     leaves.alloc(std::max<size_t>(1, plan.leaves.size()));
     if (want_vectors) {
         const size_t qelems = (size_t)ldq * (N + K_PAD + 2) + 4096;
@@ -166,16 +177,12 @@ void Solver::allocate() {
         dev_zero(Apack.p, Apack.bytes(), stream);
         dev_zero(Qa.p, Qa.bytes(), stream);
         dev_zero(Qb.p, Qb.bytes(), stream);
-        probs.alloc(2 * maxdesc + 2);
 #if CUPPEN_CUDA
         const char* gv = getenv("CUPPEN_GEMM");
         if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         num_sms = prop.multiProcessorCount;
-        // Apack: ldq rows (contiguous) x (n + K_PAD) columns; U arena: ldb columns (contiguous) x (n + 2 K_PAD) rows
-        mapA = make_tma_map(Apack.p, (uint64_t)ldq, (uint64_t)(N + K_PAD), (uint64_t)ldq);
-        mapB = make_tma_map(B.p, (uint64_t)ldb, (uint64_t)(N + 2 * K_PAD), (uint64_t)ldb);
 #endif
     }
     dev_zero(halo.p, halo.bytes(), stream);
@@ -199,6 +206,7 @@ void Solver::set_matrix(const double* D, const double* E) {
     for (const PlanNode& nd : plan.nodes)
         if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.rho == 0.0)
             CUPPEN_THROW(CUPPEN_ERR_ZERO, "zero off-diagonal entry at a reference split (row %d)", nd.off + nd.n1);
+    prepare_levels();
     dev_h2d(dDm.p, plan.D.data(), sizeof(double) * n, stream);
     dev_h2d(dOD.p, hD.data(), sizeof(double) * n, stream);
     if (n > 1) {
@@ -210,9 +218,9 @@ void Solver::set_matrix(const double* D, const double* E) {
     solved = false;
 }
 
-LevelCtx Solver::level_ctx() {
+LevelCtx Solver::level_ctx(int h) {
     LevelCtx c;
-    c.n = n; c.desc = desc.p; c.node_of = node_of.p; c.lam = lam.p; c.frow = frow.p; c.lrow = lrow.p;
+    c.n = n; c.desc = desc_all.p + levels[h].desc_off; c.node_of = node_of_all.p + (size_t)h * n; c.lam = lam.p; c.frow = frow.p; c.lrow = lrow.p;
     c.d = d.p; c.z = z.p; c.dn = dn.p; c.zn = zn.p; c.G = G.p; c.gc = gc.p; c.gs = gs.p; c.lsort = lsort.p;
     c.head = head.p; c.sup = sup.p; c.tpos = tpos.p; c.bpos = bpos.p; c.dl = dl.p; c.wl = wl.p; c.zl = zl.p;
     c.lidx = lidx.p; c.org = org.p; c.tau = tau.p; c.zhat = zhat.p; c.nrm = nrm.p; c.toplist = toplist.p;
@@ -252,7 +260,7 @@ void Solver::run_leaves() {
 
 // ---- one tree level ---------------------------------------------------------------------------------
 template <int BM, int BN, int BK, int WMs, int WNs, int STAGES>
-static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tiles, int ntiles) {
+static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, long grid_want) {
 #if CUPPEN_CUDA
     using Cfg = DmmaCfg<BM, BN, BK, WMs, WNs, STAGES>;
     auto kern = dgemm_dmma_kernel<BM, BN, BK, WMs, WNs, STAGES>;
@@ -261,47 +269,82 @@ static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tile
         CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
         attr_set = true;
     }
-    int grid = std::min(ntiles, 148 * 8);
-    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(probs, tiles, ntiles);
+    int grid = (int)std::max<long>(1, grid_want);
+    kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(probs, tiles, ntiles_ptr);
     CUDA_CHECK(cudaGetLastError());
 #else
-    (void)s; (void)probs; (void)tiles; (void)ntiles;
+    (void)s; (void)probs; (void)tiles; (void)ntiles_ptr; (void)grid_want;
 #endif
 }
 
-void Solver::run_level(int h) {
-    // nodes of this height that intersect my rows
-    std::vector<int> ids;
-    for (int id : plan.by_height[h]) {
-        const PlanNode& nd = plan.nodes[id];
-        if (nd.off < R1 && nd.off + nd.n > R0) ids.push_back(id);
-    }
-    if (ids.empty()) return;
-    const int nd_cnt = (int)ids.size();
-    std::vector<MergeDesc> hd(nd_cnt);
-    std::vector<int> hnode(n, -1);
-    int glo = comm.rank, gcnt = 1;           // rank group of a cooperative node
-    bool any_accurate = false;
-    for (int t = 0; t < nd_cnt; ++t) {
-        const PlanNode& nd = plan.nodes[ids[t]];
-        MergeDesc& D = hd[t];
-        memset(&D, 0, sizeof D);
-        D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
-        D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale;
-        any_accurate = any_accurate || nd.mode == MODE_ACCURATE;
-        for (int g = nd.off; g < nd.off + nd.n; ++g) hnode[g] = t;
-        if (nd.off < R0 || nd.off + nd.n > R1) {       // spans several ranks
-            if (nd_cnt != 1) CUPPEN_THROW(CUPPEN_ERR_STATE, "cooperative node is not alone on its level");
-            glo = 0;
-            while (rank_lo[glo] < nd.off) ++glo;
-            int ghi = glo;
-            while (ghi < comm.world && rank_hi[ghi] <= nd.off + nd.n) ++ghi;
-            gcnt = ghi - glo;
+void Solver::prepare_levels() {
+    const int H = (int)plan.by_height.size();
+    levels.assign(H, LevelInfo());
+    h_desc_all.clear();
+    std::vector<int> hnode((size_t)std::max(H, 1) * n, -1);
+    for (int h = 1; h < H; ++h) {
+        LevelInfo& L = levels[h];
+        L.desc_off = h_desc_all.size();
+        L.glo = comm.rank; L.gcnt = 1;
+        for (int id : plan.by_height[h]) {
+            const PlanNode& nd = plan.nodes[id];
+            if (nd.off < R1 && nd.off + nd.n > R0) L.ids.push_back(id);
+        }
+        for (size_t t = 0; t < L.ids.size(); ++t) {
+            const PlanNode& nd = plan.nodes[L.ids[t]];
+            MergeDesc D;
+            memset(&D, 0, sizeof D);
+            D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
+            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale;
+            h_desc_all.push_back(D);
+            L.any_accurate = L.any_accurate || nd.mode == MODE_ACCURATE;
+            for (int g = nd.off; g < nd.off + nd.n; ++g) hnode[(size_t)h * n + g] = (int)t;
+            L.maxm = std::max(L.maxm, nd.n);
+            L.maxm_rows = std::max(L.maxm_rows, std::min(nd.off + nd.n, R1) - std::max(nd.off, R0));
+            for (int half = 0; half < 2; ++half) {
+                const int hs = half ? nd.off + nd.n1 : nd.off, he = half ? nd.off + nd.n : nd.off + nd.n1;
+                const int rs = std::max(hs, R0), re = std::min(he, R1);
+                if (re <= rs) continue;
+                if ((rs - R0) & 1) L.aligned = false;
+                const long N = std::min(W > 0 ? W : nd.n, nd.n);
+                L.worst_tiles_big += (long)((re - rs + 127) / 128) * ((N + 127) / 128);
+                L.worst_tiles_small += (long)((re - rs + 63) / 64) * ((N + 63) / 64);
+            }
+            if (nd.off < R0 || nd.off + nd.n > R1) {       // spans several ranks
+                if (L.ids.size() != 1) CUPPEN_THROW(CUPPEN_ERR_STATE, "cooperative node is not alone on its level");
+                int glo = 0;
+                while (rank_lo[glo] < nd.off) ++glo;
+                int ghi = glo;
+                while (ghi < comm.world && rank_hi[ghi] <= nd.off + nd.n) ++ghi;
+                L.glo = glo; L.gcnt = ghi - glo;
+            }
         }
     }
-    dev_h2d(desc.p, hd.data(), sizeof(MergeDesc) * nd_cnt, stream);
-    dev_h2d(node_of.p, hnode.data(), sizeof(int) * n, stream);
-    LevelCtx c = level_ctx();
+    if (desc_all.n < h_desc_all.size() + 1) desc_all.alloc(h_desc_all.size() + 1);
+    if (node_of_all.n < hnode.size()) node_of_all.alloc(hnode.size());
+    if (!h_desc_all.empty()) dev_h2d(desc_all.p, h_desc_all.data(), sizeof(MergeDesc) * h_desc_all.size(), stream);
+    dev_h2d(node_of_all.p, hnode.data(), sizeof(int) * hnode.size(), stream);
+    if (want_vectors) {
+        long worst_t = 1;
+        size_t worst_p = 2;
+        for (const LevelInfo& L : levels) {
+            worst_t = std::max(worst_t, std::max(L.worst_tiles_big, L.worst_tiles_small));
+            worst_p = std::max(worst_p, 2 * L.ids.size());
+        }
+        if (tiles.n < (size_t)worst_t) tiles.alloc((size_t)worst_t);
+        if (probs.n < worst_p) probs.alloc(worst_p);
+    }
+    if (ntiles_dev.n < 4) ntiles_dev.alloc(4);
+    dev_sync(stream);
+}
+
+void Solver::run_level(int h) {
+    const LevelInfo& L = levels[h];
+    if (L.ids.empty()) return;
+    const int nd_cnt = (int)L.ids.size();
+    const int glo = L.glo, gcnt = L.gcnt;
+    MergeDesc* hd = h_desc_all.data() + L.desc_off;      // host mirror (device-written fields valid after a read-back)
+    LevelCtx c = level_ctx(h);
 
     if (gcnt > 1) {
         // children's eigenvalues and boundary rows from their owners (src/main.c:501-517,530-542)
@@ -316,65 +359,52 @@ void Solver::run_level(int h) {
 
     pt.begin(T_DEFL, stream);
     launch_items(stream, n, ZAssemble{c});
-    if (any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
+    if (L.any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
     launch_items(stream, n, FlagDeflate{c});
     launch_warps(stream, n, RankLive{c});
     launch_items(stream, n, GivensSweep{c});
     launch_warps(stream, n, Compact{c});
     pt.end(stream);
-    dev_d2h(hd.data(), desc.p, sizeof(MergeDesc) * nd_cnt, stream);
-    dev_sync(stream);
 
-    int maxk = 0, maxm_rows = 0;
-    for (int t = 0; t < nd_cnt; ++t) {
-        const MergeDesc& D = hd[t];
-        maxk = std::max(maxk, D.k);
-        maxm_rows = std::max(maxm_rows, std::min(D.off + D.m, R1) - std::max(D.off, R0));
-        cuppen_merge_stat st;
-        st.offset = D.off; st.m = D.m; st.n1 = D.n1; st.mode = D.mode; st.zdefl = D.m - D.nlive1;
-        st.givens = D.nlive1 - D.k; st.k = D.k; st.height = h; st.rho = plan.nodes[ids[t]].beta * plan.nodes[ids[t]].theta;
-        stats.push_back(st);
-    }
-
-    if (maxk > 0) {
-        pt.begin(T_ROOT, stream);
-        const int part = comm.rank - glo;
-        const int per = (maxk + gcnt - 1) / gcnt;
+    // secular roots: worst-case grid, the kernel reads the live count k of every merge on the device
+    pt.begin(T_ROOT, stream);
+    const int part = comm.rank - glo;
+    const int per = (L.maxm + gcnt - 1) / gcnt;
 #if CUPPEN_CUDA
-        {
-            int kcap = std::min((int)round_up(maxk, 32), (int)SEC_SMEM_K);
-            size_t smem = (size_t)2 * kcap * sizeof(double);
-            static bool attr_set = false;
-            if (!attr_set) {
-                CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)(2 * SEC_SMEM_K * sizeof(double))));
-                attr_set = true;
-            }
-            dim3 grid((unsigned)((per + SEC_WARPS - 1) / SEC_WARPS), (unsigned)nd_cnt);
-            secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, gcnt);
-            CUDA_CHECK(cudaGetLastError());
+    {
+        int kcap = std::min((int)round_up(L.maxm, 32), (int)SEC_SMEM_K);
+        size_t smem = (size_t)2 * kcap * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(2 * SEC_SMEM_K * sizeof(double))));
+            attr_set = true;
         }
+        dim3 grid((unsigned)((per + SEC_WARPS - 1) / SEC_WARPS), (unsigned)nd_cnt);
+        secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, gcnt);
+        CUDA_CHECK(cudaGetLastError());
+    }
 #else
-        secular_host(c, nd_cnt, part, gcnt);
+    secular_host(c, nd_cnt, part, gcnt);
 #endif
-        g_launches.launches++;
-        pt.end(stream);
-        if (gcnt > 1) {
-            const MergeDesc& D = hd[0];
-            const int per1 = (D.k + gcnt - 1) / gcnt;
-            for (int r = 0; r < gcnt; ++r) {
-                int i0 = r * per1, i1 = std::min(D.k, i0 + per1);
-                if (i1 <= i0) continue;
-                comm.group_bcast(tau.p + D.off + i0, sizeof(double) * (i1 - i0), glo + r, glo, gcnt, stream);
-                comm.group_bcast(org.p + D.off + i0, sizeof(int) * (i1 - i0), glo + r, glo, gcnt, stream);
-            }
+    g_launches.launches++;
+    pt.end(stream);
+    if (gcnt > 1) {
+        // root slices -> everybody in the group; the slice sizes need k on the host (one small read-back)
+        dev_d2h(hd, desc_all.p + L.desc_off, sizeof(MergeDesc), stream);
+        dev_sync(stream);
+        const MergeDesc& D = hd[0];
+        const int per1 = (D.k + gcnt - 1) / gcnt;
+        for (int r = 0; r < gcnt; ++r) {
+            int i0 = r * per1, i1 = std::min(D.k, i0 + per1);
+            if (i1 <= i0) continue;
+            comm.group_bcast(tau.p + D.off + i0, sizeof(double) * (i1 - i0), glo + r, glo, gcnt, stream);
+            comm.group_bcast(org.p + D.off + i0, sizeof(int) * (i1 - i0), glo + r, glo, gcnt, stream);
         }
-        pt.begin(T_EVX, stream);
-        launch_warps(stream, n, Loewner{c});
-        launch_warps(stream, n, Norms{c});
-        pt.end(stream);
     }
     pt.begin(T_EVX, stream);
+    launch_warps(stream, n, Loewner{c});
+    launch_warps(stream, n, Norms{c});
     launch_items(stream, n, NewLambda{c});
     pt.end(stream);
 
@@ -382,30 +412,20 @@ void Solver::run_level(int h) {
         RowCtx r{frow.p, lrow.p, frow2.p, lrow2.p, fpack.p, lpack.p};
         pt.begin(T_EVX, stream);
         launch_items(stream, n, RowPack{c, r});
-        if (maxk > 0) launch_warps(stream, n, RowGemv{c, r});
+        launch_warps(stream, n, RowGemv{c, r});
+        launch_items(stream, n, RowCommit{c, r, frow.p, lrow.p});
         pt.end(stream);
-        // copy the new rows of this level's nodes back (other index ranges keep their values)
-        for (int t = 0; t < nd_cnt; ++t) {
-            dev_d2d(frow.p + hd[t].off, frow2.p + hd[t].off, sizeof(double) * hd[t].m, stream);
-            dev_d2d(lrow.p + hd[t].off, lrow2.p + hd[t].off, sizeof(double) * hd[t].m, stream);
-        }
         return;
     }
 
     MatCtx M = mat_ctx();
-    for (int t = 0; t < nd_cnt; ++t) {
-        const MergeDesc& D = hd[t];
-        const double rows = std::min(D.off + D.m, R1) - std::max(D.off, R0);
-        acc_pack_bytes += 8.0 * rows * D.m          // every column of the parent block is written once (Q' or Apack)
-                        + 8.0 * (rows / 2) * D.m;   // every child column is read over its own half
-    }
     pt.begin(T_PACK, stream);
 #if CUPPEN_CUDA
     {
-        dim3 grid((unsigned)n, (unsigned)((maxm_rows + PACK_THREADS * PACK_ROWS - 1) / (PACK_THREADS * PACK_ROWS)));
+        dim3 grid((unsigned)n, (unsigned)((L.maxm_rows + PACK_THREADS * PACK_ROWS - 1) / (PACK_THREADS * PACK_ROWS)));
         pack_kernel<<<grid, PACK_THREADS, 0, stream>>>(c, M);
         CUDA_CHECK(cudaGetLastError());
-        dim3 grid2((unsigned)nd_cnt, (unsigned)((maxm_rows + 127) / 128));
+        dim3 grid2((unsigned)nd_cnt, (unsigned)((L.maxm_rows + 127) / 128));
         pack_tail_kernel<<<grid2, 128, 0, stream>>>(c, M);
         CUDA_CHECK(cudaGetLastError());
     }
@@ -416,10 +436,12 @@ void Solver::run_level(int h) {
     g_launches.launches += 2;
     pt.end(stream);
 
-    // panels of W root columns: U generation, then one GEMM launch over all (merge, half) problems
-    const bool small_tiles = (maxm_rows <= 256);
-    for (int p0 = 0; p0 < maxk; p0 += W) {
-        const int width = std::min(W, maxk - p0);
+    // panels of W root columns: U generation, device-built work list, one GEMM launch over all
+    // (merge, half) problems of the level
+    const bool small_tiles = (L.maxm_rows <= 256);
+    const int BMN = small_tiles ? 64 : 128;
+    for (int p0 = 0; p0 < L.maxm; p0 += W) {
+        const int width = std::min(W, L.maxm - p0);
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
         {
@@ -433,49 +455,26 @@ void Solver::run_level(int h) {
         g_launches.launches++;
         pt.end(stream);
 
-        std::vector<GemmProblem> hp;
-        std::vector<GemmTile> ht;
-        const int BM = small_tiles ? 64 : 128, BN = small_tiles ? 64 : 128;
-        for (int t = 0; t < nd_cnt; ++t) {
-            const MergeDesc& D = hd[t];
-            if (D.k <= p0) continue;
-            const int N = std::min(width, D.k - p0);
-            for (int half = 0; half < 2; ++half) {
-                const int hs = half ? D.off + D.n1 : D.off;             // first global row of the half
-                const int he = half ? D.off + D.m : D.off + D.n1;
-                const int rs = std::max(hs, R0), re = std::min(he, R1);
-                if (re <= rs) continue;
-                GemmProblem Pb;
-                Pb.M = re - rs; Pb.N = N; Pb.K = half ? D.kbot : D.ktop;
-                Pb.A = Apack.p + (rs - R0) + (long)D.off * ldq; Pb.lda = ldq;
-                Pb.B = B.p + (long)hs * ldb; Pb.ldb = ldb;
-                Pb.C = Qnext + (rs - R0) + (long)D.off * ldq; Pb.ldc = ldq;
-                Pb.colidx = lidx.p + D.off + p0;
-                Pb.a_row0 = rs - R0; Pb.a_col0 = D.off; Pb.b_row0 = hs; Pb.b_col0 = 0;
-                const int pi = (int)hp.size();
-                hp.push_back(Pb);
-                for (int m0 = 0; m0 < Pb.M; m0 += BM)
-                    for (int n0 = 0; n0 < Pb.N; n0 += BN) ht.push_back(GemmTile{pi, m0, n0});
-                acc_gemm_flop += 2.0 * Pb.M * (double)Pb.N * Pb.K;
-                acc_ugen_bytes += 8.0 * Pb.K * (double)Pb.N;
-            }
-        }
-        if (hp.empty()) continue;
-        if (probs.n < hp.size()) probs.alloc(hp.size());
-        if (tiles.n < ht.size()) tiles.alloc(ht.size() + ht.size() / 2);
-        dev_h2d(probs.p, hp.data(), sizeof(GemmProblem) * hp.size(), stream);
-        dev_h2d(tiles.p, ht.data(), sizeof(GemmTile) * ht.size(), stream);
+        WorkCtx w;
+        w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN; w.R0 = R0; w.R1 = R1;
+        w.ldq = ldq; w.ldb = ldb; w.Apack = Apack.p; w.B = B.p; w.Qnext = Qnext; w.lidx = lidx.p;
+        w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
+        const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
         pt.begin(T_GEMM, stream);
 #if CUPPEN_CUDA
-        if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, (int)ht.size());
-        else if (gemm_variant == 1) launch_gemm_tma(stream, mapA, mapB, probs.p, tiles.p, (int)ht.size(), num_sms);
-        else launch_gemm<128, 128, 16, 2, 4, 3>(stream, probs.p, tiles.p, (int)ht.size());
+        build_gemm_work_kernel<<<1, 256, sizeof(int) * 2 * nd_cnt, stream>>>(w);
+        CUDA_CHECK(cudaGetLastError());
+        const int grid = (int)std::min<long>(worst, small_tiles ? num_sms * 8L : (long)num_sms);
+        if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, ntiles_dev.p, grid);
+        else if (gemm_variant == 1 && L.aligned) launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid);
+        else launch_gemm<128, 128, 16, 2, 4, 3>(stream, probs.p, tiles.p, ntiles_dev.p, std::min<long>(worst, num_sms * 2L));
 #else
-        gemm_host(hp.data(), (int)hp.size());
+        (void)worst;
+        build_gemm_work_host(w);
+        gemm_host(probs.p, tiles.p, ntiles_dev.p, BMN, BMN);
 #endif
-        g_launches.launches++;
+        g_launches.launches += 2;
         pt.end(stream);
-        dev_sync(stream);      // hp/ht are host vectors reused per panel; also bounds the event list
     }
 
     launch_items(stream, n, ExtractRows{c, Qnext, ldq, R0, R1, frow.p, lrow.p});
@@ -487,8 +486,14 @@ void Solver::run_level(int h) {
         const int par = parent_of[id];
         if (nd.height < h && par >= 0 && plan.nodes[par].height > h) {
             const int rs = std::max(nd.off, R0), re = std::min(nd.off + nd.n, R1);
+#if CUPPEN_CUDA
+            CUDA_CHECK(cudaMemcpy2DAsync(Qnext + (long)nd.off * ldq + (rs - R0), sizeof(double) * ldq,
+                                         Qcur + (long)nd.off * ldq + (rs - R0), sizeof(double) * ldq,
+                                         sizeof(double) * (re - rs), nd.n, cudaMemcpyDeviceToDevice, stream));
+#else
             for (int col = nd.off; col < nd.off + nd.n; ++col)
                 dev_d2d(Qnext + (long)col * ldq + (rs - R0), Qcur + (long)col * ldq + (rs - R0), sizeof(double) * (re - rs), stream);
+#endif
         }
     }
     std::swap(Qcur, Qnext);
@@ -556,6 +561,7 @@ void Solver::solve() {
     Qcur = Qa.p; Qnext = Qb.p;
     run_leaves();
     for (int h = 1; h < (int)plan.by_height.size(); ++h) run_level(h);
+    if (!h_desc_all.empty()) dev_d2h(h_desc_all.data(), desc_all.p, sizeof(MergeDesc) * h_desc_all.size(), stream);
     const double t1 = wall_now();
     finish();
     int hfail[4] = {0, 0, 0, 0};
@@ -566,6 +572,26 @@ void Solver::solve() {
     dev_sync(stream);
     pt.collect();
     const double t2 = wall_now();
+    // per-merge records and executed work, from the descriptors the device filled in
+    for (int h = 1; h < (int)levels.size(); ++h)
+        for (size_t t = 0; t < levels[h].ids.size(); ++t) {
+            const MergeDesc& D = h_desc_all[levels[h].desc_off + t];
+            const PlanNode& nd = plan.nodes[levels[h].ids[t]];
+            cuppen_merge_stat st;
+            st.offset = D.off; st.m = D.m; st.n1 = D.n1; st.mode = D.mode; st.zdefl = D.m - D.nlive1;
+            st.givens = D.nlive1 - D.k; st.k = D.k; st.height = h; st.rho = nd.beta * nd.theta;
+            stats.push_back(st);
+            if (!want_vectors) continue;
+            const double rows = std::min(D.off + D.m, R1) - std::max(D.off, R0);
+            acc_pack_bytes += 8.0 * rows * D.m + 8.0 * (rows / 2) * D.m;
+            for (int half = 0; half < 2; ++half) {
+                const int hs = half ? D.off + D.n1 : D.off, he = half ? D.off + D.m : D.off + D.n1;
+                const double mr = std::max(0, std::min(he, R1) - std::max(hs, R0));
+                const double kh = half ? D.kbot : D.ktop;
+                acc_gemm_flop += 2.0 * mr * D.k * kh;
+                acc_ugen_bytes += 8.0 * kh * D.k;
+            }
+        }
     timers.total_s = t1 - t0;
     timers.root_finding_s = pt.acc[T_ROOT];
     timers.ev_extract_s = pt.acc[T_EVX] + pt.acc[T_UGEN];
@@ -584,6 +610,9 @@ void Solver::solve() {
     { float ms = 0; cudaEventElapsedTime(&ms, ev_begin, ev_end); timers.device_s = ms * 1e-3; }
 #else
     timers.device_s = t2 - t0;
+#endif
+#if CUPPEN_CUDA
+    if (want_vectors && gemm_variant == 1) tma_check_abort();
 #endif
     if (hfail[0] != 0) CUPPEN_THROW(CUPPEN_ERR_CONVERGENCE, "leaf QL iteration did not converge (row %d)", hfail[0] - 1);
     solved = true;
@@ -809,7 +838,7 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    const int row0 = 3;                                      // odd row offset, like the lower half of an odd split
+    const int row0 = (variant == 1) ? 2 : 3;                 // odd row offset (cp.async kernels), even for the 16-byte bulk-copy lines
     const long lda = round_up(M + row0 + 128, 16), ldb = round_up(N, 16) + 16, ldc = lda;
     const long Kp = round_up(K, K_PAD);
     DevBuf<double> A, Bm, C, err;
@@ -836,21 +865,25 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     dprob.alloc(1); dtiles.alloc(ht.size());
     CUDA_CHECK(cudaMemcpy(dprob.p, &P, sizeof P, cudaMemcpyHostToDevice));
     CUDA_CHECK(cudaMemcpy(dtiles.p, ht.data(), sizeof(GemmTile) * ht.size(), cudaMemcpyHostToDevice));
-    CUtensorMap mA = make_tma_map(A.p, (uint64_t)lda, (uint64_t)(Kp + K_PAD), (uint64_t)lda);
-    CUtensorMap mB = make_tma_map(Bm.p, (uint64_t)ldb, (uint64_t)(Kp + 2 * K_PAD), (uint64_t)ldb);
+    DevBuf<int> dnt;
+    dnt.alloc(4);
+    int hnt[4] = {(int)ht.size(), 0, 0, 0};
+    CUDA_CHECK(cudaMemcpy(dnt.p, hnt, sizeof hnt, cudaMemcpyHostToDevice));
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     float best = 1e30f;
     for (int r = 0; r < std::max(1, reps) + 1; ++r) {
         CUDA_CHECK(cudaEventRecord(e0, s));
-        if (variant == 1) launch_gemm_tma(s, mA, mB, dprob.p, dtiles.p, (int)ht.size(), prop.multiProcessorCount);
-        else if (variant == 2) launch_gemm<64, 64, 16, 2, 2, 3>(s, dprob.p, dtiles.p, (int)ht.size());
-        else launch_gemm<128, 128, 16, 2, 4, 3>(s, dprob.p, dtiles.p, (int)ht.size());
+        const long nt = (long)ht.size();
+        if (variant == 1) launch_gemm_tma(s, dprob.p, dtiles.p, dnt.p, (int)std::min<long>(nt, prop.multiProcessorCount));
+        else if (variant == 2) launch_gemm<64, 64, 16, 2, 2, 3>(s, dprob.p, dtiles.p, dnt.p, std::min<long>(nt, prop.multiProcessorCount * 8L));
+        else launch_gemm<128, 128, 16, 2, 4, 3>(s, dprob.p, dtiles.p, dnt.p, std::min<long>(nt, prop.multiProcessorCount * 2L));
         CUDA_CHECK(cudaEventRecord(e1, s));
         CUDA_CHECK(cudaEventSynchronize(e1));
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
         if (r > 0 || reps <= 0) best = std::min(best, ms);
     }
+    tma_check_abort();
     const int samples = 8192;
     sample_check_kernel<<<(samples + 127) / 128, 128>>>(P, samples, err.p);
     CUDA_CHECK(cudaDeviceSynchronize());

@@ -126,7 +126,7 @@ def test_resolve_is_repeatable(lib, oracle):
 
 
 @pytest.mark.parametrize("variant", [0, 1, 2])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (1, 1, 1), (300, 200, 70), (77, 129, 0), (1000, 1203, 513), (2048, 1024, 2048)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (1, 1, 1), (300, 200, 70), (77, 129, 0), (1000, 1203, 513), (130, 4000, 33), (2048, 1024, 2048)])
 def test_gemm_kernels_against_fma_reference(lib, variant, M, N, K):
     """The three back-transformation GEMM kernels (cp.async 128x128, TMA 128x128, cp.async 64x64) on random
     data with an odd row offset, ragged M/N/K and scattered output columns; fp64 tolerance: K * 4 ulp."""
