@@ -111,8 +111,10 @@ __global__ void __launch_bounds__(256) build_gemm_work_kernel(WorkCtx w) {
 
 #if CUPPEN_CUDA
 // ------------------------------------------------------------------------------------------------
-// K0: one warp per leaf, lane r owns row r of Q (kept in shared memory), the scalar QL recurrence
-// is executed redundantly by all lanes (no divergence), lane 0 owns the d/e updates.
+// K0: one warp per leaf, lane r owns row r of Q (kept in shared memory).  The scalar QL recurrence
+// is executed redundantly by all lanes and every lane stores the identical d/e values, so the warp
+// needs no synchronisation inside a sweep; the next pole pair is prefetched ahead of the dependent
+// sqrt/divide chain.  The leaf is scaled by a power of two first so that f*f+g*g cannot overflow.
 __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict__ leaves, int nleaves,
                                                       const double* __restrict__ Dm, const double* __restrict__ E,
                                                       double* __restrict__ lam, double* __restrict__ frow,
@@ -129,13 +131,22 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
     double* d = sd[w];
     double* e = se[w];
     for (int c = 0; c < nl; ++c) q[lane][c] = (lane == c) ? 1.0 : 0.0;
-    if (lane < nl) d[lane] = Dm[off + lane];
-    if (lane < nl) e[lane] = (lane < nl - 1) ? E[off + lane] : 0.0;
+    double dv = (lane < nl) ? Dm[off + lane] : 0.0;
+    double ev = (lane < nl - 1) ? E[off + lane] : 0.0;
+    double mx = fmax(fabs(dv), fabs(ev));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int ex = 0;
+    if (mx > 0.0) frexp(mx, &ex);
+    const double scl = ldexp(1.0, -ex), unscl = ldexp(1.0, ex);
+    if (lane < nl) d[lane] = dv * scl;
+    if (lane < nl) e[lane] = ev * scl;
     __syncwarp();
     const double eps = 2.220446049250313e-16;
     for (int l = 0; l < nl; ++l) {
         int iter = 0, m;
         do {
+            __syncwarp();      // all lanes have finished the previous sweep before anybody rescans d/e
             for (m = l; m < nl - 1; ++m) {
                 double dd = fabs(d[m]) + fabs(d[m + 1]);
                 if (fabs(e[m]) <= eps * dd) break;
@@ -146,37 +157,36 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
                 double r = sqrt(g * g + 1.0);
                 g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? r : -r));
                 double s = 1.0, c = 1.0, p = 0.0;
-                int i;
+                double ei = e[m - 1], di = d[m - 1], dip1 = d[m];
+                __syncwarp();  // the shift above read d/e: no lane may start storing before all have read
                 bool early = false;
-                for (i = m - 1; i >= l; --i) {
-                    double f = s * e[i];
-                    double b = c * e[i];
-                    r = hypot(f, g);
-                    __syncwarp();
-                    if (lane == 0) e[i + 1] = r;
-                    if (r == 0.0) {
-                        if (lane == 0) { d[i + 1] -= p; e[m] = 0.0; }
+                for (int i = m - 1; i >= l; --i) {
+                    const double e_nx = (i > l) ? e[i - 1] : 0.0, d_nx = (i > l) ? d[i - 1] : 0.0;
+                    const double f = s * ei, b = c * ei;
+                    const double h2 = f * f + g * g;
+                    if (h2 == 0.0) {
+                        e[i + 1] = 0.0;
+                        d[i + 1] = dip1 - p;
+                        e[m] = 0.0;
                         early = true;
                         break;
                     }
-                    s = f / r;
-                    c = g / r;
-                    g = d[i + 1] - p;
-                    r = (d[i] - g) * s + 2.0 * c * b;
+                    r = sqrt(h2);
+                    const double rinv = 1.0 / r;
+                    e[i + 1] = r;
+                    s = f * rinv;
+                    c = g * rinv;
+                    g = dip1 - p;
+                    r = (di - g) * s + 2.0 * c * b;
                     p = s * r;
-                    __syncwarp();
-                    if (lane == 0) d[i + 1] = g + p;
+                    d[i + 1] = g + p;
                     g = c * r - b;
-                    double f2 = q[lane][i + 1];
-                    double q0 = q[lane][i];
+                    const double f2 = q[lane][i + 1], q0 = q[lane][i];
                     q[lane][i + 1] = s * q0 + c * f2;
                     q[lane][i] = c * q0 - s * f2;
+                    dip1 = di; di = d_nx; ei = e_nx;
                 }
-                __syncwarp();
-                if (!early) {
-                    if (lane == 0) { d[l] -= p; e[l] = g; e[m] = 0.0; }
-                }
-                __syncwarp();
+                if (!early) { d[l] = dip1 - p; e[l] = g; e[m] = 0.0; }   // dip1 holds the old d[l] here
             }
         } while (m != l);
     }
@@ -185,16 +195,18 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
     for (int i = 0; i < nl - 1; ++i) {
         int kmin = i;
         double p = d[i];
+        const double di0 = p;
         for (int k2 = i + 1; k2 < nl; ++k2) if (d[k2] < p) { kmin = k2; p = d[k2]; }
         __syncwarp();
         if (kmin != i) {
-            if (lane == 0) { d[kmin] = d[i]; d[i] = p; }
+            d[kmin] = di0; d[i] = p;
             double t = q[lane][i]; q[lane][i] = q[lane][kmin]; q[lane][kmin] = t;
         }
         __syncwarp();
     }
+    __syncwarp();
     if (lane < nl) {
-        lam[off + lane] = d[lane];
+        lam[off + lane] = d[lane] * unscl;
         frow[off + lane] = q[0][lane];
         lrow[off + lane] = q[nl - 1][lane];
     }
