@@ -8,7 +8,7 @@ CSRC     := symmetric_eigenvalue_b200/csrc
 LIBDIR   := symmetric_eigenvalue_b200/lib
 LIB      := $(LIBDIR)/libcuppen_b200.so
 OBJ_NAME := cuppens
-NVFLAGS  := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC \
+NVFLAGS  := --extended-lambda -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC \
             -Xcompiler -Wall -Xcompiler -Wno-unused-function --expt-relaxed-constexpr
 HDRS     := $(wildcard $(CSRC)/*.h) include/cuppen_b200.h
 

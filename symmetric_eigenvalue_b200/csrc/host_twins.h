@@ -168,11 +168,9 @@ inline void build_gemm_work_host(WorkCtx w) {
         w.probs[p] = Pb;
         if (Pb.M == 0) continue;
         if (Pb.a_row0 & 1) mis++;
-        for (int m0 = 0; m0 < Pb.M; m0 += w.BM)
-            for (int n0 = 0; n0 < Pb.N; n0 += w.BN) {
-                if (run < w.tile_cap) w.tiles[run] = GemmTile{p, m0, n0};
-                ++run;
-            }
+        GemmTile* tl = w.tiles;
+        work_emit_tiles(w, Pb, p, run, [tl](int t, GemmTile T) { tl[t] = T; });
+        run += ((Pb.M + w.BM - 1) / w.BM) * ((Pb.N + w.BN - 1) / w.BN);
     }
     w.ntiles[0] = run < w.tile_cap ? run : w.tile_cap;
     w.ntiles[1] = mis;

@@ -54,6 +54,27 @@ struct WorkCtx {
     int tile_cap;
 };
 
+// Tile order of one problem: super-columns of `nsw` n-tiles whose B panel (K x nsw*BN doubles) fits
+// in a third of the 126 MB L2, all m-tiles inside a super-column, n fastest -- so B is read from
+// DRAM once and A once per super-column instead of B once per m-tile.
+CUPPEN_HD int work_supercol(const WorkCtx& w, const GemmProblem& Pb) {
+    const int ntn = (Pb.N + w.BN - 1) / w.BN;
+    long nsw = (48L << 20) / ((long)(Pb.K > 0 ? Pb.K : 1) * 8 * w.BN);
+    if (nsw < 1) nsw = 1;
+    return nsw < ntn ? (int)nsw : ntn;
+}
+template <class Emit>
+CUPPEN_HD void work_emit_tiles(const WorkCtx& w, const GemmProblem& Pb, int p, int t, Emit emit) {
+    const int ntm = (Pb.M + w.BM - 1) / w.BM, ntn = (Pb.N + w.BN - 1) / w.BN;
+    const int nsw = work_supercol(w, Pb);
+    for (int ns = 0; ns < ntn; ns += nsw)
+        for (int mt = 0; mt < ntm; ++mt)
+            for (int nt = ns; nt < ns + nsw && nt < ntn; ++nt) {
+                if (t < w.tile_cap) emit(t, GemmTile{p, mt * w.BM, nt * w.BN});
+                ++t;
+            }
+}
+
 CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
     const MergeDesc& D = w.desc[p >> 1];
     const int half = p & 1;
@@ -99,12 +120,8 @@ __global__ void __launch_bounds__(256) build_gemm_work_kernel(WorkCtx w) {
     for (int p = threadIdx.x; p < np; p += blockDim.x) {
         const GemmProblem Pb = w.probs[p];
         if (Pb.M == 0) continue;
-        int t = work_off[p];
-        for (int m0 = 0; m0 < Pb.M; m0 += w.BM)
-            for (int n0 = 0; n0 < Pb.N; n0 += w.BN) {
-                if (t < w.tile_cap) w.tiles[t] = GemmTile{p, m0, n0};
-                ++t;
-            }
+        GemmTile* tl = w.tiles;
+        work_emit_tiles(w, Pb, p, work_off[p], [tl](int t, GemmTile T) { tl[t] = T; });
     }
 }
 #endif
