@@ -311,7 +311,8 @@ __global__ void __launch_bounds__(128) pack_tail_kernel(LevelCtx c, MatCtx M) {
 }
 
 // K5b: B[row = arena row of pole j][col = root i - p0] = zhat_j / (((d_j - d_org(i)) - tau_i) N_i)
-// grid.x = arena row (global index), grid.y = column chunk of 256.
+// grid.x = arena row (global index), grid.y = a few column lanes; a block strides over the 256-wide
+// column chunks of its row (the live count k is only known on the device).
 __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width) {
     const int row = blockIdx.x;
     const int id = c.node_of[row];
@@ -321,19 +322,22 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
     const int jj = row - (top ? D.off : D.off + D.n1);
     const int kh = top ? D.ktop : D.kbot;
     if (jj >= kh) return;
-    const int i = p0 + blockIdx.y * 256 + threadIdx.x;
-    if (i >= D.k || i >= p0 + width) return;
+    const int iend = min(D.k, p0 + width);
     const int j = top ? c.toplist[row] : c.botlist[row];
     const double* dl = c.dl + D.off;
     const double dj = dl[j], zj = c.zhat[D.off + j];
-    double den = ((dj - dl[c.org[D.off + i]]) - c.tau[D.off + i]) * c.nrm[D.off + i];
-    if (den == 0.0) den = 4.9e-324;
-    double v = zj / den;
-    if (!(fabs(v) < 1.7e308)) v = (v > 0) ? 1.7e308 : -1.7e308;
-    M.B[(long)row * M.ldb + (i - p0)] = v;
+    double* out = M.B + (long)row * M.ldb - p0;
+    for (int i = p0 + blockIdx.y * 256 + threadIdx.x; i < iend; i += gridDim.y * 256) {
+        double den = ((dj - dl[c.org[D.off + i]]) - c.tau[D.off + i]) * c.nrm[D.off + i];
+        if (den == 0.0) den = 4.9e-324;
+        double v = zj / den;
+        if (!(fabs(v) < 1.7e308)) v = (v > 0) ? 1.7e308 : -1.7e308;
+        out[i] = v;
+    }
 }
 
-// K8: one block per output column; V holds the columns already in ascending-lambda order
+// K8: one block per output column; V holds the columns already in ascending-lambda order.
+// Four independent rows per thread and iteration keep enough loads in flight to stream from HBM.
 __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ V, long ldq, int n, int R0, int R1,
                                                        const double* __restrict__ OD, const double* __restrict__ OE,
                                                        const double* __restrict__ lam_sorted,
@@ -343,12 +347,24 @@ __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict_
     const double* x = V + (long)col * ldq;
     const double lambda = lam_sorted[col];
     double acc = 0;
-    for (int r = R0 + threadIdx.x; r < R1; r += blockDim.x) {
-        const double xc = x[r - R0];
-        double y = OD[r] * xc - lambda * xc;
-        if (r > 0) y += OE[r - 1] * ((r > R0) ? x[r - 1 - R0] : halo_lo[col]);
-        if (r < n - 1) y += OE[r] * ((r + 1 < R1) ? x[r + 1 - R0] : halo_hi[col]);
-        acc += y * y;
+    for (int r0 = R0 + threadIdx.x; r0 < R1; r0 += 4 * 256) {
+        double xm[4], xc[4], xp[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 256;
+            xc[u] = (r < R1) ? x[r - R0] : 0.0;
+            xm[u] = (r < R1 && r > 0) ? ((r > R0) ? x[r - 1 - R0] : halo_lo[col]) : 0.0;
+            xp[u] = (r < R1 && r < n - 1) ? ((r + 1 < R1) ? x[r + 1 - R0] : halo_hi[col]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = r0 + u * 256;
+            if (r >= R1) continue;
+            double y = OD[r] * xc[u] - lambda * xc[u];
+            if (r > 0) y += OE[r - 1] * xm[u];
+            if (r < n - 1) y += OE[r] * xp[u];
+            acc += y * y;
+        }
     }
     __shared__ double red[8];
 #pragma unroll

@@ -445,7 +445,7 @@ void Solver::run_level(int h) {
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
         {
-            dim3 grid((unsigned)n, (unsigned)((width + 255) / 256));
+            dim3 grid((unsigned)n, (unsigned)std::min(4, (width + 255) / 256));
             ugen_kernel<<<grid, 256, 0, stream>>>(c, M, p0, width);
             CUDA_CHECK(cudaGetLastError());
         }
