@@ -145,11 +145,11 @@ def run_ours(a):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
     sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()                                  # nvidia-smi needs ~0.5 s before its first sample
     for _ in range(a.warmup):
         solver.solve()
     barrier()
-    if sampler:
-        sampler.start()
     dev_ms, wall_ms, tsum = [], [], None
     for _ in range(a.steps):
         flush.zero_()                                    # L2 flush between timed iterations (untimed)
@@ -194,6 +194,18 @@ def run_ours(a):
 
     ms = float(np.mean(dev_ms))
     peaks, peak_src = measured_peaks()
+    one_gpu = None
+    if world > 1 and not a.no_single_gpu_compare and a.n <= 32768:
+        # the same workload on this rank's GPU alone (strong-scaling numerator), outside the timed region
+        solo = se.CuppenSolver(a.n, ref_leaves=a.ref_leaves, vectors=True, device=local)
+        solo.set_tridiagonal(D, E)
+        tt = []
+        for it in range(3):
+            solo.solve()
+            if it > 0:
+                tt.append(solo.timers()["device_s"])
+        solo.close()
+        one_gpu = {"value": float(np.mean(tt)), "unit": "s", "speedup": float(np.mean(tt)) / (ms * 1e-3)}
     # dominant kernel class of the step, by CUDA-event time inside the library
     cats = {"gemm": tavg["gemm_s"], "pack": tavg["pack_s"], "ugen": tavg["backtransform_ev_s"], "secular": tavg["root_finding_s"],
             "deflation": tavg["deflation_s"], "leaf": tavg["leaf_s"], "residual": tavg["residual_s"]}
@@ -241,6 +253,7 @@ def run_ours(a):
         "gemm_tflops_executed": gemm_tflops,
         "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(8 * (4 * a.n - 2)), "d2h_bytes_per_step": int(8 * 2 * a.n)},
         "gpu_launches": int(tsum["kernel_launches"]),
+        "same_workload_1gpu": one_gpu,
         "phase_ms": {k: v * 1e3 for k, v in cats.items()},
         "roofline": roof,
         "fp64_yardsticks_tflops": {"dmma_issue_loop": dmma_tf, "dfma_issue_loop": dfma_tf, "cublas_dgemm_8192": dgemm_tf},
@@ -358,12 +371,19 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=4096)
-    ap.add_argument("--matrix", default="s1", choices=["s1", "s2", "goe", "randu", "wilk"])
+    ap.add_argument("--size", dest="n", type=int, default=None)
+    ap.add_argument("--matrix", default=None, choices=["s1", "s2", "goe", "randu", "wilk"])
     ap.add_argument("--ref-leaves", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-single-gpu-compare", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=25.0, help="seconds of CPU work per reference step")
     a = ap.parse_args()
+    # default workload: BASELINE configs[1] (`-s 1 -n 4096`, one B200) at N=1; configs[2] (seeded random
+    # symmetric tridiagonal n=16384, divide tree sharded across 2/4/8 B200) at N>1
+    if a.n is None:
+        a.n = 4096 if a.gpus == 1 else 16384
+    if a.matrix is None:
+        a.matrix = "s1" if a.gpus == 1 else "goe"
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference_arm(a)

@@ -259,6 +259,50 @@ __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int
     if (L.lane() == 0) { c.org[D.off + i] = r.origin; c.tau[D.off + i] = r.tau; }
 }
 
+// Fused front end for the small merges at the bottom of the tree: one CTA per merge runs every vector
+// stage (z assembly ... new eigenvalues, and in eigenvalue-only mode the boundary-row update) back
+// to back with block barriers in between, instead of ~12 separate launches per level.
+enum { FUSE_MAXM = 512, FUSE_THREADS = 1024 };
+__global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, RowCtx rc, int rows_mode) {
+    const int id = blockIdx.x;
+    const int off = c.desc[id].off, m = c.desc[id].m;
+    const int tid = threadIdx.x, warp = tid >> 5, nwarps = FUSE_THREADS / 32;
+    const WarpLanes L;
+    for (int g = off + tid; g < off + m; g += FUSE_THREADS) ZAssemble{c}(g);
+    __syncthreads();
+    if (warp == 0) MergeTol{c}(id, L);
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += FUSE_THREADS) FlagDeflate{c}(g);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) RankLive{c}(g, L);
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += FUSE_THREADS) GivensSweep{c}(g);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) Compact{c}(g, L);
+    __syncthreads();
+    {
+        const MergeDesc& D = c.desc[id];
+        const int k = D.k;
+        for (int i = warp; i < k; i += nwarps) {
+            SecularRoot r = secular_solve(L, k, c.dl + off, c.wl + off, fabs(D.rho), D.sumw, i);
+            if (L.lane() == 0) { c.org[off + i] = r.origin; c.tau[off + i] = r.tau; }
+        }
+    }
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) Loewner{c}(g, L);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) Norms{c}(g, L);
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += FUSE_THREADS) NewLambda{c}(g);
+    if (!rows_mode) return;
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += FUSE_THREADS) RowPack{c, rc}(g);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) RowGemv{c, rc}(g, L);
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += FUSE_THREADS) RowCommit{c, rc, const_cast<double*>(c.frow), const_cast<double*>(c.lrow)}(g);
+}
+
 // K5a: walk every rotation chain once per row.  grid.x = global column, grid.y = row chunk.
 enum { PACK_THREADS = 128, PACK_ROWS = 4 };
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M) {

@@ -357,6 +357,21 @@ void Solver::run_level(int h) {
         comm.group_bcast(frow.p + D.off + D.n1, sizeof(double) * D.n2, gmid, glo, gcnt, stream);
     }
 
+    RowCtx rowc{frow.p, lrow.p, frow2.p, lrow2.p, fpack.p, lpack.p};
+#if CUPPEN_CUDA
+    const bool fused = (gcnt == 1 && L.maxm <= FUSE_MAXM);
+#else
+    const bool fused = false;
+#endif
+    if (fused) {
+#if CUPPEN_CUDA
+        pt.begin(T_DEFL, stream);
+        fused_front_kernel<<<(unsigned)nd_cnt, FUSE_THREADS, 0, stream>>>(c, rowc, want_vectors ? 0 : 1);
+        CUDA_CHECK(cudaGetLastError());
+        g_launches.launches++;
+        pt.end(stream);
+#endif
+    } else {
     pt.begin(T_DEFL, stream);
     launch_items(stream, n, ZAssemble{c});
     if (L.any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
@@ -407,16 +422,15 @@ void Solver::run_level(int h) {
     launch_warps(stream, n, Norms{c});
     launch_items(stream, n, NewLambda{c});
     pt.end(stream);
-
     if (!want_vectors) {
-        RowCtx r{frow.p, lrow.p, frow2.p, lrow2.p, fpack.p, lpack.p};
         pt.begin(T_EVX, stream);
-        launch_items(stream, n, RowPack{c, r});
-        launch_warps(stream, n, RowGemv{c, r});
-        launch_items(stream, n, RowCommit{c, r, frow.p, lrow.p});
+        launch_items(stream, n, RowPack{c, rowc});
+        launch_warps(stream, n, RowGemv{c, rowc});
+        launch_items(stream, n, RowCommit{c, rowc, frow.p, lrow.p});
         pt.end(stream);
-        return;
     }
+    }   // !fused
+    if (!want_vectors) return;
 
     MatCtx M = mat_ctx();
     pt.begin(T_PACK, stream);
