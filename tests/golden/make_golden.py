@@ -36,6 +36,9 @@ CASES = [
     ("goe_n1024_p4", ("goe", 1024), 4, False),
     ("randu_n1024_p4", ("randu", 1024), 4, False),
     ("wilk64_n1024_p4", ("wilk", 1024), 4, False),
+    # BASELINE sizes; eigenvalues only -- the reference's -e is O(n^4) here
+    ("s2_n16384_p8", ("scheme", 2, 16384), 8, False),
+    ("goe_n4096_p8", ("goe", 4096), 8, False),
 ]
 
 
@@ -52,7 +55,10 @@ def make_input(gen):
 
 def main():
     oracle.build(ref=True)
+    only = sys.argv[1:]
     for name, gen, P, vec in CASES:
+        if only and name not in only:
+            continue
         D, E, args = make_input(gen)
         with tempfile.TemporaryDirectory() as td:
             if args is None:
