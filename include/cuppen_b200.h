@@ -101,6 +101,10 @@ typedef struct {
     int (*group_bcast)(void* user, void* buf, size_t bytes, int root, int lo, int cnt);
     int (*allreduce_sum_f64)(void* user, double* buf, size_t count);
     int (*allgather)(void* user, const void* send, void* recv, size_t bytes_per_rank);
+    int (*allreduce_sum_i32)(void* user, int* buf, size_t count);
+    /* personalised exchange: send[r] (sbytes[r] bytes) goes to rank r, recv[r] (rbytes[r]) comes from rank r;
+     * entries for the calling rank itself are ignored */
+    int (*alltoallv)(void* user, const void* const* send, const size_t* sbytes, void* const* recv, const size_t* rbytes);
 } cuppen_comm_callbacks;
 
 #define CUPPEN_NCCL_ID_BYTES 128
@@ -134,6 +138,9 @@ int cuppen_get_timers(cuppen_handle h, cuppen_timers* out);
 /* rows [*row0, *row0+*rows) of V held by this rank, columns in ascending-lambda order,
  * column-major with leading dimension ld (>= *rows).  V may be NULL to query the row range. */
 int cuppen_local_rows(cuppen_handle h, int* row0, int* rows);
+/* global row index of every local row (length *rows of cuppen_local_rows): with several GPUs a rank
+ * holds one slice of every subtree of the divide tree's top levels, not one contiguous range */
+int cuppen_local_row_map(cuppen_handle h, int* global_rows);
 int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld);
 const char* cuppen_last_error(void);
 

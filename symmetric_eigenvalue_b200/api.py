@@ -36,11 +36,14 @@ _BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, cty
                              ctypes.c_int, ctypes.c_int)
 _ALLRED_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t)
 _ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t)
+_ALLRED_I32_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_size_t)
+_ALLTOALLV_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t),
+                                 ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_size_t))
 
 
 class _Callbacks(ctypes.Structure):
     _fields_ = [("user", ctypes.c_void_p), ("group_bcast", _BCAST_FN), ("allreduce_sum_f64", _ALLRED_FN),
-                ("allgather", _ALLGATHER_FN)]
+                ("allgather", _ALLGATHER_FN), ("allreduce_sum_i32", _ALLRED_I32_FN), ("alltoallv", _ALLTOALLV_FN)]
 
 
 MergeStat = namedtuple("MergeStat", "offset m n1 mode zdefl givens k height rho")
@@ -70,6 +73,7 @@ def _declare(lib):
         "cuppen_get_merge_stats": [H, ctypes.POINTER(_MergeStat), ctypes.c_int, ip],
         "cuppen_get_timers": [H, ctypes.POINTER(_Timers)],
         "cuppen_local_rows": [H, ip, ip],
+        "cuppen_local_row_map": [H, ip],
         "cuppen_copy_eigenvectors": [H, dp, ctypes.c_long],
         "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_selftest_gemm": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
@@ -90,7 +94,7 @@ def _declare(lib):
 EXPORTED_SYMBOLS = (
     "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
-    "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_copy_eigenvectors",
+    "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors",
     "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_selftest_gemm", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
@@ -226,6 +230,13 @@ class CuppenSolver:
         r0, rows = ctypes.c_int(0), ctypes.c_int(0)
         _chk(self.lib, self.lib.cuppen_local_rows(self._h, ctypes.byref(r0), ctypes.byref(rows)))
         return r0.value, rows.value
+
+    def local_row_map(self):
+        """Global row index of every local row of eigenvectors()."""
+        _, rows = self.local_rows()
+        out = np.zeros(max(rows, 1), dtype=np.int32)
+        _chk(self.lib, self.lib.cuppen_local_row_map(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))))
+        return out[:rows]
 
     def eigenvectors(self):
         """Rows of V owned by this rank (all rows when world == 1), columns in ascending-lambda order."""

@@ -128,6 +128,37 @@ struct Comm {
         CUPPEN_THROW(CUPPEN_ERR_COMM, "no communicator");
 #endif
     }
+    void allreduce_sum_i32(int* buf, size_t count, Stream s) {
+        if (world <= 1) return;
+        if (use_cb) { dev_sync(s); check_cb(cb.allreduce_sum_i32(cb.user, buf, count), "allreduce_i32"); return; }
+#if CUPPEN_CUDA
+        NCCL_CHECK(nccl_api().AllReduce(buf, buf, count, ncclInt32, ncclSum, nccl, s));
+#else
+        CUPPEN_THROW(CUPPEN_ERR_COMM, "no communicator");
+#endif
+    }
+    // personalised exchange of byte buffers (entry `rank` is ignored)
+    void alltoallv(const std::vector<const void*>& send, const std::vector<size_t>& sbytes, const std::vector<void*>& recv,
+                   const std::vector<size_t>& rbytes, Stream s) {
+        if (world <= 1) return;
+        if (use_cb) {
+            dev_sync(s);
+            check_cb(cb.alltoallv(cb.user, send.data(), sbytes.data(), recv.data(), rbytes.data()), "alltoallv");
+            return;
+        }
+#if CUPPEN_CUDA
+        NcclApi& api = nccl_api();
+        NCCL_CHECK(api.GroupStart());
+        for (int r = 0; r < world; ++r) {
+            if (r == rank) continue;
+            if (sbytes[r]) NCCL_CHECK(api.Send(send[r], sbytes[r], ncclInt8, r, nccl, s));
+            if (rbytes[r]) NCCL_CHECK(api.Recv(recv[r], rbytes[r], ncclInt8, r, nccl, s));
+        }
+        NCCL_CHECK(api.GroupEnd());
+#else
+        CUPPEN_THROW(CUPPEN_ERR_COMM, "no communicator");
+#endif
+    }
     void allgather(const void* send, void* recv, size_t bytes, Stream s) {
         if (world <= 1) { dev_d2d(recv, send, bytes, s); return; }
         if (use_cb) { dev_sync(s); check_cb(cb.allgather(cb.user, send, recv, bytes), "allgather"); return; }

@@ -100,11 +100,9 @@ inline void pack_host(LevelCtx c, MatCtx M) {
         const int off = D.off, e = g - off;
         const bool zdefl = c.G[g] == -2;
         if (!zdefl && !c.head[g]) continue;
-        const int rlo = std::max(off, M.R0), rhi = std::min(off + D.m, M.R1);
-        const int split = off + D.n1;
-        for (int r = rlo; r < rhi; ++r) {
-            const long rl = r - M.R0;
-            const bool rtop = r < split;
+        for (int r = D.lr0; r < D.lr1; ++r) {
+            const long rl = r;
+            const bool rtop = r < D.lsplit;
             if (zdefl) {
                 const bool mine = (e < D.n1) == rtop;
                 M.Qnew[rl + (long)g * M.ldq] = mine ? M.Qold[rl + (long)g * M.ldq] : 0.0;
@@ -128,12 +126,11 @@ inline void pack_host(LevelCtx c, MatCtx M) {
 inline void pack_tail_host(LevelCtx c, MatCtx M, int ndesc) {
     for (int id = 0; id < ndesc; ++id) {
         const MergeDesc& D = c.desc[id];
-        const int rlo = std::max(D.off, M.R0), rhi = std::min(D.off + D.m, M.R1);
-        for (int r = rlo; r < rhi; ++r) {
-            const bool rtop = r < D.off + D.n1;
+        for (int r = D.lr0; r < D.lr1; ++r) {
+            const bool rtop = r < D.lsplit;
             const int kh = rtop ? D.ktop : D.kbot;
             const int kend = (kh + K_PAD - 1) / K_PAD * K_PAD;
-            for (int kk = kh; kk < kend; ++kk) M.Apack[(long)(r - M.R0) + (long)(D.off + kk) * M.ldq] = 0.0;
+            for (int kk = kh; kk < kend; ++kk) M.Apack[(long)r + (long)(D.off + kk) * M.ldq] = 0.0;
         }
     }
 }
@@ -195,20 +192,21 @@ inline void gemm_host(const GemmProblem* probs, const GemmTile* tiles, const int
     }
 }
 
-inline void residual_host(const double* Q, long ldq, int n, int R0, int R1, const double* OD, const double* OE,
-                          const double* lam_sorted, const double* halo_lo, const double* halo_hi, double* res2) {
+inline void residual_host(const double* V, long ldq, int n, int g0, int l0, int cnt, const double* OD, const double* OE,
+                          const double* lam_sorted, const double* halo_lo, const double* halo_hi, double* res2, int accumulate) {
+    const int g1 = g0 + cnt;
     for (int col = 0; col < n; ++col) {
-        const double* x = Q + (long)col * ldq;
+        const double* x = V + (long)col * ldq + l0 - g0;
         const double lambda = lam_sorted[col];
         double acc = 0;
-        for (int r = R0; r < R1; ++r) {
-            const double xc = x[r - R0];
+        for (int r = g0; r < g1; ++r) {
+            const double xc = x[r];
             double y = OD[r] * xc - lambda * xc;
-            if (r > 0) y += OE[r - 1] * ((r > R0) ? x[r - 1 - R0] : halo_lo[col]);
-            if (r < n - 1) y += OE[r] * ((r + 1 < R1) ? x[r + 1 - R0] : halo_hi[col]);
+            if (r > 0) y += OE[r - 1] * ((r > g0) ? x[r - 1] : halo_lo[col]);
+            if (r < n - 1) y += OE[r] * ((r + 1 < g1) ? x[r + 1] : halo_hi[col]);
             acc += y * y;
         }
-        res2[col] = acc;
+        res2[col] = accumulate ? res2[col] + acc : acc;
     }
 }
 

@@ -26,7 +26,6 @@ struct LeafDesc { int off, n; };
 
 struct MatCtx {
     int n;                // global size
-    int R0, R1;           // global rows owned by this rank: [R0,R1)
     long ldq;             // leading dimension of the Q buffers and of Apack (local rows, padded)
     const double* Qold;   // children (block diagonal), column-major, local rows
     double* Qnew;         // parents
@@ -42,7 +41,6 @@ struct WorkCtx {
     int nd;                 // merges of this level
     int p0, width;          // panel of root columns [p0, p0+width)
     int BM, BN;             // CTA tile of the GEMM kernel that will consume the list
-    int R0, R1;
     long ldq, ldb;
     double* Apack;
     double* B;
@@ -80,18 +78,17 @@ CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
     const int half = p & 1;
     Pb.M = 0; Pb.N = 0; Pb.K = 0;
     if (D.k <= w.p0) return 0;
-    const int hs = half ? D.off + D.n1 : D.off;
-    const int he = half ? D.off + D.m : D.off + D.n1;
-    const int rs = hs > w.R0 ? hs : w.R0, re = he < w.R1 ? he : w.R1;
+    const int hs = half ? D.off + D.n1 : D.off;                 // arena row of the half's first pole
+    const int rs = half ? D.lsplit : D.lr0, re = half ? D.lr1 : D.lsplit;   // local rows of the half
     if (re <= rs) return 0;
     Pb.M = re - rs;
     Pb.N = (D.k - w.p0) < w.width ? (D.k - w.p0) : w.width;
     Pb.K = half ? D.kbot : D.ktop;
-    Pb.A = w.Apack + (rs - w.R0) + (long)D.off * w.ldq; Pb.lda = w.ldq;
+    Pb.A = w.Apack + rs + (long)D.off * w.ldq; Pb.lda = w.ldq;
     Pb.B = w.B + (long)hs * w.ldb; Pb.ldb = w.ldb;
-    Pb.C = w.Qnext + (rs - w.R0) + (long)D.off * w.ldq; Pb.ldc = w.ldq;
+    Pb.C = w.Qnext + rs + (long)D.off * w.ldq; Pb.ldc = w.ldq;
     Pb.colidx = w.lidx + D.off + w.p0;
-    Pb.a_row0 = rs - w.R0; Pb.a_col0 = D.off; Pb.b_row0 = hs; Pb.b_col0 = 0;
+    Pb.a_row0 = rs; Pb.a_col0 = D.off; Pb.b_row0 = hs; Pb.b_col0 = 0;
     return ((Pb.M + w.BM - 1) / w.BM) * ((Pb.N + w.BN - 1) / w.BN);
 }
 
@@ -314,13 +311,11 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
     const int Gg = c.G[g];
     const bool zdefl = (Gg == -2);
     if (!zdefl && !c.head[g]) return;
-    const int rlo = max(off, M.R0), rhi = min(off + D.m, M.R1);   // global rows of this block held here
-    const int split = off + D.n1;
     for (int t = 0; t < PACK_ROWS; ++t) {
-        const int r = rlo + (blockIdx.y * PACK_ROWS + t) * PACK_THREADS + threadIdx.x;
-        if (r >= rhi) return;
-        const long rl = r - M.R0;
-        const bool rtop = r < split;
+        const int r = D.lr0 + (blockIdx.y * PACK_ROWS + t) * PACK_THREADS + threadIdx.x;   // local row
+        if (r >= D.lr1) return;
+        const long rl = r;
+        const bool rtop = r < D.lsplit;
         if (zdefl) {
             const bool mine = (e < D.n1) == rtop;
             M.Qnew[rl + (long)g * M.ldq] = mine ? M.Qold[rl + (long)g * M.ldq] : 0.0;
@@ -345,13 +340,12 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
 // grid.y = row chunk.
 __global__ void __launch_bounds__(128) pack_tail_kernel(LevelCtx c, MatCtx M) {
     const MergeDesc& D = c.desc[blockIdx.x];
-    const int rlo = max(D.off, M.R0), rhi = min(D.off + D.m, M.R1);
-    const int r = rlo + blockIdx.y * 128 + threadIdx.x;
-    if (r >= rhi) return;
-    const bool rtop = r < D.off + D.n1;
+    const int r = D.lr0 + blockIdx.y * 128 + threadIdx.x;      // local row
+    if (r >= D.lr1) return;
+    const bool rtop = r < D.lsplit;
     const int kh = rtop ? D.ktop : D.kbot;
     const int kend = (kh + K_PAD - 1) / K_PAD * K_PAD;
-    for (int kk = kh; kk < kend; ++kk) M.Apack[(long)(r - M.R0) + (long)(D.off + kk) * M.ldq] = 0.0;
+    for (int kk = kh; kk < kend; ++kk) M.Apack[(long)r + (long)(D.off + kk) * M.ldq] = 0.0;
 }
 
 // K5b: B[row = arena row of pole j][col = root i - p0] = zhat_j / (((d_j - d_org(i)) - tau_i) N_i)
@@ -380,30 +374,33 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
     }
 }
 
-// K8: one block per output column; V holds the columns already in ascending-lambda order.
-// Four independent rows per thread and iteration keep enough loads in flight to stream from HBM.
-__global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ V, long ldq, int n, int R0, int R1,
+// K8: one block per output column over one contiguous slice of rows: global rows [g0, g0+cnt) stored
+// at local rows [l0, l0+cnt).  V holds the columns already in ascending-lambda order.  Four
+// independent rows per thread and iteration keep enough loads in flight to stream from HBM.
+// `accumulate` adds to res2 (a rank holds several slices when the rows are distributed).
+__global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ V, long ldq, int n, int g0, int l0, int cnt,
                                                        const double* __restrict__ OD, const double* __restrict__ OE,
                                                        const double* __restrict__ lam_sorted,
                                                        const double* __restrict__ halo_lo, const double* __restrict__ halo_hi,
-                                                       double* __restrict__ res2) {
+                                                       double* __restrict__ res2, int accumulate) {
     const int col = blockIdx.x;
-    const double* x = V + (long)col * ldq;
+    const double* x = V + (long)col * ldq + l0 - g0;      // x[r] = element of global row r
     const double lambda = lam_sorted[col];
+    const int g1 = g0 + cnt;
     double acc = 0;
-    for (int r0 = R0 + threadIdx.x; r0 < R1; r0 += 4 * 256) {
+    for (int r0 = g0 + threadIdx.x; r0 < g1; r0 += 4 * 256) {
         double xm[4], xc[4], xp[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int r = r0 + u * 256;
-            xc[u] = (r < R1) ? x[r - R0] : 0.0;
-            xm[u] = (r < R1 && r > 0) ? ((r > R0) ? x[r - 1 - R0] : halo_lo[col]) : 0.0;
-            xp[u] = (r < R1 && r < n - 1) ? ((r + 1 < R1) ? x[r + 1 - R0] : halo_hi[col]) : 0.0;
+            xc[u] = (r < g1) ? x[r] : 0.0;
+            xm[u] = (r < g1 && r > 0) ? ((r > g0) ? x[r - 1] : halo_lo[col]) : 0.0;
+            xp[u] = (r < g1 && r < n - 1) ? ((r + 1 < g1) ? x[r + 1] : halo_hi[col]) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int r = r0 + u * 256;
-            if (r >= R1) continue;
+            if (r >= g1) continue;
             double y = OD[r] * xc[u] - lambda * xc[u];
             if (r > 0) y += OE[r - 1] * xm[u];
             if (r < n - 1) y += OE[r] * xp[u];
@@ -418,7 +415,7 @@ __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict_
     if (threadIdx.x == 0) {
         double s = 0;
         for (int w = 0; w < 8; ++w) s += red[w];
-        res2[col] = s;
+        res2[col] = accumulate ? res2[col] + s : s;
     }
 }
 

@@ -31,6 +31,10 @@ struct MergeDesc {
     double rho;      // rank-one weight as seen by the solver: beta*theta (reference rule) or 2*beta
     double theta;    // z = [last row of Q1 ; first row of Q2 / theta]
     double zscale;   // 1 (reference rule) or 1/sqrt(2) (accurate rule, LAPACK dlaed2 convention)
+    // rows of this node's Q block held by this rank: local rows [lr0, lr1), the lower half starts at lsplit
+    int lr0, lsplit, lr1;
+    int own_first, own_last;   // this rank holds the node's first / last global row
+    int pad1;
     // ---- written by the device ----
     int nlive1;      // entries that survive z-deflation
     int k;           // live entries after the Givens sweep = number of secular roots
@@ -440,16 +444,15 @@ struct ExtractRows {
     LevelCtx c;
     const double* Q;
     long ldq;
-    int R0, R1;
     double* frow;
     double* lrow;
     CUPPEN_HD void operator()(long g) const {
         int id = c.node_of[g];
         if (id < 0) return;
         const MergeDesc& D = c.desc[id];
-        const int first = D.off, last = D.off + D.m - 1;
-        if (first >= R0 && first < R1) frow[g] = Q[(long)(first - R0) + g * ldq];
-        if (last >= R0 && last < R1) lrow[g] = Q[(long)(last - R0) + g * ldq];
+        if (D.lr1 <= D.lr0) return;
+        if (D.own_first) frow[g] = Q[(long)D.lr0 + g * ldq];
+        if (D.own_last) lrow[g] = Q[(long)(D.lr1 - 1) + g * ldq];
     }
 };
 

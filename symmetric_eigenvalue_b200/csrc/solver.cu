@@ -65,24 +65,35 @@ struct Solver {
     Comm comm;
     Plan plan;
     bool have_matrix = false, solved = false;
-    int R0 = 0, R1 = 0, nloc = 0;
     long ldq = 0, ldb = 0;
     int W = 0;                    // panel width of the U arena
     Stream stream = 0;
+
+    // ---- row ownership ---------------------------------------------------------------------------
+    // G ranks; subtree s = s-th node at depth log2(G) of the divide tree, global rows
+    // [sub_off[s], sub_off[s]+sub_n[s]).
+    //  layout L (local phase): rank g holds all rows of subtree g, local row = r - R0.
+    //  layout C (cooperative phase, the top log2(G) levels): rank g holds slice g of EVERY subtree,
+    //    rows [sub_off[s]+slice_lo(s,g), sub_off[s]+slice_lo(s,g+1)) at local rows crow0[s]... ;
+    //    every cooperative merge is then split evenly over all ranks whatever its halves deflate to.
+    int G = 1, glog = 0;
+    std::vector<int> sub_off, sub_n, sub_root;
+    int R0 = 0, R1 = 0, nlocL = 0, nlocC = 0;
+    std::vector<int> crow0;
+    int nloc_final = 0;           // local rows of the final V
+    int slice_lo(int s, int j) const { return j >= G ? sub_n[s] : (int)(((long)j * sub_n[s] / G) & ~1L); }
 
     std::vector<double> hD, hE;   // original matrix (host)
     DevBuf<double> dDm, dE, dOD, dOE;
     DevBuf<double> lam, lam_sorted, frow, lrow, frow2, lrow2, fpack, lpack;
     DevBuf<double> d, z, dn, zn, gc, gs, dl, wl, zl, tau, zhat, nrm, res2, halo, halo_all;
-    DevBuf<int> node_of, G, lsort, head, sup, tpos, bpos, lidx, org, toplist, botlist, perm, fail;
+    DevBuf<int> G_, lsort, head, sup, tpos, bpos, lidx, org, toplist, botlist, perm, fail;
     DevBuf<double> Qa, Qb, Apack, B;
-    DevBuf<MergeDesc> desc;
     DevBuf<LeafDesc> leaves;
     DevBuf<GemmProblem> probs;
     DevBuf<GemmTile> tiles;
     double* Qcur = nullptr;       // children / final
     double* Qnext = nullptr;
-    bool final_sorted_in_next = false;
 
     std::vector<double> h_lam_sorted, h_resid;
     std::vector<cuppen_merge_stat> stats;
@@ -94,62 +105,77 @@ struct Solver {
 #if CUPPEN_CUDA
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
 #endif
-    // rank layout
-    std::vector<int> rank_lo, rank_hi;       // row range per rank
     std::vector<int> parent_of;              // plan node -> parent node id
-    // per-level data prepared once per matrix (descriptors and index maps live on the device)
+
+    // ---- schedule: local levels (by height), then cooperative levels (by height) ------------------
+    struct Carry { int off, n, lr0, lr1; };  // finished block that waits for a higher parent
     struct LevelInfo {
-        std::vector<int> ids;                // plan nodes of this height that touch my rows
+        std::vector<int> ids;                // plan nodes merged at this step
+        std::vector<Carry> carry;            // blocks to copy along into the new Q buffer
         size_t desc_off = 0;                 // offset into desc_all
+        int height = 0;
+        bool coop = false;
         int maxm = 0, maxm_rows = 0;
-        int glo = 0, gcnt = 1;               // rank group of a cooperative node
         bool any_accurate = false, aligned = true;
         long worst_tiles_big = 0, worst_tiles_small = 0;
     };
     std::vector<LevelInfo> levels;
+    int first_coop = -1;                     // index of the first cooperative level (-1: none)
     std::vector<MergeDesc> h_desc_all;
     DevBuf<MergeDesc> desc_all;
     DevBuf<int> node_of_all;                 // [levels][n]
     DevBuf<int> ntiles_dev;
-    void prepare_levels();
 
     void init_layout();
     void allocate();
+    void prepare_levels();
     void set_matrix(const double* D, const double* E);
     void solve();
     void run_leaves();
-    void run_level(int h);
+    void run_level(int li);
+    void enter_cooperative();
     void finish();
-    LevelCtx level_ctx(int h);
+    LevelCtx level_ctx(int li);
     MatCtx mat_ctx();
+    int subtree_at(int off) const {
+        for (int s = 0; s < G; ++s) if (sub_off[s] == off) return s;
+        if (off == n) return G;
+        CUPPEN_THROW(CUPPEN_ERR_STATE, "offset %d is not a subtree boundary", off);
+    }
 };
 
 // ---- layout --------------------------------------------------------------------------------------
 void Solver::init_layout() {
-    const int world = comm.world;
-    rank_lo.assign(world, 0);
-    rank_hi.assign(world, n);
-    if (world > 1) {
-        int g = 0;
-        while ((1 << g) < world) ++g;
-        if ((1 << g) != world) CUPPEN_THROW(CUPPEN_ERR_ARG, "world size %d is not a power of two", world);
-        std::vector<std::pair<int, int>> ranges;
-        for (const PlanNode& nd : plan.nodes)
-            if (nd.depth == g) ranges.push_back({nd.off, nd.off + nd.n});
-        std::sort(ranges.begin(), ranges.end());
-        long covered = 0;
-        for (auto& r : ranges) covered += r.second - r.first;
-        if ((int)ranges.size() != world || covered != n)
-            CUPPEN_THROW(CUPPEN_ERR_ARG, "the divide tree of n=%d (reference leaves %d) has no level with %d subtrees", n, P, world);
-        for (int r = 0; r < world; ++r) { rank_lo[r] = ranges[r].first; rank_hi[r] = ranges[r].second; }
-    }
+    G = comm.world;
+    glog = 0;
+    while ((1 << glog) < G) ++glog;
+    if ((1 << glog) != G) CUPPEN_THROW(CUPPEN_ERR_ARG, "world size %d is not a power of two", G);
+    std::vector<std::pair<int, int>> roots;      // (offset, node id) of the nodes at depth log2 G
+    for (size_t id = 0; id < plan.nodes.size(); ++id)
+        if (plan.nodes[id].depth == glog) roots.push_back({plan.nodes[id].off, (int)id});
+    std::sort(roots.begin(), roots.end());
+    long covered = 0;
+    for (auto& r : roots) covered += plan.nodes[r.second].n;
+    if ((int)roots.size() != G || covered != n)
+        CUPPEN_THROW(CUPPEN_ERR_ARG, "the divide tree of n=%d (reference leaves %d) has no level with %d subtrees", n, P, G);
+    sub_off.resize(G); sub_n.resize(G); sub_root.resize(G);
+    for (int s = 0; s < G; ++s) { sub_off[s] = roots[s].first; sub_root[s] = roots[s].second; sub_n[s] = plan.nodes[roots[s].second].n; }
     parent_of.assign(plan.nodes.size(), -1);
     for (size_t id = 0; id < plan.nodes.size(); ++id)
         if (plan.nodes[id].left >= 0) { parent_of[plan.nodes[id].left] = (int)id; parent_of[plan.nodes[id].right] = (int)id; }
-    R0 = rank_lo[comm.rank];
-    R1 = rank_hi[comm.rank];
-    nloc = R1 - R0;
-    ldq = round_up(nloc, 16);
+    R0 = sub_off[comm.rank];
+    R1 = R0 + sub_n[comm.rank];
+    nlocL = R1 - R0;
+    crow0.assign(G + 1, 0);
+    for (int s = 0; s < G; ++s) {
+        const int len = slice_lo(s, comm.rank + 1) - slice_lo(s, comm.rank);
+        if (G > 1 && want_vectors && len <= 0)
+            CUPPEN_THROW(CUPPEN_ERR_ARG, "n=%d is too small to distribute over %d GPUs", n, G);
+        crow0[s + 1] = crow0[s] + len;
+    }
+    nlocC = crow0[G];
+    nloc_final = (G > 1) ? nlocC : nlocL;
+    ldq = round_up(std::max(nlocL, nlocC), 16);
 }
 
 void Solver::allocate() {
@@ -157,11 +183,11 @@ void Solver::allocate() {
     for (DevBuf<double>* b : {&dDm, &dE, &dOD, &dOE, &lam, &lam_sorted, &frow, &lrow, &frow2, &lrow2, &fpack, &lpack, &d, &z,
                               &dn, &zn, &gc, &gs, &dl, &wl, &zl, &tau, &zhat, &nrm, &res2})
         b->alloc(N + 64);
-    for (DevBuf<int>* b : {&node_of, &G, &lsort, &head, &sup, &tpos, &bpos, &lidx, &org, &toplist, &botlist, &perm})
+    for (DevBuf<int>* b : {&G_, &lsort, &head, &sup, &tpos, &bpos, &lidx, &org, &toplist, &botlist, &perm})
         b->alloc(N + 64);
     fail.alloc(4);
-    halo.alloc(2 * N + 64);
-    halo_all.alloc(2 * N * (size_t)comm.world + 64);
+    halo.alloc(2 * N * (size_t)std::max(1, G) + 64);
+    halo_all.alloc(2 * N * (size_t)G * (size_t)G + 64);
     leaves.alloc(std::max<size_t>(1, plan.leaves.size()));
     if (want_vectors) {
         const size_t qelems = (size_t)ldq * (N + K_PAD + 2) + 4096;
@@ -192,17 +218,11 @@ void Solver::allocate() {
 void Solver::set_matrix(const double* D, const double* E) {
     hD.assign(D, D + n);
     hE.assign(E, E + std::max(0, n - 1));
-    for (int i = 0; i < n - 1; ++i)
-        if (hE[i] == 0.0 && P > 1) {
-            // only the reference-rule splits need beta != 0 (assert at src/main.c:196-200, src/eigenvalues.c:68)
-            for (const PlanNode& nd : plan.nodes)
-                if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.off + nd.n1 - 1 == i)
-                    CUPPEN_THROW(CUPPEN_ERR_ZERO, "zero off-diagonal entry E[%d] at a reference split", i);
-        }
     Plan fresh;
     int rc = build_plan(fresh, n, hD.data(), hE.data(), P, LEAF_MAX);
     if (rc != 0) CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
     plan = fresh;
+    // only the reference-rule splits need beta != 0 (assert at src/main.c:196-200, src/eigenvalues.c:68)
     for (const PlanNode& nd : plan.nodes)
         if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.rho == 0.0)
             CUPPEN_THROW(CUPPEN_ERR_ZERO, "zero off-diagonal entry at a reference split (row %d)", nd.off + nd.n1);
@@ -218,10 +238,10 @@ void Solver::set_matrix(const double* D, const double* E) {
     solved = false;
 }
 
-LevelCtx Solver::level_ctx(int h) {
+LevelCtx Solver::level_ctx(int li) {
     LevelCtx c;
-    c.n = n; c.desc = desc_all.p + levels[h].desc_off; c.node_of = node_of_all.p + (size_t)h * n; c.lam = lam.p; c.frow = frow.p; c.lrow = lrow.p;
-    c.d = d.p; c.z = z.p; c.dn = dn.p; c.zn = zn.p; c.G = G.p; c.gc = gc.p; c.gs = gs.p; c.lsort = lsort.p;
+    c.n = n; c.desc = desc_all.p + levels[li].desc_off; c.node_of = node_of_all.p + (size_t)li * n; c.lam = lam.p; c.frow = frow.p; c.lrow = lrow.p;
+    c.d = d.p; c.z = z.p; c.dn = dn.p; c.zn = zn.p; c.G = G_.p; c.gc = gc.p; c.gs = gs.p; c.lsort = lsort.p;
     c.head = head.p; c.sup = sup.p; c.tpos = tpos.p; c.bpos = bpos.p; c.dl = dl.p; c.wl = wl.p; c.zl = zl.p;
     c.lidx = lidx.p; c.org = org.p; c.tau = tau.p; c.zhat = zhat.p; c.nrm = nrm.p; c.toplist = toplist.p;
     c.botlist = botlist.p;
@@ -230,7 +250,7 @@ LevelCtx Solver::level_ctx(int h) {
 
 MatCtx Solver::mat_ctx() {
     MatCtx M;
-    M.n = n; M.R0 = R0; M.R1 = R1; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qnext; M.Apack = Apack.p; M.B = B.p; M.ldb = ldb;
+    M.n = n; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qnext; M.Apack = Apack.p; M.B = B.p; M.ldb = ldb;
     return M;
 }
 
@@ -278,47 +298,88 @@ static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tile
 }
 
 void Solver::prepare_levels() {
-    const int H = (int)plan.by_height.size();
-    levels.assign(H, LevelInfo());
+    // (phase, height) -> level; phase 0: nodes inside my subtree, phase 1: nodes above the subtrees
+    std::map<std::pair<int, int>, std::vector<int>> groups;
+    for (size_t id = 0; id < plan.nodes.size(); ++id) {
+        const PlanNode& nd = plan.nodes[id];
+        if (nd.left < 0) continue;
+        const bool coop = nd.depth < glog;
+        if (!coop && !(nd.off >= R0 && nd.off + nd.n <= R1)) continue;      // another rank's subtree
+        groups[{coop ? 1 : 0, nd.height}].push_back((int)id);
+    }
+    levels.clear();
+    first_coop = -1;
     h_desc_all.clear();
-    std::vector<int> hnode((size_t)std::max(H, 1) * n, -1);
-    for (int h = 1; h < H; ++h) {
-        LevelInfo& L = levels[h];
+    std::vector<int> level_of(plan.nodes.size(), -1);        // schedule index at which a node's Q is produced
+    for (auto& kv : groups) {
+        LevelInfo L;
+        L.coop = kv.first.first == 1;
+        L.height = kv.first.second;
+        L.ids = kv.second;
+        std::sort(L.ids.begin(), L.ids.end(), [&](int a, int b) { return plan.nodes[a].off < plan.nodes[b].off; });
+        if (L.coop && first_coop < 0) first_coop = (int)levels.size();
+        for (int id : L.ids) level_of[id] = (int)levels.size();
+        levels.push_back(L);
+    }
+    const int NL = (int)levels.size();
+    std::vector<int> hnode((size_t)std::max(NL, 1) * n, -1);
+    // local row range of a node's block in the layout of the phase in which it is consumed
+    auto local_rows = [&](const PlanNode& nd, bool coop_layout, int& lr0, int& lsplit, int& lr1) {
+        if (!coop_layout) { lr0 = nd.off - R0; lsplit = nd.off + nd.n1 - R0; lr1 = nd.off + nd.n - R0; return; }
+        const int s0 = subtree_at(nd.off), s1 = subtree_at(nd.off + nd.n);
+        const int sm = nd.left >= 0 ? subtree_at(nd.off + nd.n1) : s1;
+        lr0 = crow0[s0]; lsplit = crow0[sm]; lr1 = crow0[s1];
+    };
+    for (int li = 0; li < NL; ++li) {
+        LevelInfo& L = levels[li];
         L.desc_off = h_desc_all.size();
-        L.glo = comm.rank; L.gcnt = 1;
-        for (int id : plan.by_height[h]) {
-            const PlanNode& nd = plan.nodes[id];
-            if (nd.off < R1 && nd.off + nd.n > R0) L.ids.push_back(id);
-        }
         for (size_t t = 0; t < L.ids.size(); ++t) {
             const PlanNode& nd = plan.nodes[L.ids[t]];
             MergeDesc D;
             memset(&D, 0, sizeof D);
             D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
             D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale;
+            local_rows(nd, L.coop, D.lr0, D.lsplit, D.lr1);
+            D.own_first = L.coop ? (comm.rank == 0) : 1;
+            D.own_last = L.coop ? (comm.rank == G - 1) : 1;
+            if (!want_vectors) { D.lr0 = D.lsplit = D.lr1 = 0; }
             h_desc_all.push_back(D);
             L.any_accurate = L.any_accurate || nd.mode == MODE_ACCURATE;
-            for (int g = nd.off; g < nd.off + nd.n; ++g) hnode[(size_t)h * n + g] = (int)t;
+            for (int g = nd.off; g < nd.off + nd.n; ++g) hnode[(size_t)li * n + g] = (int)t;
             L.maxm = std::max(L.maxm, nd.n);
-            L.maxm_rows = std::max(L.maxm_rows, std::min(nd.off + nd.n, R1) - std::max(nd.off, R0));
+            L.maxm_rows = std::max(L.maxm_rows, D.lr1 - D.lr0);
+            const long N = std::min(W > 0 ? W : nd.n, nd.n);
             for (int half = 0; half < 2; ++half) {
-                const int hs = half ? nd.off + nd.n1 : nd.off, he = half ? nd.off + nd.n : nd.off + nd.n1;
-                const int rs = std::max(hs, R0), re = std::min(he, R1);
+                const int rs = half ? D.lsplit : D.lr0, re = half ? D.lr1 : D.lsplit;
                 if (re <= rs) continue;
-                if ((rs - R0) & 1) L.aligned = false;
-                const long N = std::min(W > 0 ? W : nd.n, nd.n);
+                if (rs & 1) L.aligned = false;
                 L.worst_tiles_big += (long)((re - rs + 127) / 128) * ((N + 127) / 128);
                 L.worst_tiles_small += (long)((re - rs + 63) / 64) * ((N + 63) / 64);
             }
-            if (nd.off < R0 || nd.off + nd.n > R1) {       // spans several ranks
-                if (L.ids.size() != 1) CUPPEN_THROW(CUPPEN_ERR_STATE, "cooperative node is not alone on its level");
-                int glo = 0;
-                while (rank_lo[glo] < nd.off) ++glo;
-                int ghi = glo;
-                while (ghi < comm.world && rank_hi[ghi] <= nd.off + nd.n) ++ghi;
-                L.glo = glo; L.gcnt = ghi - glo;
-            }
         }
+        // finished blocks that are consumed later than the next step must be carried into the new buffer
+        if (want_vectors)
+            for (size_t id = 0; id < plan.nodes.size(); ++id) {
+                const PlanNode& nd = plan.nodes[id];
+                const int par = parent_of[id];
+                if (par < 0 || level_of[par] <= li) continue;                   // consumed now or earlier
+                int produced;                                                   // schedule index after which the block exists
+                if (!L.coop) {
+                    // layout L: only blocks of my own subtree exist
+                    if (nd.depth < glog || !(nd.off >= R0 && nd.off + nd.n <= R1)) continue;
+                    produced = (nd.left < 0) ? -1 : level_of[id];
+                } else {
+                    // layout C: the subtree roots (all of them, one slice each) and the cooperative nodes
+                    if (nd.depth > glog) continue;
+                    produced = (nd.depth == glog) ? first_coop - 1 : level_of[id];
+                }
+                if (produced >= li) continue;                                   // not there yet
+                Carry c;
+                c.off = nd.off; c.n = nd.n;
+                int ls;
+                local_rows(nd, L.coop, c.lr0, ls, c.lr1);
+                if (c.lr1 > c.lr0) L.carry.push_back(c);
+            }
     }
     if (desc_all.n < h_desc_all.size() + 1) desc_all.alloc(h_desc_all.size() + 1);
     if (node_of_all.n < hnode.size()) node_of_all.alloc(hnode.size());
@@ -338,28 +399,83 @@ void Solver::prepare_levels() {
     dev_sync(stream);
 }
 
-void Solver::run_level(int h) {
-    const LevelInfo& L = levels[h];
-    if (L.ids.empty()) return;
-    const int nd_cnt = (int)L.ids.size();
-    const int glo = L.glo, gcnt = L.gcnt;
-    MergeDesc* hd = h_desc_all.data() + L.desc_off;      // host mirror (device-written fields valid after a read-back)
-    LevelCtx c = level_ctx(h);
-
-    if (gcnt > 1) {
-        // children's eigenvalues and boundary rows from their owners (src/main.c:501-517,530-542)
-        const MergeDesc& D = hd[0];
-        int gmid = glo;
-        while (rank_lo[gmid] < D.off + D.n1) ++gmid;                 // first rank of the right child
-        comm.group_bcast(lam.p + D.off, sizeof(double) * D.n1, gmid - 1, glo, gcnt, stream);
-        comm.group_bcast(lrow.p + D.off, sizeof(double) * D.n1, gmid - 1, glo, gcnt, stream);
-        comm.group_bcast(lam.p + D.off + D.n1, sizeof(double) * D.n2, gmid, glo, gcnt, stream);
-        comm.group_bcast(frow.p + D.off + D.n1, sizeof(double) * D.n2, gmid, glo, gcnt, stream);
+// ---- transition to the cooperative phase: replicate the subtree vectors, redistribute the rows ------
+void Solver::enter_cooperative() {
+    if (G <= 1) return;
+    // every rank has lam / first row / last row of its own subtree: zero the rest and sum
+    for (DevBuf<double>* b : {&lam, &frow, &lrow}) {
+        if (R0 > 0) dev_zero(b->p, sizeof(double) * R0, stream);
+        if (R1 < n) dev_zero(b->p + R1, sizeof(double) * (n - R1), stream);
+        comm.allreduce_sum(b->p, n, stream);
     }
-
-    RowCtx rowc{frow.p, lrow.p, frow2.p, lrow2.p, fpack.p, lpack.p};
+    if (!want_vectors) return;
+    // rows: my subtree block (nlocL x nlocL at columns [R0,R1)) is cut into G slices; slice j goes to rank j.
+    // staging: Apack (send, one contiguous len x nlocL block per destination), Qnext (receive)
+    const int me = comm.rank;
+    std::vector<const void*> sp(G, nullptr);
+    std::vector<void*> rp(G, nullptr);
+    std::vector<size_t> sb(G, 0), rb(G, 0);
+    size_t sofs = 0, rofs = 0;
+    std::vector<size_t> rofs_of(G, 0);
+    for (int j = 0; j < G; ++j) {
+        const int lo = slice_lo(me, j), len = slice_lo(me, j + 1) - lo;
+        sp[j] = Apack.p + sofs; sb[j] = sizeof(double) * (size_t)len * nlocL;
+        if (j != me && len > 0) {
 #if CUPPEN_CUDA
-    const bool fused = (gcnt == 1 && L.maxm <= FUSE_MAXM);
+            CUDA_CHECK(cudaMemcpy2DAsync(Apack.p + sofs, sizeof(double) * len, Qcur + (long)R0 * ldq + lo, sizeof(double) * ldq,
+                                         sizeof(double) * len, nlocL, cudaMemcpyDeviceToDevice, stream));
+#else
+            for (int col = 0; col < nlocL; ++col)
+                memcpy(Apack.p + sofs + (size_t)col * len, Qcur + (long)(R0 + col) * ldq + lo, sizeof(double) * len);
+#endif
+        }
+        sofs += (size_t)len * nlocL;
+    }
+    for (int s = 0; s < G; ++s) {
+        const int len = crow0[s + 1] - crow0[s];
+        rofs_of[s] = rofs;
+        rp[s] = Qnext + rofs; rb[s] = sizeof(double) * (size_t)len * sub_n[s];
+        rofs += (size_t)len * sub_n[s];
+    }
+    // my own slice moves inside the buffer: stage it like a received block
+    {
+        const int lo = slice_lo(me, me), len = slice_lo(me, me + 1) - lo;
+#if CUPPEN_CUDA
+        CUDA_CHECK(cudaMemcpy2DAsync(Qnext + rofs_of[me], sizeof(double) * len, Qcur + (long)R0 * ldq + lo, sizeof(double) * ldq,
+                                     sizeof(double) * len, nlocL, cudaMemcpyDeviceToDevice, stream));
+#else
+        for (int col = 0; col < nlocL; ++col)
+            memcpy(Qnext + rofs_of[me] + (size_t)col * len, Qcur + (long)(R0 + col) * ldq + lo, sizeof(double) * len);
+#endif
+    }
+    comm.alltoallv(sp, sb, rp, rb, stream);
+    // unpack into Qcur in layout C: slice of subtree s at local rows crow0[s], columns of subtree s
+    for (int s = 0; s < G; ++s) {
+        const int len = crow0[s + 1] - crow0[s];
+        if (len <= 0) continue;
+#if CUPPEN_CUDA
+        CUDA_CHECK(cudaMemcpy2DAsync(Qcur + (long)sub_off[s] * ldq + crow0[s], sizeof(double) * ldq, Qnext + rofs_of[s],
+                                     sizeof(double) * len, sizeof(double) * len, sub_n[s], cudaMemcpyDeviceToDevice, stream));
+#else
+        for (int col = 0; col < sub_n[s]; ++col)
+            memcpy(Qcur + (long)(sub_off[s] + col) * ldq + crow0[s], Qnext + rofs_of[s] + (size_t)col * len, sizeof(double) * len);
+#endif
+    }
+}
+
+void Solver::run_level(int li) {
+    const LevelInfo& L = levels[li];
+    if (L.ids.empty()) return;
+    if (li == first_coop) enter_cooperative();
+    const int nd_cnt = (int)L.ids.size();
+    const bool coop = L.coop && G > 1;
+    LevelCtx c = level_ctx(li);
+    RowCtx rowc{frow.p, lrow.p, frow2.p, lrow2.p, fpack.p, lpack.p};
+    int lo_idx = n, hi_idx = 0;              // index range covered by this level's nodes
+    for (int id : L.ids) { lo_idx = std::min(lo_idx, plan.nodes[id].off); hi_idx = std::max(hi_idx, plan.nodes[id].off + plan.nodes[id].n); }
+
+#if CUPPEN_CUDA
+    const bool fused = (!coop && L.maxm <= FUSE_MAXM);
 #else
     const bool fused = false;
 #endif
@@ -372,70 +488,67 @@ void Solver::run_level(int h) {
         pt.end(stream);
 #endif
     } else {
-    pt.begin(T_DEFL, stream);
-    launch_items(stream, n, ZAssemble{c});
-    if (L.any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
-    launch_items(stream, n, FlagDeflate{c});
-    launch_warps(stream, n, RankLive{c});
-    launch_items(stream, n, GivensSweep{c});
-    launch_warps(stream, n, Compact{c});
-    pt.end(stream);
-
-    // secular roots: worst-case grid, the kernel reads the live count k of every merge on the device
-    pt.begin(T_ROOT, stream);
-    const int part = comm.rank - glo;
-    const int per = (L.maxm + gcnt - 1) / gcnt;
-#if CUPPEN_CUDA
-    {
-        int kcap = std::min((int)round_up(L.maxm, 32), (int)SEC_SMEM_K);
-        size_t smem = (size_t)2 * kcap * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(2 * SEC_SMEM_K * sizeof(double))));
-            attr_set = true;
-        }
-        dim3 grid((unsigned)((per + SEC_WARPS - 1) / SEC_WARPS), (unsigned)nd_cnt);
-        secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, gcnt);
-        CUDA_CHECK(cudaGetLastError());
-    }
-#else
-    secular_host(c, nd_cnt, part, gcnt);
-#endif
-    g_launches.launches++;
-    pt.end(stream);
-    if (gcnt > 1) {
-        // root slices -> everybody in the group; the slice sizes need k on the host (one small read-back)
-        dev_d2h(hd, desc_all.p + L.desc_off, sizeof(MergeDesc), stream);
-        dev_sync(stream);
-        const MergeDesc& D = hd[0];
-        const int per1 = (D.k + gcnt - 1) / gcnt;
-        for (int r = 0; r < gcnt; ++r) {
-            int i0 = r * per1, i1 = std::min(D.k, i0 + per1);
-            if (i1 <= i0) continue;
-            comm.group_bcast(tau.p + D.off + i0, sizeof(double) * (i1 - i0), glo + r, glo, gcnt, stream);
-            comm.group_bcast(org.p + D.off + i0, sizeof(int) * (i1 - i0), glo + r, glo, gcnt, stream);
-        }
-    }
-    pt.begin(T_EVX, stream);
-    launch_warps(stream, n, Loewner{c});
-    launch_warps(stream, n, Norms{c});
-    launch_items(stream, n, NewLambda{c});
-    pt.end(stream);
-    if (!want_vectors) {
-        pt.begin(T_EVX, stream);
-        launch_items(stream, n, RowPack{c, rowc});
-        launch_warps(stream, n, RowGemv{c, rowc});
-        launch_items(stream, n, RowCommit{c, rowc, frow.p, lrow.p});
+        pt.begin(T_DEFL, stream);
+        launch_items(stream, n, ZAssemble{c});
+        if (L.any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
+        launch_items(stream, n, FlagDeflate{c});
+        launch_warps(stream, n, RankLive{c});
+        launch_items(stream, n, GivensSweep{c});
+        launch_warps(stream, n, Compact{c});
         pt.end(stream);
+
+        // secular roots: worst-case grid, the kernel reads the live count k of every merge on the device.
+        // Cooperative levels: every rank solves its contiguous share of the roots of every merge; the
+        // (tau, origin) arrays are zeroed first so that a sum over ranks assembles them.
+        pt.begin(T_ROOT, stream);
+        const int part = coop ? comm.rank : 0, nparts = coop ? G : 1;
+        if (coop) {
+            dev_zero(tau.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), stream);
+            dev_zero(org.p + lo_idx, sizeof(int) * (hi_idx - lo_idx), stream);
+        }
+        const int per = (L.maxm + nparts - 1) / nparts;
+#if CUPPEN_CUDA
+        {
+            int kcap = std::min((int)round_up(L.maxm, 32), (int)SEC_SMEM_K);
+            size_t smem = (size_t)2 * kcap * sizeof(double);
+            static bool attr_set = false;
+            if (!attr_set) {
+                CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)(2 * SEC_SMEM_K * sizeof(double))));
+                attr_set = true;
+            }
+            dim3 grid((unsigned)((per + SEC_WARPS - 1) / SEC_WARPS), (unsigned)nd_cnt);
+            secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, nparts);
+            CUDA_CHECK(cudaGetLastError());
+        }
+#else
+        secular_host(c, nd_cnt, part, nparts);
+#endif
+        g_launches.launches++;
+        pt.end(stream);
+        if (coop) {
+            comm.allreduce_sum(tau.p + lo_idx, hi_idx - lo_idx, stream);
+            comm.allreduce_sum_i32(org.p + lo_idx, hi_idx - lo_idx, stream);
+        }
+        pt.begin(T_EVX, stream);
+        launch_warps(stream, n, Loewner{c});
+        launch_warps(stream, n, Norms{c});
+        launch_items(stream, n, NewLambda{c});
+        pt.end(stream);
+        if (!want_vectors) {
+            pt.begin(T_EVX, stream);
+            launch_items(stream, n, RowPack{c, rowc});
+            launch_warps(stream, n, RowGemv{c, rowc});
+            launch_items(stream, n, RowCommit{c, rowc, frow.p, lrow.p});
+            pt.end(stream);
+        }
     }
-    }   // !fused
     if (!want_vectors) return;
 
     MatCtx M = mat_ctx();
     pt.begin(T_PACK, stream);
 #if CUPPEN_CUDA
-    {
+    if (L.maxm_rows > 0) {
         dim3 grid((unsigned)n, (unsigned)((L.maxm_rows + PACK_THREADS * PACK_ROWS - 1) / (PACK_THREADS * PACK_ROWS)));
         pack_kernel<<<grid, PACK_THREADS, 0, stream>>>(c, M);
         CUDA_CHECK(cudaGetLastError());
@@ -454,7 +567,7 @@ void Solver::run_level(int h) {
     // (merge, half) problems of the level
     const bool small_tiles = (L.maxm_rows <= 256);
     const int BMN = small_tiles ? 64 : 128;
-    for (int p0 = 0; p0 < L.maxm; p0 += W) {
+    for (int p0 = 0; p0 < L.maxm && L.maxm_rows > 0; p0 += W) {
         const int width = std::min(W, L.maxm - p0);
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
@@ -470,7 +583,7 @@ void Solver::run_level(int h) {
         pt.end(stream);
 
         WorkCtx w;
-        w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN; w.R0 = R0; w.R1 = R1;
+        w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN;
         w.ldq = ldq; w.ldb = ldb; w.Apack = Apack.p; w.B = B.p; w.Qnext = Qnext; w.lidx = lidx.p;
         w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
         const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
@@ -491,39 +604,37 @@ void Solver::run_level(int h) {
         pt.end(stream);
     }
 
-    launch_items(stream, n, ExtractRows{c, Qnext, ldq, R0, R1, frow.p, lrow.p});
-    // blocks that are produced below this level but consumed above it (unbalanced trees only)
-    // must follow into the new buffer
-    for (size_t id = 0; id < plan.nodes.size(); ++id) {
-        const PlanNode& nd = plan.nodes[id];
-        if (nd.off >= R1 || nd.off + nd.n <= R0) continue;
-        const int par = parent_of[id];
-        if (nd.height < h && par >= 0 && plan.nodes[par].height > h) {
-            const int rs = std::max(nd.off, R0), re = std::min(nd.off + nd.n, R1);
+    launch_items(stream, n, ExtractRows{c, Qnext, ldq, frow.p, lrow.p});
+    if (coop && li + 1 < (int)levels.size()) {
+        // first rows live on rank 0, last rows on rank G-1 (slice layout): replicate them for the next level
+        comm.group_bcast(frow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), 0, 0, G, stream);
+        comm.group_bcast(lrow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), G - 1, 0, G, stream);
+    }
+    for (const Carry& cb : L.carry) {
 #if CUPPEN_CUDA
-            CUDA_CHECK(cudaMemcpy2DAsync(Qnext + (long)nd.off * ldq + (rs - R0), sizeof(double) * ldq,
-                                         Qcur + (long)nd.off * ldq + (rs - R0), sizeof(double) * ldq,
-                                         sizeof(double) * (re - rs), nd.n, cudaMemcpyDeviceToDevice, stream));
+        CUDA_CHECK(cudaMemcpy2DAsync(Qnext + (long)cb.off * ldq + cb.lr0, sizeof(double) * ldq, Qcur + (long)cb.off * ldq + cb.lr0,
+                                     sizeof(double) * ldq, sizeof(double) * (cb.lr1 - cb.lr0), cb.n, cudaMemcpyDeviceToDevice, stream));
 #else
-            for (int col = nd.off; col < nd.off + nd.n; ++col)
-                dev_d2d(Qnext + (long)col * ldq + (rs - R0), Qcur + (long)col * ldq + (rs - R0), sizeof(double) * (re - rs), stream);
+        for (int col = cb.off; col < cb.off + cb.n; ++col)
+            dev_d2d(Qnext + (long)col * ldq + cb.lr0, Qcur + (long)col * ldq + cb.lr0, sizeof(double) * (cb.lr1 - cb.lr0), stream);
 #endif
-        }
     }
     std::swap(Qcur, Qnext);
 }
 
 // ---- final ordering, eigenvector gather, residuals -------------------------------------------------
 void Solver::finish() {
+    if (first_coop < 0 && G > 1) enter_cooperative();         // (cannot happen: G > 1 implies cooperative levels)
     launch_warps(stream, n, FinalRank{n, lam.p, perm.p, lam_sorted.p});
     h_lam_sorted.resize(n);
     dev_d2h(h_lam_sorted.data(), lam_sorted.p, sizeof(double) * n, stream);
     h_resid.clear();
     if (want_vectors) {
+        const int nloc = nloc_final;
         pt.begin(T_RESID, stream);
 #if CUPPEN_CUDA
         {
-            dim3 grid((unsigned)n, (unsigned)std::min(64, (nloc + 255) / 256));
+            dim3 grid((unsigned)n, (unsigned)std::max(1, std::min(64, (nloc + 255) / 256)));
             gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Qnext, ldq, nloc, perm.p);
             CUDA_CHECK(cudaGetLastError());
         }
@@ -533,23 +644,37 @@ void Solver::finish() {
         g_launches.launches++;
         std::swap(Qcur, Qnext);           // Qcur: V with columns in ascending-lambda order
         if (!(flags & CUPPEN_FLAG_NO_RESIDUALS)) {
-            double* halo_lo = halo.p;
-            double* halo_hi = halo.p + n;
-            if (comm.world > 1) {
-                // first and last local row of every rank -> neighbours' halos
-                launch_items(stream, n, ExtractRowVec{Qcur, ldq, 0, halo.p});
-                launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)nloc - 1, halo.p + n});
-                comm.allgather(halo.p, halo_all.p, sizeof(double) * 2 * n, stream);
-                halo_lo = (comm.rank > 0) ? halo_all.p + (size_t)(comm.rank - 1) * 2 * n + n : halo.p;
-                halo_hi = (comm.rank + 1 < comm.world) ? halo_all.p + (size_t)(comm.rank + 1) * 2 * n : halo.p;
+            // slices of global rows held here: one (G == 1) or one per subtree
+            struct Slice { int g0, l0, cnt; const double* lo; const double* hi; };
+            std::vector<Slice> sl;
+            if (G == 1) sl.push_back(Slice{0, 0, n, halo.p, halo.p});
+            else {
+                // halo rows: first and last local row of every slice of every rank
+                for (int s = 0; s < G; ++s) {
+                    launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s], halo.p + (size_t)(2 * s) * n});
+                    launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s + 1] - 1, halo.p + (size_t)(2 * s + 1) * n});
+                }
+                comm.allgather(halo.p, halo_all.p, sizeof(double) * 2 * n * G, stream);
+                auto row_of = [&](int rank, int s, int which) { return halo_all.p + ((size_t)rank * 2 * G + 2 * s + which) * n; };
+                const int me = comm.rank;
+                for (int s = 0; s < G; ++s) {
+                    Slice x;
+                    x.g0 = sub_off[s] + slice_lo(s, me); x.l0 = crow0[s]; x.cnt = crow0[s + 1] - crow0[s];
+                    x.lo = (me > 0) ? row_of(me - 1, s, 1) : (s > 0 ? row_of(G - 1, s - 1, 1) : halo.p);
+                    x.hi = (me < G - 1) ? row_of(me + 1, s, 0) : (s < G - 1 ? row_of(0, s + 1, 0) : halo.p);
+                    sl.push_back(x);
+                }
             }
+            for (size_t i = 0; i < sl.size(); ++i) {
 #if CUPPEN_CUDA
-            residual_kernel<<<(unsigned)n, 256, 0, stream>>>(Qcur, ldq, n, R0, R1, dOD.p, dOE.p, lam_sorted.p, halo_lo, halo_hi, res2.p);
-            CUDA_CHECK(cudaGetLastError());
+                residual_kernel<<<(unsigned)n, 256, 0, stream>>>(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p,
+                                                                 sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
+                CUDA_CHECK(cudaGetLastError());
 #else
-            residual_host(Qcur, ldq, n, R0, R1, dOD.p, dOE.p, lam_sorted.p, halo_lo, halo_hi, res2.p);
+                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
 #endif
-            g_launches.launches++;
+                g_launches.launches++;
+            }
             comm.allreduce_sum(res2.p, n, stream);
             h_resid.resize(n);
             dev_d2h(h_resid.data(), res2.p, sizeof(double) * n, stream);
@@ -574,7 +699,7 @@ void Solver::solve() {
     acc_pack_bytes = acc_ugen_bytes = acc_gemm_flop = 0;
     Qcur = Qa.p; Qnext = Qb.p;
     run_leaves();
-    for (int h = 1; h < (int)plan.by_height.size(); ++h) run_level(h);
+    for (int li = 0; li < (int)levels.size(); ++li) run_level(li);
     if (!h_desc_all.empty()) dev_d2h(h_desc_all.data(), desc_all.p, sizeof(MergeDesc) * h_desc_all.size(), stream);
     const double t1 = wall_now();
     finish();
@@ -587,24 +712,19 @@ void Solver::solve() {
     pt.collect();
     const double t2 = wall_now();
     // per-merge records and executed work, from the descriptors the device filled in
-    for (int h = 1; h < (int)levels.size(); ++h)
-        for (size_t t = 0; t < levels[h].ids.size(); ++t) {
-            const MergeDesc& D = h_desc_all[levels[h].desc_off + t];
-            const PlanNode& nd = plan.nodes[levels[h].ids[t]];
+    for (size_t li = 0; li < levels.size(); ++li)
+        for (size_t t = 0; t < levels[li].ids.size(); ++t) {
+            const MergeDesc& D = h_desc_all[levels[li].desc_off + t];
+            const PlanNode& nd = plan.nodes[levels[li].ids[t]];
             cuppen_merge_stat st;
             st.offset = D.off; st.m = D.m; st.n1 = D.n1; st.mode = D.mode; st.zdefl = D.m - D.nlive1;
-            st.givens = D.nlive1 - D.k; st.k = D.k; st.height = h; st.rho = nd.beta * nd.theta;
+            st.givens = D.nlive1 - D.k; st.k = D.k; st.height = nd.height; st.rho = nd.beta * nd.theta;
             stats.push_back(st);
             if (!want_vectors) continue;
-            const double rows = std::min(D.off + D.m, R1) - std::max(D.off, R0);
+            const double rows = D.lr1 - D.lr0;
             acc_pack_bytes += 8.0 * rows * D.m + 8.0 * (rows / 2) * D.m;
-            for (int half = 0; half < 2; ++half) {
-                const int hs = half ? D.off + D.n1 : D.off, he = half ? D.off + D.m : D.off + D.n1;
-                const double mr = std::max(0, std::min(he, R1) - std::max(hs, R0));
-                const double kh = half ? D.kbot : D.ktop;
-                acc_gemm_flop += 2.0 * mr * D.k * kh;
-                acc_ugen_bytes += 8.0 * kh * D.k;
-            }
+            acc_gemm_flop += 2.0 * D.k * ((double)(D.lsplit - D.lr0) * D.ktop + (double)(D.lr1 - D.lsplit) * D.kbot);
+            acc_ugen_bytes += 8.0 * D.k * ((double)D.ktop + D.kbot);
         }
     timers.total_s = t1 - t0;
     timers.root_finding_s = pt.acc[T_ROOT];
@@ -799,7 +919,20 @@ int cuppen_get_timers(cuppen_handle h, cuppen_timers* out) {
 int cuppen_local_rows(cuppen_handle h, int* row0, int* rows) {
     CUPPEN_API_BEGIN
     if (!h || !row0 || !rows) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
-    *row0 = h->s.R0; *rows = h->s.nloc;
+    *row0 = (h->s.G > 1) ? h->s.sub_off[0] + h->s.slice_lo(0, h->s.comm.rank) : 0;
+    *rows = h->s.nloc_final;
+    CUPPEN_API_END
+}
+
+int cuppen_local_row_map(cuppen_handle h, int* global_rows) {
+    CUPPEN_API_BEGIN
+    if (!h || !global_rows) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    Solver& s = h->s;
+    if (s.G == 1) { for (int r = 0; r < s.n; ++r) global_rows[r] = r; }
+    else
+        for (int sub = 0; sub < s.G; ++sub)
+            for (int l = s.crow0[sub]; l < s.crow0[sub + 1]; ++l)
+                global_rows[l] = s.sub_off[sub] + s.slice_lo(sub, s.comm.rank) + (l - s.crow0[sub]);
     CUPPEN_API_END
 }
 
@@ -808,14 +941,14 @@ int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld) {
     if (!h || !V) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
     Solver& s = h->s;
     if (!s.solved || !s.want_vectors) CUPPEN_THROW(CUPPEN_ERR_STATE, "no eigenvectors (solve with CUPPEN_FLAG_VECTORS)");
-    if (ld < s.nloc) CUPPEN_THROW(CUPPEN_ERR_ARG, "ld too small");
+    if (ld < s.nloc_final) CUPPEN_THROW(CUPPEN_ERR_ARG, "ld too small");
 #if CUPPEN_CUDA
     CUDA_CHECK(cudaSetDevice(s.device));
-    CUDA_CHECK(cudaMemcpy2DAsync(V, sizeof(double) * ld, s.Qcur, sizeof(double) * s.ldq, sizeof(double) * s.nloc, s.n,
+    CUDA_CHECK(cudaMemcpy2DAsync(V, sizeof(double) * ld, s.Qcur, sizeof(double) * s.ldq, sizeof(double) * s.nloc_final, s.n,
                                  cudaMemcpyDeviceToHost, s.stream));
     dev_sync(s.stream);
 #else
-    for (int c = 0; c < s.n; ++c) memcpy(V + (long)c * ld, s.Qcur + (long)c * s.ldq, sizeof(double) * s.nloc);
+    for (int c = 0; c < s.n; ++c) memcpy(V + (long)c * ld, s.Qcur + (long)c * s.ldq, sizeof(double) * s.nloc_final);
 #endif
     CUPPEN_API_END
 }

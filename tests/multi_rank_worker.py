@@ -49,11 +49,37 @@ def make_callbacks(rank, world):
         as_tensor(recv, nbytes * world).copy_(torch.cat(out))
         return 0
 
+    def allreduce_i32(user, buf, count):
+        t = torch.from_numpy(np.ctypeslib.as_array(buf, shape=(count,)))
+        dist.all_reduce(t)
+        return 0
+
+    def alltoallv(user, send, sbytes, recv, rbytes):
+        try:
+            reqs = []
+            keep = []
+            for k in range(1, world):
+                dst, src = (rank + k) % world, (rank - k) % world
+                if sbytes[dst]:
+                    t = as_tensor(send[dst], sbytes[dst]).clone()
+                    keep.append(t)
+                    reqs.append(dist.isend(t, dst))
+                if rbytes[src]:
+                    reqs.append(dist.irecv(as_tensor(recv[src], rbytes[src]), src))
+            for r in reqs:
+                r.wait()
+            return 0
+        except Exception as e:      # pragma: no cover
+            print("alltoallv failed:", e, flush=True)
+            return 1
+
     cb = api._Callbacks()
     cb.user = None
     cb.group_bcast = api._BCAST_FN(group_bcast)
     cb.allreduce_sum_f64 = api._ALLRED_FN(allreduce)
     cb.allgather = api._ALLGATHER_FN(allgather)
+    cb.allreduce_sum_i32 = api._ALLRED_I32_FN(allreduce_i32)
+    cb.alltoallv = api._ALLTOALLV_FN(alltoallv)
     return cb
 
 
@@ -70,6 +96,7 @@ def main():
     s.solve()
     lam = s.eigenvalues()
     r0, rows = s.local_rows()
+    rowmap = s.local_row_map() if vectors else None
     # every rank must hold the same eigenvalues
     t = torch.from_numpy(lam.copy()); ref = t.clone()
     dist.broadcast(ref, 0)
@@ -83,8 +110,12 @@ def main():
     if vectors:
         V = s.eigenvectors()
         res = s.residuals()
-        assert V.shape == (rows, n)
-        assert np.abs(V - single["V"][r0:r0 + rows]).max() <= 1e-13
+        assert V.shape == (rows, n) and rowmap.size == rows
+        # all ranks together hold every row exactly once
+        cnt = torch.zeros(n, dtype=torch.int64); cnt[rowmap] += 1
+        dist.all_reduce(cnt)
+        assert bool((cnt == 1).all()), "row ownership is not a partition"
+        assert np.abs(V - single["V"][rowmap]).max() <= 1e-13
         assert np.abs(res - single["resid"]).max() <= 1e-12 + 1e-6 * single["resid"].max()
     o = oracle.solve(D, E, P)
     assert np.abs(lam - o["lam"]).max() <= 1e-12 * (np.abs(D).max() + 2 * np.abs(E).max())

@@ -46,6 +46,9 @@ def _run(world, gen, n, P, vectors, hostemu):
     (2, "s2", 256, 1, True),       # accurate tree, cooperative top merge
     (4, "goe", 400, 4, True),
     (4, "rand_u", 333, 8, False),  # eigenvalue-only mode
+    (2, "goe", 333, 1, True),      # odd sizes: slices start at odd rows
+    (4, "s2", 1000, 8, True),      # reference leaves of 125 rows, Givens-heavy
+    (8, "goe", 640, 8, True),      # one rank per reference leaf, three cooperative levels
 ])
 def test_sharded_solve_over_gloo(hostemu, oracle, world, gen, n, P, vectors):
     _run(world, gen, n, P, vectors, hostemu)
