@@ -193,10 +193,11 @@ inline void gemm_host(const GemmProblem* probs, const GemmTile* tiles, const int
 }
 
 inline void residual_host(const double* V, long ldq, int n, int g0, int l0, int cnt, const double* OD, const double* OE,
-                          const double* lam_sorted, const double* halo_lo, const double* halo_hi, double* res2, int accumulate) {
+                          const double* lam_sorted, const int* perm, const double* halo_lo, const double* halo_hi, double* res2,
+                          int accumulate) {
     const int g1 = g0 + cnt;
     for (int col = 0; col < n; ++col) {
-        const double* x = V + (long)col * ldq + l0 - g0;
+        const double* x = V + (long)perm[col] * ldq + l0 - g0;
         const double lambda = lam_sorted[col];
         double acc = 0;
         for (int r = g0; r < g1; ++r) {

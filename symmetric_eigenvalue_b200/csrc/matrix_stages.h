@@ -301,6 +301,8 @@ __global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, R
 }
 
 // K5a: walk every rotation chain once per row.  grid.x = global column, grid.y = row chunk.
+// Columns without a rotation (z-deflated, or live and unrotated: the common cases) take a fast path
+// that issues the loads of all PACK_ROWS rows before the stores.
 enum { PACK_THREADS = 128, PACK_ROWS = 4 };
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M) {
     const int g = blockIdx.x;
@@ -311,16 +313,39 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
     const int Gg = c.G[g];
     const bool zdefl = (Gg == -2);
     if (!zdefl && !c.head[g]) return;
+    const int rbase = D.lr0 + blockIdx.y * PACK_ROWS * PACK_THREADS + threadIdx.x;      // local row
+    if (rbase >= D.lr1) return;
+    const bool etop = e < D.n1;
+    if (zdefl || Gg == -1) {
+        // plain column move: own-half rows from the child, zeros in the other half (deflated columns
+        // go to Q', live ones to their K slot of Apack -- only over the rows of their own half)
+        double* dst;
+        bool write_other;
+        if (zdefl) { dst = M.Qnew + (long)g * M.ldq; write_other = true; }
+        else {
+            const int pos = etop ? c.tpos[g] : c.bpos[g];
+            dst = M.Apack + (long)(off + pos) * M.ldq;
+            write_other = false;
+        }
+        const double* src = M.Qold + (long)g * M.ldq;
+        double v[PACK_ROWS];
+#pragma unroll
+        for (int t = 0; t < PACK_ROWS; ++t) {
+            const int r = rbase + t * PACK_THREADS;
+            v[t] = (r < D.lr1 && ((r < D.lsplit) == etop)) ? src[r] : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < PACK_ROWS; ++t) {
+            const int r = rbase + t * PACK_THREADS;
+            if (r < D.lr1 && (write_other || ((r < D.lsplit) == etop))) dst[r] = v[t];
+        }
+        return;
+    }
     for (int t = 0; t < PACK_ROWS; ++t) {
-        const int r = D.lr0 + (blockIdx.y * PACK_ROWS + t) * PACK_THREADS + threadIdx.x;   // local row
+        const int r = rbase + t * PACK_THREADS;
         if (r >= D.lr1) return;
         const long rl = r;
         const bool rtop = r < D.lsplit;
-        if (zdefl) {
-            const bool mine = (e < D.n1) == rtop;
-            M.Qnew[rl + (long)g * M.ldq] = mine ? M.Qold[rl + (long)g * M.ldq] : 0.0;
-            continue;
-        }
         int a = e;
         double carry = ((a < D.n1) == rtop) ? M.Qold[rl + (long)(off + a) * M.ldq] : 0.0;
         int b;
@@ -375,16 +400,16 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
 }
 
 // K8: one block per output column over one contiguous slice of rows: global rows [g0, g0+cnt) stored
-// at local rows [l0, l0+cnt).  V holds the columns already in ascending-lambda order.  Four
+// at local rows [l0, l0+cnt).  Output column c (ascending lambda) is storage column perm[c] of V.  Four
 // independent rows per thread and iteration keep enough loads in flight to stream from HBM.
 // `accumulate` adds to res2 (a rank holds several slices when the rows are distributed).
 __global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ V, long ldq, int n, int g0, int l0, int cnt,
                                                        const double* __restrict__ OD, const double* __restrict__ OE,
-                                                       const double* __restrict__ lam_sorted,
+                                                       const double* __restrict__ lam_sorted, const int* __restrict__ perm,
                                                        const double* __restrict__ halo_lo, const double* __restrict__ halo_hi,
                                                        double* __restrict__ res2, int accumulate) {
     const int col = blockIdx.x;
-    const double* x = V + (long)col * ldq + l0 - g0;      // x[r] = element of global row r
+    const double* x = V + (long)perm[col] * ldq + l0 - g0;      // x[r] = element of global row r
     const double lambda = lam_sorted[col];
     const int g1 = g0 + cnt;
     double acc = 0;

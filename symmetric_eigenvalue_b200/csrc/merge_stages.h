@@ -472,12 +472,14 @@ struct FinalRank {
     }
 };
 
+// one local row of V in ascending-lambda column order
 struct ExtractRowVec {
     const double* Q;
     long ldq;
     long rowlocal;
+    const int* perm;
     double* out;
-    CUPPEN_HD void operator()(long c) const { out[c] = Q[rowlocal + c * ldq]; }
+    CUPPEN_HD void operator()(long c) const { out[c] = Q[rowlocal + (long)perm[c] * ldq]; }
 };
 
 }  // namespace cuppen

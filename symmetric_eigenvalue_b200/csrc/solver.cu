@@ -94,6 +94,8 @@ struct Solver {
     DevBuf<GemmTile> tiles;
     double* Qcur = nullptr;       // children / final
     double* Qnext = nullptr;
+    bool sorted_materialised = false;    // Qcur already holds the columns in ascending-lambda order
+    void materialise_sorted();
 
     std::vector<double> h_lam_sorted, h_resid;
     std::vector<cuppen_merge_stat> stats;
@@ -630,19 +632,10 @@ void Solver::finish() {
     dev_d2h(h_lam_sorted.data(), lam_sorted.p, sizeof(double) * n, stream);
     h_resid.clear();
     if (want_vectors) {
-        const int nloc = nloc_final;
         pt.begin(T_RESID, stream);
-#if CUPPEN_CUDA
-        {
-            dim3 grid((unsigned)n, (unsigned)std::max(1, std::min(64, (nloc + 255) / 256)));
-            gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Qnext, ldq, nloc, perm.p);
-            CUDA_CHECK(cudaGetLastError());
-        }
-#else
-        gather_cols_host(Qcur, Qnext, ldq, nloc, perm.p, n);
-#endif
-        g_launches.launches++;
-        std::swap(Qcur, Qnext);           // Qcur: V with columns in ascending-lambda order
+        // V stays in storage order; (perm, lam_sorted) define the ascending order.  The sorted copy is
+        // only materialised when the caller asks for the eigenvectors (cuppen_copy_eigenvectors).
+        sorted_materialised = false;
         if (!(flags & CUPPEN_FLAG_NO_RESIDUALS)) {
             // slices of global rows held here: one (G == 1) or one per subtree
             struct Slice { int g0, l0, cnt; const double* lo; const double* hi; };
@@ -651,8 +644,8 @@ void Solver::finish() {
             else {
                 // halo rows: first and last local row of every slice of every rank
                 for (int s = 0; s < G; ++s) {
-                    launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s], halo.p + (size_t)(2 * s) * n});
-                    launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s + 1] - 1, halo.p + (size_t)(2 * s + 1) * n});
+                    launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s], perm.p, halo.p + (size_t)(2 * s) * n});
+                    launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s + 1] - 1, perm.p, halo.p + (size_t)(2 * s + 1) * n});
                 }
                 comm.allgather(halo.p, halo_all.p, sizeof(double) * 2 * n * G, stream);
                 auto row_of = [&](int rank, int s, int which) { return halo_all.p + ((size_t)rank * 2 * G + 2 * s + which) * n; };
@@ -668,10 +661,10 @@ void Solver::finish() {
             for (size_t i = 0; i < sl.size(); ++i) {
 #if CUPPEN_CUDA
                 residual_kernel<<<(unsigned)n, 256, 0, stream>>>(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p,
-                                                                 sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
+                                                                 perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
                 CUDA_CHECK(cudaGetLastError());
 #else
-                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
+                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
 #endif
                 g_launches.launches++;
             }
@@ -683,6 +676,24 @@ void Solver::finish() {
     }
     dev_sync(stream);
     for (double& r : h_resid) r = sqrt(r);
+}
+
+// column gather into ascending-lambda order (src/filehandling.c:315-321), on demand
+void Solver::materialise_sorted() {
+    if (sorted_materialised || !want_vectors) return;
+#if CUPPEN_CUDA
+    {
+        dim3 grid((unsigned)n, (unsigned)std::max(1, std::min(64, (nloc_final + 255) / 256)));
+        gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Qnext, ldq, nloc_final, perm.p);
+        CUDA_CHECK(cudaGetLastError());
+    }
+#else
+    gather_cols_host(Qcur, Qnext, ldq, nloc_final, perm.p, n);
+#endif
+    g_launches.launches++;
+    std::swap(Qcur, Qnext);
+    dev_sync(stream);
+    sorted_materialised = true;
 }
 
 void Solver::solve() {
@@ -944,6 +955,9 @@ int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld) {
     if (ld < s.nloc_final) CUPPEN_THROW(CUPPEN_ERR_ARG, "ld too small");
 #if CUPPEN_CUDA
     CUDA_CHECK(cudaSetDevice(s.device));
+#endif
+    s.materialise_sorted();
+#if CUPPEN_CUDA
     CUDA_CHECK(cudaMemcpy2DAsync(V, sizeof(double) * ld, s.Qcur, sizeof(double) * s.ldq, sizeof(double) * s.nloc_final, s.n,
                                  cudaMemcpyDeviceToHost, s.stream));
     dev_sync(s.stream);
