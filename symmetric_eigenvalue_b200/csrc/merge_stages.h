@@ -34,7 +34,8 @@ struct MergeDesc {
     // rows of this node's Q block held by this rank: local rows [lr0, lr1), the lower half starts at lsplit
     int lr0, lsplit, lr1;
     int own_first, own_last;   // this rank holds the node's first / last global row
-    int pad1;
+    double sigma;              // max |entry| of T: LAPACK's dstedc scales T to unit norm before its
+                               // tolerances apply; we keep T unscaled and scale the tolerance instead
     // ---- written by the device ----
     int nlive1;      // entries that survive z-deflation
     int k;           // live entries after the Givens sweep = number of secular roots
@@ -101,7 +102,8 @@ struct ZAssemble {
     }
 };
 
-// accurate rule: deflation tolerance 8 eps max(|d|max,|z|max) of every merge (one warp per merge)
+// accurate rule: deflation tolerance 8 eps max(|d|max, sigma |z|max) of every merge (one warp per merge;
+// dlaed2's rule for a matrix that dstedc has scaled by 1/sigma)
 struct MergeTol {
     LevelCtx c;
     template <class L>
@@ -117,7 +119,7 @@ struct MergeTol {
         }
         dmax = lanes.max(dmax);
         zmax = lanes.max(zmax);
-        if (lanes.lane() == 0) D.tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, zmax);
+        if (lanes.lane() == 0) D.tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, D.sigma * zmax);
     }
 };
 

@@ -323,6 +323,10 @@ void Solver::prepare_levels() {
         for (int id : L.ids) level_of[id] = (int)levels.size();
         levels.push_back(L);
     }
+    double sigma = 0;
+    for (double v : hD) sigma = std::max(sigma, fabs(v));
+    for (double v : hE) sigma = std::max(sigma, fabs(v));
+    if (!(sigma > 0)) sigma = 1.0;
     const int NL = (int)levels.size();
     std::vector<int> hnode((size_t)std::max(NL, 1) * n, -1);
     // local row range of a node's block in the layout of the phase in which it is consumed
@@ -340,7 +344,7 @@ void Solver::prepare_levels() {
             MergeDesc D;
             memset(&D, 0, sizeof D);
             D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
-            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale;
+            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = sigma;
             local_rows(nd, L.coop, D.lr0, D.lsplit, D.lr1);
             D.own_first = L.coop ? (comm.rank == 0) : 1;
             D.own_last = L.coop ? (comm.rank == G - 1) : 1;

@@ -62,6 +62,14 @@ def test_accurate_mode_against_lapack(lib, oracle, gen, n):
     assert np.abs(V.T @ V - np.eye(n)).max() < 1e-13
 
 
+@pytest.mark.parametrize("name", __import__("families").FAMILIES)
+def test_matrix_families(lib, name):
+    """Graded, glued, clustered, badly scaled ... inputs under the accurate rule, against LAPACK."""
+    import families
+    D, E = families.family(name, 777)
+    families.check_accurate(se.cuppens(D, E, ref_leaves=1, lib=lib), D, E)
+
+
 def test_baseline_config_properties(lib, oracle):
     """BASELINE configs[1]: -s 1 -n 4096 with eigenvectors (reference tree P=8): properties that
     need no oracle -- T V = V Lambda, V^T V = I, trace, ordering."""

@@ -145,6 +145,14 @@ def test_hostemu_accurate_mode(hostemu, oracle, gen, n):
     assert np.abs(V.T @ V - np.eye(n)).max() < 5e-14
 
 
+@pytest.mark.parametrize("name", __import__("families").FAMILIES)
+def test_hostemu_matrix_families(hostemu, name):
+    """Graded, glued, clustered, badly scaled ... inputs under the accurate rule, against LAPACK."""
+    import families
+    D, E = families.family(name, 200)
+    families.check_accurate(se.cuppens(D, E, ref_leaves=1, lib=hostemu), D, E)
+
+
 def test_hostemu_orthogonality_beats_reference(hostemu, oracle):
     D, E = oracle.goe(256)
     o = oracle.solve(D, E, 4, vectors=True)
