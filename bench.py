@@ -59,32 +59,32 @@ def workload_name(a):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
+    One query per ~100 ms (single-shot calls: `nvidia-smi -lms` block-buffers its output on a pipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
         self.stop_flag = False
-        self.proc = None
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([x.strip() for x in line.split(",")])
-                if self.stop_flag:
-                    break
-        except Exception:
-            pass
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
 
     def finish(self):
         self.stop_flag = True
-        if self.proc:
-            self.proc.terminate()
+        self.join(timeout=6)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
@@ -165,7 +165,6 @@ def run_ours(a):
         dev_ms.append(float(pair[0])); wall_ms.append(float(pair[1]))
         tsum = t if tsum is None else {k: tsum[k] + t[k] for k in t}
     barrier()
-    clocks = sampler.finish() if sampler else None
     tavg = {k: v / a.steps for k, v in tsum.items()}
     lam = solver.eigenvalues(); res = solver.residuals()
 
@@ -185,6 +184,7 @@ def run_ours(a):
         if it > 0:
             e2e.append(float(dt[0]))
     e2e_s = float(np.mean(e2e))
+    clocks = sampler.finish() if sampler else None
 
     if rank != 0:
         solver.close()

@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int
 // Fused front end for the small merges at the bottom of the tree: one CTA per merge runs every vector
 // stage (z assembly ... new eigenvalues, and in eigenvalue-only mode the boundary-row update) back
 // to back with block barriers in between, instead of ~12 separate launches per level.
-enum { FUSE_MAXM = 512, FUSE_THREADS = 1024 };
+enum { FUSE_MAXM = 128, FUSE_THREADS = 512 };
 __global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, RowCtx rc, int rows_mode) {
     const int id = blockIdx.x;
     const int off = c.desc[id].off, m = c.desc[id].m;

@@ -31,6 +31,8 @@ static double wall_now() {
 enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_NCAT };
 struct PhaseTimers {
     double acc[T_NCAT] = {0};
+    bool capturing = false;     // stream capture in progress: record events as external graph nodes
+    bool keep = false;          // spans belong to an instantiated graph: re-read them after every replay
 #if CUPPEN_CUDA
     struct Span { int cat; cudaEvent_t a, b; };
     std::vector<Span> spans;
@@ -39,22 +41,28 @@ struct PhaseTimers {
         if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
         cudaEvent_t e; CUDA_CHECK(cudaEventCreate(&e)); return e;
     }
-    void begin(int cat, Stream s) { Span sp{cat, get(), get()}; CUDA_CHECK(cudaEventRecord(sp.a, s)); spans.push_back(sp); }
-    void end(Stream s) { CUDA_CHECK(cudaEventRecord(spans.back().b, s)); }
+    void record(cudaEvent_t e, Stream s) {
+        if (capturing) CUDA_CHECK(cudaEventRecordWithFlags(e, s, cudaEventRecordExternal));
+        else CUDA_CHECK(cudaEventRecord(e, s));
+    }
+    void begin(int cat, Stream s) { Span sp{cat, get(), get()}; record(sp.a, s); spans.push_back(sp); }
+    void end(Stream s) { record(spans.back().b, s); }
     void collect() {
         for (auto& sp : spans) {
             float ms = 0; cudaEventElapsedTime(&ms, sp.a, sp.b);
             acc[sp.cat] += ms * 1e-3;
-            pool.push_back(sp.a); pool.push_back(sp.b);
+            if (!keep) { pool.push_back(sp.a); pool.push_back(sp.b); }
         }
-        spans.clear();
+        if (!keep) spans.clear();
     }
+    void drop_spans() { for (auto& sp : spans) { pool.push_back(sp.a); pool.push_back(sp.b); } spans.clear(); keep = false; }
     ~PhaseTimers() { for (auto e : pool) cudaEventDestroy(e); for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);} }
 #else
     int cur = -1; double t0 = 0;
     void begin(int cat, Stream) { cur = cat; t0 = wall_now(); }
     void end(Stream) { acc[cur] += wall_now() - t0; }
     void collect() {}
+    void drop_spans() {}
 #endif
     void reset() { for (double& a : acc) a = 0; }
 };
@@ -96,6 +104,25 @@ struct Solver {
     double* Qnext = nullptr;
     bool sorted_materialised = false;    // Qcur already holds the columns in ascending-lambda order
     void materialise_sorted();
+    // one-GPU solves are captured into a CUDA graph on the second call and replayed afterwards
+    // (the whole decomposition is enqueued without any host read-back); env CUPPEN_GRAPH=0 disables
+    bool use_graph = true, graph_failed = false;
+    int solves_done = 0;
+    long graph_launches = 0;
+    bool graph_final_is_a = true;
+    std::vector<LeafDesc> h_leaves;
+    double* pin_lam = nullptr;           // pinned staging of the results read back at the end of a solve
+    double* pin_res = nullptr;
+    MergeDesc* pin_desc = nullptr;
+    int* pin_fail = nullptr;
+    size_t pin_desc_cap = 0;
+#if CUPPEN_CUDA
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+#endif
+    void enqueue_solve();
+    void drop_graph();
+    ~Solver();
 
     std::vector<double> h_lam_sorted, h_resid;
     std::vector<cuppen_merge_stat> stats;
@@ -214,7 +241,43 @@ void Solver::allocate() {
 #endif
     }
     dev_zero(halo.p, halo.bytes(), stream);
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaMallocHost((void**)&pin_lam, sizeof(double) * N));
+    CUDA_CHECK(cudaMallocHost((void**)&pin_res, sizeof(double) * N));
+    CUDA_CHECK(cudaMallocHost((void**)&pin_fail, sizeof(int) * 4));
+    const char* ge = getenv("CUPPEN_GRAPH");
+    if (ge && !strcmp(ge, "0")) use_graph = false;
+#else
+    pin_lam = (double*)malloc(sizeof(double) * N);
+    pin_res = (double*)malloc(sizeof(double) * N);
+    pin_fail = (int*)malloc(sizeof(int) * 4);
+    use_graph = false;
+#endif
+    if (G > 1) use_graph = false;
     dev_sync(stream);
+}
+
+Solver::~Solver() {
+    drop_graph();
+#if CUPPEN_CUDA
+    if (pin_lam) cudaFreeHost(pin_lam);
+    if (pin_res) cudaFreeHost(pin_res);
+    if (pin_fail) cudaFreeHost(pin_fail);
+    if (pin_desc) cudaFreeHost(pin_desc);
+    if (ev_begin) cudaEventDestroy(ev_begin);
+    if (ev_end) cudaEventDestroy(ev_end);
+#else
+    free(pin_lam); free(pin_res); free(pin_fail); free(pin_desc);
+#endif
+}
+
+void Solver::drop_graph() {
+#if CUPPEN_CUDA
+    if (graph_exec) { cudaGraphExecDestroy(graph_exec); graph_exec = nullptr; }
+    if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+#endif
+    pt.drop_spans();
+    solves_done = 0;
 }
 
 void Solver::set_matrix(const double* D, const double* E) {
@@ -258,15 +321,9 @@ MatCtx Solver::mat_ctx() {
 
 // ---- leaves ---------------------------------------------------------------------------------------
 void Solver::run_leaves() {
-    std::vector<LeafDesc> hl;
-    for (int id : plan.leaves) {
-        const PlanNode& nd = plan.nodes[id];
-        if (nd.off >= R0 && nd.off + nd.n <= R1) hl.push_back(LeafDesc{nd.off, nd.n});
-        else if (nd.off < R1 && nd.off + nd.n > R0) CUPPEN_THROW(CUPPEN_ERR_STATE, "leaf straddles a rank boundary");
-    }
-    if (hl.empty()) return;
-    dev_h2d(leaves.p, hl.data(), sizeof(LeafDesc) * hl.size(), stream);
+    const std::vector<LeafDesc>& hl = h_leaves;
     dev_zero(fail.p, sizeof(int) * 4, stream);
+    if (hl.empty()) return;
     pt.begin(T_LEAF, stream);
     double* Q = want_vectors ? Qcur : nullptr;
 #if CUPPEN_CUDA
@@ -300,6 +357,14 @@ static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tile
 }
 
 void Solver::prepare_levels() {
+    drop_graph();
+    h_leaves.clear();
+    for (int id : plan.leaves) {
+        const PlanNode& nd = plan.nodes[id];
+        if (nd.off >= R0 && nd.off + nd.n <= R1) h_leaves.push_back(LeafDesc{nd.off, nd.n});
+        else if (nd.off < R1 && nd.off + nd.n > R0) CUPPEN_THROW(CUPPEN_ERR_STATE, "leaf straddles a rank boundary");
+    }
+    if (!h_leaves.empty()) dev_h2d(leaves.p, h_leaves.data(), sizeof(LeafDesc) * h_leaves.size(), stream);
     // (phase, height) -> level; phase 0: nodes inside my subtree, phase 1: nodes above the subtrees
     std::map<std::pair<int, int>, std::vector<int>> groups;
     for (size_t id = 0; id < plan.nodes.size(); ++id) {
@@ -402,6 +467,16 @@ void Solver::prepare_levels() {
         if (probs.n < worst_p) probs.alloc(worst_p);
     }
     if (ntiles_dev.n < 4) ntiles_dev.alloc(4);
+    if (pin_desc_cap < h_desc_all.size() + 1) {
+#if CUPPEN_CUDA
+        if (pin_desc) cudaFreeHost(pin_desc);
+        CUDA_CHECK(cudaMallocHost((void**)&pin_desc, sizeof(MergeDesc) * (h_desc_all.size() + 1)));
+#else
+        free(pin_desc);
+        pin_desc = (MergeDesc*)malloc(sizeof(MergeDesc) * (h_desc_all.size() + 1));
+#endif
+        pin_desc_cap = h_desc_all.size() + 1;
+    }
     dev_sync(stream);
 }
 
@@ -632,9 +707,7 @@ void Solver::run_level(int li) {
 void Solver::finish() {
     if (first_coop < 0 && G > 1) enter_cooperative();         // (cannot happen: G > 1 implies cooperative levels)
     launch_warps(stream, n, FinalRank{n, lam.p, perm.p, lam_sorted.p});
-    h_lam_sorted.resize(n);
-    dev_d2h(h_lam_sorted.data(), lam_sorted.p, sizeof(double) * n, stream);
-    h_resid.clear();
+    dev_d2h(pin_lam, lam_sorted.p, sizeof(double) * n, stream);
     if (want_vectors) {
         pt.begin(T_RESID, stream);
         // V stays in storage order; (perm, lam_sorted) define the ascending order.  The sorted copy is
@@ -673,13 +746,10 @@ void Solver::finish() {
                 g_launches.launches++;
             }
             comm.allreduce_sum(res2.p, n, stream);
-            h_resid.resize(n);
-            dev_d2h(h_resid.data(), res2.p, sizeof(double) * n, stream);
+            dev_d2h(pin_res, res2.p, sizeof(double) * n, stream);
         }
         pt.end(stream);
     }
-    dev_sync(stream);
-    for (double& r : h_resid) r = sqrt(r);
 }
 
 // column gather into ascending-lambda order (src/filehandling.c:315-321), on demand
@@ -700,32 +770,81 @@ void Solver::materialise_sorted() {
     sorted_materialised = true;
 }
 
+// everything a solve does on the device, enqueued on `stream` without a single host synchronisation
+void Solver::enqueue_solve() {
+#if CUPPEN_CUDA
+    pt.record(ev_begin, stream);
+#endif
+    Qcur = Qa.p; Qnext = Qb.p;
+    run_leaves();
+    for (int li = 0; li < (int)levels.size(); ++li) run_level(li);
+    if (!h_desc_all.empty()) dev_d2h(pin_desc, desc_all.p, sizeof(MergeDesc) * h_desc_all.size(), stream);
+    finish();
+    dev_d2h(pin_fail, fail.p, sizeof(int), stream);
+#if CUPPEN_CUDA
+    pt.record(ev_end, stream);
+#endif
+}
+
 void Solver::solve() {
     if (!have_matrix) CUPPEN_THROW(CUPPEN_ERR_STATE, "cuppen_set_tridiagonal has not been called");
     const double t0 = wall_now();
     const long l0 = g_launches.launches;
 #if CUPPEN_CUDA
     if (!ev_begin) { CUDA_CHECK(cudaEventCreate(&ev_begin)); CUDA_CHECK(cudaEventCreate(&ev_end)); }
-    CUDA_CHECK(cudaEventRecord(ev_begin, stream));
 #endif
     stats.clear();
     pt.reset();
     memset(&timers, 0, sizeof timers);
     acc_pack_bytes = acc_ugen_bytes = acc_gemm_flop = 0;
-    Qcur = Qa.p; Qnext = Qb.p;
-    run_leaves();
-    for (int li = 0; li < (int)levels.size(); ++li) run_level(li);
-    if (!h_desc_all.empty()) dev_d2h(h_desc_all.data(), desc_all.p, sizeof(MergeDesc) * h_desc_all.size(), stream);
-    const double t1 = wall_now();
-    finish();
-    int hfail[4] = {0, 0, 0, 0};
-    dev_d2h(hfail, fail.p, sizeof(int), stream);
+    sorted_materialised = false;
+    bool replayed = false;
 #if CUPPEN_CUDA
-    CUDA_CHECK(cudaEventRecord(ev_end, stream));
+    if (use_graph && !graph_failed && graph_exec) {
+        CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
+        Qcur = graph_final_is_a ? Qa.p : Qb.p;
+        Qnext = graph_final_is_a ? Qb.p : Qa.p;
+        g_launches.launches += graph_launches;
+        replayed = true;
+    } else if (use_graph && !graph_failed && solves_done >= 1) {
+        // second solve of this matrix: capture, instantiate, run
+        pt.drop_spans();
+        pt.capturing = true;
+        cudaError_t ce = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+        if (ce == cudaSuccess) {
+            try { enqueue_solve(); } catch (...) { cudaGraph_t g2 = nullptr; cudaStreamEndCapture(stream, &g2); if (g2) cudaGraphDestroy(g2); pt.capturing = false; graph_failed = true; throw; }
+            ce = cudaStreamEndCapture(stream, &graph);
+        }
+        pt.capturing = false;
+        if (ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&graph_exec, graph, 0);
+        if (ce == cudaSuccess && graph_exec) {
+            graph_launches = g_launches.launches - l0;
+            graph_final_is_a = (Qcur == Qa.p);
+            pt.keep = true;
+            CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
+            replayed = true;
+        } else {
+            cudaGetLastError();
+            graph_failed = true;
+            pt.drop_spans();
+            if (graph) { cudaGraphDestroy(graph); graph = nullptr; }
+        }
+    }
 #endif
+    if (!replayed) enqueue_solve();
+    const double t1 = wall_now();
     dev_sync(stream);
     pt.collect();
     const double t2 = wall_now();
+    solves_done++;
+    h_lam_sorted.assign(pin_lam, pin_lam + n);
+    h_resid.clear();
+    if (want_vectors && !(flags & CUPPEN_FLAG_NO_RESIDUALS)) {
+        h_resid.assign(pin_res, pin_res + n);
+        for (double& r : h_resid) r = sqrt(r);
+    }
+    if (!h_desc_all.empty()) memcpy(h_desc_all.data(), pin_desc, sizeof(MergeDesc) * h_desc_all.size());
+    int hfail[4] = {pin_fail[0], 0, 0, 0};
     // per-merge records and executed work, from the descriptors the device filled in
     for (size_t li = 0; li < levels.size(); ++li)
         for (size_t t = 0; t < levels[li].ids.size(); ++t) {

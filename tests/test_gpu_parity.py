@@ -126,10 +126,21 @@ def test_resolve_is_repeatable(lib, oracle):
     D, E = oracle.goe(900)
     s = se.CuppenSolver(900, ref_leaves=4, lib=lib)
     s.set_tridiagonal(D, E)
-    s.solve()
-    a = s.eigenvalues().copy(); ra = s.residuals().copy()
-    s.solve()
-    assert np.array_equal(a, s.eigenvalues()) and np.array_equal(ra, s.residuals())
+    s.solve()                                   # eager
+    a = s.eigenvalues().copy(); ra = s.residuals().copy(); Va = s.eigenvectors().copy()
+    st = s.merge_stats()
+    for it in range(3):                         # CUDA-graph capture, then replays
+        s.solve()
+        assert np.array_equal(a, s.eigenvalues()) and np.array_equal(ra, s.residuals())
+        assert s.merge_stats() == st
+    assert np.array_equal(Va, s.eigenvectors())
+    # a new matrix on the same handle invalidates the captured graph
+    D2, E2 = oracle.goe(900, seed=11)
+    s.set_tridiagonal(D2, E2)
+    for it in range(3):
+        s.solve()
+    ref = se.cuppens(D2, E2, ref_leaves=4, lib=lib)
+    assert np.array_equal(ref["lam"], s.eigenvalues())
     s.close()
 
 
