@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
 
 // K3: one warp per secular root; poles and weights of the merge staged in shared memory when
 // they fit (k <= SEC_SMEM_K), otherwise read through L1/L2.
-enum { SEC_SMEM_K = 6144, SEC_WARPS = 16 };
+enum { SEC_SMEM_K = 14336, SEC_WARPS = 16 };
 __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int kcap, int part, int nparts) {
     extern __shared__ double sec_smem[];
     const int id = blockIdx.y;

@@ -39,20 +39,28 @@ struct SerialLanes {
 #endif
 
 // psi = sum_{j<=split} w_j/(delta_j - tau), phi = sum_{j>split}; derivatives likewise.
-// `skip0`, `skip1` (pole indices or -1) are left out (used for the initial guess).
+// Branch-free loop bodies, unrolled: four independent reciprocal chains per lane keep the FP64
+// pipe busy.
 template <class Lanes>
 CUPPEN_HD SecularSums secular_eval(const Lanes& L, int k, const double* __restrict__ d,
-                                   const double* __restrict__ w, double dorg, double tau, int split,
-                                   int skip0, int skip1) {
+                                   const double* __restrict__ w, double dorg, double tau, int split) {
     double psi = 0, dpsi = 0, phi = 0, dphi = 0, err = 0;
-    for (int j = L.lane(); j < k; j += L.lanes()) {
-        if (j == skip0 || j == skip1) continue;
-        double t = (d[j] - dorg) - tau;
-        double inv = 1.0 / t;
-        double r = w[j] * inv;
-        if (j <= split) { psi += r; dpsi += r * inv; }
-        else { phi += r; dphi += r * inv; }
-        err += fabs(r);
+    const int nl = L.lanes();
+    int j = L.lane();
+    const int split1 = split + 1 < k ? split + 1 : k;
+#pragma unroll 4
+    for (; j < split1; j += nl) {
+        const double t = (d[j] - dorg) - tau;
+        const double inv = 1.0 / t;
+        const double r = w[j] * inv;
+        psi += r; dpsi += r * inv; err += fabs(r);
+    }
+#pragma unroll 4
+    for (; j < k; j += nl) {
+        const double t = (d[j] - dorg) - tau;
+        const double inv = 1.0 / t;
+        const double r = w[j] * inv;
+        phi += r; dphi += r * inv; err += fabs(r);
     }
     SecularSums s;
     s.psi = L.sum(psi); s.dpsi = L.sum(dpsi); s.phi = L.sum(phi); s.dphi = L.sum(dphi); s.err = L.sum(err);
@@ -86,10 +94,10 @@ CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restr
     if (!last) {
         // decide the origin from the sign of g at the midpoint (evaluated relative to pole i)
         const double half = 0.5 * gap;
-        SecularSums s = secular_eval(L, k, d, w, d[i], half, i, ip0, ip1);
+        SecularSums s = secular_eval(L, k, d, w, d[i], half, i);
         out.iters++;
-        const double c = rhoinv + s.psi + s.phi;                 // all poles except ip0, ip1
-        const double gmid = c + w[ip0] / (-half) + w[ip1] / half;
+        const double gmid = rhoinv + s.psi + s.phi;              // full secular function at the midpoint
+        const double c = gmid - w[ip0] / (-half) - w[ip1] / half;   // without the two nearest poles (initial guess only)
         const double a_ = c * gap, w0 = w[ip0], w1 = w[ip1];
         if (gmid >= 0.0) {            // root in the left half: origin i, tau in (0, gap/2]
             org = i; lo = 0.0; hi = half;
@@ -107,11 +115,11 @@ CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restr
         org = k - 1;
         const double R = rho * sumw;
         const double mid = 0.5 * R;
-        SecularSums s = secular_eval(L, k, d, w, d[org], mid, k, ip0, ip1);
+        SecularSums s = secular_eval(L, k, d, w, d[org], mid, k);
         out.iters++;
-        const double c = rhoinv + s.psi;                         // poles 0..k-3
         const double w0 = w[ip0], w1 = w[ip1];
-        const double gmid = c + w0 / (-gap - mid) + w1 / (-mid);
+        const double gmid = rhoinv + s.psi;                      // full secular function at the midpoint
+        const double c = gmid - w0 / (-gap - mid) - w1 / (-mid); // poles 0..k-3 only (initial guess)
         const double a = -c * gap + w0 + w1, b = w1 * gap;
         const double disc = sqrt(fabs(a * a + 4.0 * b * c));
         if (gmid <= 0.0) {            // root above the midpoint
@@ -131,7 +139,7 @@ CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restr
     double prevabs = INFINITY;
     int slow = 0;
     for (int it = 0; it < 80; ++it) {
-        SecularSums s = secular_eval(L, k, d, w, dorg, tau, split, -1, -1);
+        SecularSums s = secular_eval(L, k, d, w, dorg, tau, split);
         out.iters++;
         const double h = rhoinv + s.psi + s.phi;
         const double errb = eps * (8.0 * s.err + fabs(rhoinv) + fabs(tau) * (s.dpsi + s.dphi));

@@ -157,7 +157,8 @@ struct Solver {
 
     void init_layout();
     void allocate();
-    void prepare_levels();
+    void prepare_levels();          // tree-shape dependent data: once per handle (the shape depends on (n, P) only)
+    void update_descriptors();      // matrix dependent fields (rho, theta, sigma): every cuppen_set_tridiagonal
     void set_matrix(const double* D, const double* E);
     void solve();
     void run_leaves();
@@ -291,7 +292,7 @@ void Solver::set_matrix(const double* D, const double* E) {
     for (const PlanNode& nd : plan.nodes)
         if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.rho == 0.0)
             CUPPEN_THROW(CUPPEN_ERR_ZERO, "zero off-diagonal entry at a reference split (row %d)", nd.off + nd.n1);
-    prepare_levels();
+    update_descriptors();
     dev_h2d(dDm.p, plan.D.data(), sizeof(double) * n, stream);
     dev_h2d(dOD.p, hD.data(), sizeof(double) * n, stream);
     if (n > 1) {
@@ -356,6 +357,21 @@ static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tile
 #endif
 }
 
+void Solver::update_descriptors() {
+    double sigma = 0;
+    for (double v : hD) sigma = std::max(sigma, fabs(v));
+    for (double v : hE) sigma = std::max(sigma, fabs(v));
+    if (!(sigma > 0)) sigma = 1.0;
+    for (const LevelInfo& L : levels)
+        for (size_t t = 0; t < L.ids.size(); ++t) {
+            const PlanNode& nd = plan.nodes[L.ids[t]];
+            MergeDesc& D = h_desc_all[L.desc_off + t];
+            if (D.off != nd.off || D.m != nd.n || D.n1 != nd.n1) CUPPEN_THROW(CUPPEN_ERR_STATE, "divide tree changed shape");
+            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = sigma; D.mode = nd.mode;
+        }
+    if (!h_desc_all.empty()) dev_h2d(desc_all.p, h_desc_all.data(), sizeof(MergeDesc) * h_desc_all.size(), stream);
+}
+
 void Solver::prepare_levels() {
     drop_graph();
     h_leaves.clear();
@@ -388,10 +404,6 @@ void Solver::prepare_levels() {
         for (int id : L.ids) level_of[id] = (int)levels.size();
         levels.push_back(L);
     }
-    double sigma = 0;
-    for (double v : hD) sigma = std::max(sigma, fabs(v));
-    for (double v : hE) sigma = std::max(sigma, fabs(v));
-    if (!(sigma > 0)) sigma = 1.0;
     const int NL = (int)levels.size();
     std::vector<int> hnode((size_t)std::max(NL, 1) * n, -1);
     // local row range of a node's block in the layout of the phase in which it is consumed
@@ -409,7 +421,7 @@ void Solver::prepare_levels() {
             MergeDesc D;
             memset(&D, 0, sizeof D);
             D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
-            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = sigma;
+            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = 1.0;
             local_rows(nd, L.coop, D.lr0, D.lsplit, D.lr1);
             D.own_first = L.coop ? (comm.rank == 0) : 1;
             D.own_last = L.coop ? (comm.rank == G - 1) : 1;
@@ -931,6 +943,7 @@ static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int
             CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
         s.init_layout();
         s.allocate();
+        s.prepare_levels();
     } catch (...) { delete hs; throw; }
     *h = hs;
     CUPPEN_API_END
