@@ -75,6 +75,7 @@ struct Solver {
     bool have_matrix = false, solved = false;
     long ldq = 0, ldb = 0;
     int W = 0;                    // panel width of the U arena
+    int leaf_max = LEAF_MAX;
     Stream stream = 0;
 
     // ---- row ownership ---------------------------------------------------------------------------
@@ -285,7 +286,7 @@ void Solver::set_matrix(const double* D, const double* E) {
     hD.assign(D, D + n);
     hE.assign(E, E + std::max(0, n - 1));
     Plan fresh;
-    int rc = build_plan(fresh, n, hD.data(), hE.data(), P, LEAF_MAX);
+    int rc = build_plan(fresh, n, hD.data(), hE.data(), P, leaf_max);
     if (rc != 0) CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
     plan = fresh;
     // only the reference-rule splits need beta != 0 (assert at src/main.c:196-200, src/eigenvalues.c:68)
@@ -939,7 +940,11 @@ static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int
 #endif
         // the tree shape depends only on (n, P): plan with a dummy matrix to size the buffers
         std::vector<double> D0(n, 1.0), E0(std::max(1, n - 1), 1.0);
-        if (build_plan(s.plan, n, D0.data(), E0.data(), ref_leaves, LEAF_MAX) != 0)
+        {
+            const char* le = getenv("CUPPEN_LEAF");     // leaf size of the accurate sub-tree (8..32), default 32
+            if (le && atoi(le) >= 4 && atoi(le) <= LEAF_MAX) s.leaf_max = atoi(le);
+        }
+        if (build_plan(s.plan, n, D0.data(), E0.data(), ref_leaves, s.leaf_max) != 0)
             CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
         s.init_layout();
         s.allocate();
