@@ -75,7 +75,7 @@ struct Solver {
     bool have_matrix = false, solved = false;
     long ldq = 0, ldb = 0;
     int W = 0;                    // panel width of the U arena
-    int leaf_max = LEAF_MAX;
+    int leaf_max = 16;            // leaf size of the accurate tree (measured best of 8/16/32 at n=4096); env CUPPEN_LEAF
     Stream stream = 0;
 
     // ---- row ownership ---------------------------------------------------------------------------
