@@ -59,8 +59,9 @@ def workload_name(a):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).
-    One query per ~100 ms (single-shot calls: `nvidia-smi -lms` block-buffers its output on a pipe)."""
+    """SM clock / throttle reasons during the timed region (B200_PROFILING.md recipe): NVML is polled
+    every few ms (the steps of the small workloads are shorter than an `nvidia-smi -lms` period);
+    falls back to single-shot nvidia-smi queries when pynvml is missing."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -68,36 +69,63 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.rows = []
+        self.sm, self.mx, self.reasons = [], [], set()
         self.stop_flag = False
+        self.active = False          # samples are kept only while the timed region runs
+        self.ready = threading.Event()
+        self.source = "nvml"
 
-    def run(self):
+    def _nvml_loop(self):
+        import pynvml as nv
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(self.index)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        self.ready.set()
         while not self.stop_flag:
+            if self.active:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                self.mx.append(float(mx))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            time.sleep(0.002)
+
+    def _smi_loop(self):
+        self.source = "nvidia-smi"
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        self.ready.set()
+        while not self.stop_flag:
+            if not self.active:
+                time.sleep(0.002)
+                continue
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
                                      capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
-                    self.rows.append([x.strip() for x in line.split(",")])
+                    r = [x.strip() for x in line.split(",")]
+                    self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                    for k, nm in enumerate(names):
+                        if r[3 + k].lower().startswith("active"):
+                            self.reasons.add(nm)
             except Exception:
                 pass
             time.sleep(0.1)
 
+    def run(self):
+        try:
+            self._nvml_loop()
+        except Exception:
+            self._smi_loop()
+
     def finish(self):
         self.stop_flag = True
         self.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                continue
-        busy = [s for s in sm if s > 0]
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        busy = [s for s in self.sm if s > 0]
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": self.source}
 
 
 def measured_peaks():
@@ -146,10 +174,13 @@ def run_ours(a):
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
-        sampler.start()                                  # nvidia-smi needs ~0.5 s before its first sample
+        sampler.start()
+        sampler.ready.wait(10)
     for _ in range(a.warmup):
         solver.solve()
     barrier()
+    if sampler:
+        sampler.active = True
     dev_ms, wall_ms, tsum = [], [], None
     for _ in range(a.steps):
         flush.zero_()                                    # L2 flush between timed iterations (untimed)
@@ -165,6 +196,9 @@ def run_ours(a):
         dev_ms.append(float(pair[0])); wall_ms.append(float(pair[1]))
         tsum = t if tsum is None else {k: tsum[k] + t[k] for k in t}
     barrier()
+    if sampler:
+        sampler.active = False
+    clocks = sampler.finish() if sampler else None
     tavg = {k: v / a.steps for k, v in tsum.items()}
     lam = solver.eigenvalues(); res = solver.residuals()
 
@@ -184,7 +218,6 @@ def run_ours(a):
         if it > 0:
             e2e.append(float(dt[0]))
     e2e_s = float(np.mean(e2e))
-    clocks = sampler.finish() if sampler else None
 
     if rank != 0:
         solver.close()

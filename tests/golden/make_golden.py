@@ -39,6 +39,8 @@ CASES = [
     # BASELINE sizes; eigenvalues only -- the reference's -e is O(n^4) here
     ("s2_n16384_p8", ("scheme", 2, 16384), 8, False),
     ("goe_n4096_p8", ("goe", 4096), 8, False),
+    ("wilk64_n16384_p8", ("wilk", 16384), 8, False),
+    ("randu_n16384_p8", ("randu", 16384), 8, False),
 ]
 
 

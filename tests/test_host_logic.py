@@ -112,7 +112,7 @@ def test_hostemu_matches_reference_goldens(hostemu, name):
     check_against_golden(g, out, vec)
 
 
-@pytest.mark.parametrize("name", ["goe_n4096_p8", "s2_n16384_p8"])
+@pytest.mark.parametrize("name", ["goe_n4096_p8", "s2_n16384_p8", "wilk64_n16384_p8", "randu_n16384_p8"])
 def test_hostemu_baseline_size_goldens_eigenvalue_mode(hostemu, name):
     """BASELINE-size inputs (configs 3/4) against the reference's own output, eigenvalue-only path
     (boundary-row propagation, src/main.c:613-639): the reference is off from the true spectrum by
