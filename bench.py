@@ -293,12 +293,38 @@ def run_ours(a):
         "clocks": clocks,
         "check": {"max_residual": float(res.max()), "lambda_min": float(lam[0]), "lambda_max": float(lam[-1])},
     }
+    if world == 1 and a.select > 0:
+        line["selected_mode"] = selected_mode(a, D, E, local, res)
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference(a, bounded_s=25.0)
     print(json.dumps(line), flush=True)
     solver.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def selected_mode(a, D, E, device, full_resid):
+    """The reference's -eFILE use case (extra key, not the headline metric): `--select K` evenly spaced
+    eigenvectors through the selected-eigenvector mode (no n x n matrix; select_stages.h).  Time per solve =
+    eigenvalue-only decomposition + back-application, CUDA events inside the library."""
+    import symmetric_eigenvalue_b200 as se
+    sel = np.unique(np.linspace(0, a.n - 1, a.select).astype(np.int32))
+    s = se.CuppenSolver(a.n, ref_leaves=a.ref_leaves, device=device, select=True)
+    s.set_tridiagonal(D, E)
+    s.select(sel)
+    dev, app = [], []
+    for it in range(a.warmup + max(3, min(a.steps, 10))):
+        s.solve()
+        if it >= a.warmup:
+            t = s.timers()
+            dev.append(t["device_s"]); app.append(t["apply_s"])
+    r = s.residuals(sel)
+    s.close()
+    # algorithmic work of the apply phase: pole/root pairs = sum over merges of k^2 (one fp64 reciprocal + 8 fma each)
+    return {"k": int(sel.size), "device_s_per_solve": float(np.mean(dev)), "apply_s": float(np.mean(app)),
+            "max_residual": float(r.max()), "max_residual_full_mode_same_columns": float(full_resid[sel].max()),
+            "note": "eigenvalue-only solve + implicit back-application of the K selected columns; "
+                    "the reference's -eFILE costs cpu_baseline.backtransform_s_per_eigenvector per column"}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -408,6 +434,7 @@ def main():
     ap.add_argument("--matrix", default=None, choices=["s1", "s2", "goe", "randu", "wilk"])
     ap.add_argument("--ref-leaves", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--select", type=int, default=16, help="also time the selected-eigenvector mode on K vectors (0: skip)")
     ap.add_argument("--no-single-gpu-compare", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=25.0, help="seconds of CPU work per reference step")
     a = ap.parse_args()

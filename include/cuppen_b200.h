@@ -61,7 +61,10 @@ enum {
 
 enum {
     CUPPEN_FLAG_VECTORS = 1,    /* materialise eigenvectors (the reference's -e) */
-    CUPPEN_FLAG_NO_RESIDUALS = 2
+    CUPPEN_FLAG_NO_RESIDUALS = 2,
+    CUPPEN_FLAG_SELECT = 4      /* eigenvectors of selected eigenvalues only (the reference's -eFILE): no n x n matrix
+                                   is formed, the selected columns are pushed through the implicit U factors of
+                                   the tree; see cuppen_select_eigenvectors */
 };
 
 /* One record per merge of the tree. */
@@ -91,6 +94,7 @@ typedef struct {
     double ugen_bytes;       /* algorithmic bytes of ugen_kernel: 8*K*N written */
     double secular_root_iters; /* reserved */
     long   kernel_launches;
+    double apply_s;          /* CUPPEN_FLAG_SELECT: device time of the back-application of the selected columns */
 } cuppen_timers;
 
 /* Communication callbacks for world > 1 when NCCL is not used (tests drive these with gloo).
@@ -142,6 +146,13 @@ int cuppen_local_rows(cuppen_handle h, int* row0, int* rows);
  * holds one slice of every subtree of the divide tree's top levels, not one contiguous range */
 int cuppen_local_row_map(cuppen_handle h, int* global_rows);
 int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld);
+/* Selected-eigenvector mode (handle created with CUPPEN_FLAG_SELECT): replaces determineEigenvectorsToCompute's
+ * EVToCompute list (src/filehandling.h:10-24,69) and the per-index loop of writeResults (src/filehandling.c:339-345).
+ * idx[i] = 0-based rank in ascending-lambda order; takes effect at the next cuppen_solve.  Afterwards
+ * cuppen_get_residuals answers for the selected ranks (idx == NULL: length-n array, NaN where not selected) and
+ * cuppen_copy_selected_eigenvectors returns the n x cnt matrix (column t = eigenvector of rank idx[t], column-major, ld >= n). */
+int cuppen_select_eigenvectors(cuppen_handle h, const int* idx, int cnt);
+int cuppen_copy_selected_eigenvectors(cuppen_handle h, double* V, long ld);
 const char* cuppen_last_error(void);
 
 /* FP64 yardsticks measured on the device: register-resident DMMA.8x8x4 issue loop and DFMA loop,

@@ -10,6 +10,7 @@ _LIB = None
 
 FLAG_VECTORS = 1
 FLAG_NO_RESIDUALS = 2
+FLAG_SELECT = 4
 NCCL_ID_BYTES = 128
 
 
@@ -29,7 +30,7 @@ class _Timers(ctypes.Structure):
     _fields_ = [(k, ctypes.c_double) for k in (
         "total_s", "root_finding_s", "ev_extract_s", "backtransform_s", "backtransform_ev_s", "gemm_s",
         "gemm_flop", "leaf_s", "deflation_s", "pack_s", "residual_s", "device_s", "pack_bytes", "ugen_bytes",
-        "secular_root_iters")] + [("kernel_launches", ctypes.c_long)]
+        "secular_root_iters")] + [("kernel_launches", ctypes.c_long), ("apply_s", ctypes.c_double)]
 
 
 _BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
@@ -75,6 +76,8 @@ def _declare(lib):
         "cuppen_local_rows": [H, ip, ip],
         "cuppen_local_row_map": [H, ip],
         "cuppen_copy_eigenvectors": [H, dp, ctypes.c_long],
+        "cuppen_select_eigenvectors": [H, ip, ctypes.c_int],
+        "cuppen_copy_selected_eigenvectors": [H, dp, ctypes.c_long],
         "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_selftest_gemm": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
@@ -95,6 +98,7 @@ EXPORTED_SYMBOLS = (
     "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors",
+    "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors",
     "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_selftest_gemm", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
@@ -152,14 +156,18 @@ class CuppenSolver:
     ref_leaves   P of the reference run ``mpirun -n P cuppens`` whose divide tree, theta rule and
                  deflation thresholds are reproduced at the top log2(P) levels (1: none)
     vectors      materialise eigenvectors (the reference's ``-e``)
+    select       selected-eigenvector mode (the reference's ``-eFILE``): no n x n matrix, see ``select()``
     """
 
     def __init__(self, n, ref_leaves=1, vectors=True, residuals=True, device=0, rank=0, world=1,
-                 nccl_id=None, callbacks=None, lib=None):
+                 nccl_id=None, callbacks=None, lib=None, select=False):
         self.lib = lib or load_library()
         self.n = int(n)
-        self.vectors = bool(vectors)
-        flags = (FLAG_VECTORS if vectors else 0) | (0 if residuals else FLAG_NO_RESIDUALS)
+        self.select_mode = bool(select)
+        vectors = bool(vectors) and not self.select_mode
+        self.vectors = vectors
+        self._nsel = 0
+        flags = (FLAG_VECTORS if vectors else 0) | (0 if residuals else FLAG_NO_RESIDUALS) | (FLAG_SELECT if select else 0)
         self._h = ctypes.c_void_p()
         self._cb = None
         if callbacks is not None:
@@ -197,6 +205,19 @@ class CuppenSolver:
 
     def solve(self):
         _chk(self.lib, self.lib.cuppen_solve(self._h))
+
+    def select(self, indices):
+        """0-based ranks (ascending-lambda order) of the eigenvectors wanted from the next solve()."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32).ravel()
+        _chk(self.lib, self.lib.cuppen_select_eigenvectors(self._h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), idx.size))
+        self._nsel = int(idx.size)
+
+    def selected_eigenvectors(self):
+        """n x cnt matrix, column t = eigenvector of the t-th selected rank."""
+        V = np.empty((self.n, self._nsel), order="F")
+        if self._nsel:
+            _chk(self.lib, self.lib.cuppen_copy_selected_eigenvectors(self._h, _dp(V), self.n))
+        return V
 
     def eigenvalues(self):
         out = np.empty(self.n)
@@ -310,14 +331,20 @@ def writeResults(filename, lam, resid=None, indices=None, lib=None):
     _chk(lib, rc)
 
 
-def cuppens(D, E, ref_leaves=1, vectors=True, device=0, lib=None):
-    """Convenience: full decomposition.  Returns dict(lam, resid, V, stats, timers)."""
-    s = CuppenSolver(len(D), ref_leaves=ref_leaves, vectors=vectors, device=device, lib=lib)
+def cuppens(D, E, ref_leaves=1, vectors=True, device=0, lib=None, select=None):
+    """Convenience: full decomposition.  Returns dict(lam, resid, V, stats, timers).
+    select = list of 0-based ranks: selected-eigenvector mode, V is n x len(select), resid per selected rank."""
+    s = CuppenSolver(len(D), ref_leaves=ref_leaves, vectors=vectors, device=device, lib=lib, select=select is not None)
     try:
         s.set_tridiagonal(D, E)
+        if select is not None:
+            s.select(select)
         s.solve()
         out = dict(lam=s.eigenvalues(), stats=s.merge_stats(), timers=s.timers(), resid=None, V=None)
-        if vectors:
+        if select is not None:
+            out["resid"] = s.residuals(select) if len(select) else np.zeros(0)
+            out["V"] = s.selected_eigenvectors()
+        elif vectors:
             out["resid"] = s.residuals()
             out["V"] = s.eigenvectors()
         return out

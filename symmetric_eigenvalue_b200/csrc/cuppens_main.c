@@ -10,9 +10,12 @@
  *   -p P     number of reference MPI tasks whose divide tree is reproduced (what `mpirun -n P`
  *            was; default 1 or $CUPPENS_NUMTASKS)
  *   -g G     number of B200s (one process per GPU is forked, vectors travel over NCCL)
+ * With -eFILE and few requested indices (count <= n/16, one GPU) the library's selected-eigenvector
+ * mode is used: no n x n matrix is formed (filehandling.c:339-345 computes one vector at a time too).
  */
 #define _GNU_SOURCE
 #include <ctype.h>
+#include <fcntl.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -163,18 +166,38 @@ int main(int argc, char** argv) {
     double tic = now_s();
     if (rank == 0) printf("Start divide phase ...\n");
     cuppen_handle h = NULL;
-    const int vectors = (computeEV && writeOutput) ? CUPPEN_FLAG_VECTORS : 0;
+    int vectors = (computeEV && writeOutput) ? CUPPEN_FLAG_VECTORS : 0;
+    /* -eFILE: look at the index file now (quietly -- its WARNING lines belong to the write phase, where the
+     * reference parses it, filehandling.c:339) to decide between the full and the selected-eigenvector mode */
+    int selectMode = 0, selCount = 0;
+    int* selIdx = NULL;
+    if (vectors && evFile != NULL && gpus == 1) {
+        fflush(stdout);
+        int keep = dup(1), nul = open("/dev/null", O_WRONLY);
+        if (keep >= 0 && nul >= 0) {
+            dup2(nul, 1);
+            int ok = cuppen_read_ev_file(evFile, n, &selIdx, &selCount);
+            fflush(stdout);
+            dup2(keep, 1);
+            if (ok == 0 && selCount == 0) vectors = 0;                       /* nothing valid requested */
+            else if (ok == 0 && selCount <= n / 16) { selectMode = 1; vectors = 0; }
+        }
+        if (keep >= 0) close(keep);
+        if (nul >= 0) close(nul);
+    }
+    const int createFlags = selectMode ? CUPPEN_FLAG_SELECT : vectors;
     if (gpus > 1) {
         if (rank == 0) {
             if (cuppen_nccl_unique_id(id) != 0) { fprintf(stderr, "%s\n", cuppen_last_error()); return 5; }
             for (i = 1; i < gpus; ++i) xwrite(down[i][1], id, sizeof id);
         } else xread(down[rank][0], id, sizeof id);
-        rc = cuppen_create_nccl(&h, n, numtasks, vectors, rank, rank, gpus, id);
-    } else rc = cuppen_create(&h, n, numtasks, vectors, 0);
+        rc = cuppen_create_nccl(&h, n, numtasks, createFlags, rank, rank, gpus, id);
+    } else rc = cuppen_create(&h, n, numtasks, createFlags, 0);
     if (rc == CUPPEN_ERR_LEAF) { fprintf(stderr, "Leaf Size is too small! Reduce number of tasks.\n"); return 4; }
     if (rc != 0) { fprintf(stderr, "cuppens: %s\n", cuppen_last_error()); return 5; }
     if (rank == 0) printf("Average leaf size will be %.1lf\n", n * 1.0 / numtasks);
     rc = cuppen_set_tridiagonal(h, D, E);
+    if (rc == 0 && selectMode) rc = cuppen_select_eigenvectors(h, selIdx, selCount);
     if (rc != 0) { fprintf(stderr, "cuppens: %s\n", cuppen_last_error()); return 5; }
     if (rank == 0) {
         printf("Apply QR algorithm on leaves ...\n");
@@ -191,7 +214,7 @@ int main(int argc, char** argv) {
     cuppen_get_timers(h, &tm);
     double elapsed = toc - tic;
     /* with -e the back-transformation runs inside the conquer loop; report it separately as the reference does */
-    double evalTime = vectors ? elapsed - tm.backtransform_s : elapsed;
+    double evalTime = (vectors || selectMode) ? elapsed - tm.backtransform_s : elapsed;
     if (evalTime <= 0) evalTime = elapsed;
     printf("\n");
     printf("Required time to compute all eigenvalues: %f seconds\n", evalTime);
@@ -213,7 +236,7 @@ int main(int argc, char** argv) {
         if (computeEV && evFile != NULL) {
             if (cuppen_read_ev_file(evFile, n, &indices, &count) != 0) return 3;
         }
-        if (vectors) {
+        if (vectors || selectMode) {
             resid = (double*)malloc((size_t)n * sizeof(double));
             if (cuppen_get_residuals(h, NULL, n, resid) != 0) { fprintf(stderr, "cuppens: %s\n", cuppen_last_error()); return 5; }
         }
@@ -224,7 +247,7 @@ int main(int argc, char** argv) {
             printf("Required time eigenvector extraction from U_i's within backtransformation: %f seconds; fraction: %.1f%%\n",
                    tm.backtransform_ev_s, tm.backtransform_s > 0 ? 100 * tm.backtransform_ev_s / tm.backtransform_s : 0.0);
         }
-        free(lambda); free(resid); free(indices);
+        free(lambda); free(resid); free(indices); free(selIdx);
     }
     cuppen_destroy(h);
     for (i = 1; i < gpus; ++i) { int st; waitpid(kids[i], &st, 0); }

@@ -60,7 +60,7 @@ inline int host_leaf_ql(int nl, double* d, double* e, double* q /* row-major nl 
 }
 
 inline void leaf_ql_host(const LeafDesc* leaves, int nleaves, const double* Dm, const double* E, double* lam,
-                         double* frow, double* lrow, double* Q, long ldq, int R0, int* fail) {
+                         double* frow, double* lrow, double* Q, long ldq, int R0, int* fail, int compact) {
     for (int leaf = 0; leaf < nleaves; ++leaf) {
         const int off = leaves[leaf].off, nl = leaves[leaf].n;
         std::vector<double> d(Dm + off, Dm + off + nl), e(nl, 0.0), q((size_t)nl * nl, 0.0);
@@ -72,7 +72,7 @@ inline void leaf_ql_host(const LeafDesc* leaves, int nleaves, const double* Dm, 
             lam[off + c] = d[c];
             frow[off + c] = q[c];
             lrow[off + c] = q[(size_t)(nl - 1) * nl + c];
-            if (Q) for (int r = 0; r < nl; ++r) Q[(long)(off + r - R0) + (long)(off + c) * ldq] = q[(size_t)r * nl + c];
+            if (Q) for (int r = 0; r < nl; ++r) Q[(long)(off + r - R0) + (long)(compact ? c : off + c) * ldq] = q[(size_t)r * nl + c];
         }
     }
 }

@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
                                                       const double* __restrict__ Dm, const double* __restrict__ E,
                                                       double* __restrict__ lam, double* __restrict__ frow,
                                                       double* __restrict__ lrow, double* __restrict__ Q, long ldq,
-                                                      int R0, int* __restrict__ fail) {
+                                                      int R0, int* __restrict__ fail, int compact) {
     __shared__ double sq[4][LEAF_MAX][LEAF_MAX + 1];
     __shared__ double sd[4][LEAF_MAX];
     __shared__ double se[4][LEAF_MAX + 1];
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
     }
     const int grow = off + lane;          // global row of this lane
     if (Q != nullptr && lane < nl)
-        for (int c = 0; c < nl; ++c) Q[(long)(grow - R0) + (long)(off + c) * ldq] = q[lane][c];
+        for (int c = 0; c < nl; ++c) Q[(long)(grow - R0) + (long)(compact ? c : off + c) * ldq] = q[lane][c];   // compact: (row, c) at row + c*ldq
 }
 
 // K3: one warp per secular root; poles and weights of the merge staged in shared memory when

@@ -61,6 +61,7 @@ struct LevelCtx {
     int* lsort;            // [n] off+p -> local index of the p-th z-live entry in ascending d
     int* head;             // [n] 1 if the element starts a rotation chain (singletons included)
     int* sup;              // [n] support bits of the chain ending at this element
+    int* prev;             // [n] local index of the element rotated into this one (G[prev] == this), -1 at a chain head
     int* tpos;             // [n] per element: position in the top K-list or -1
     int* bpos;             // [n] per element: position in the bottom K-list or -1
     // canonical live problem (rho>0, poles ascending), indexed off+ci
@@ -97,6 +98,7 @@ struct ZAssemble {
         c.G[g] = -1;
         c.head[g] = 0;
         c.sup[g] = 0;
+        c.prev[g] = -1;
         c.tpos[g] = -1;
         c.bpos[g] = -1;
     }
@@ -217,6 +219,7 @@ struct GivensSweep {
             else fire = fabs((dq - dc) * cs * sn) <= D.tol;
             if (fire) {
                 c.G[off + e] = eq;
+                c.prev[off + eq] = e;
                 c.gc[off + e] = cs;
                 c.gs[off + e] = sn;
                 double ti = cs * cs * dc + sn * sn * dq;                    // :126-127

@@ -13,6 +13,7 @@
 #include "plan.h"
 #include "merge_stages.h"
 #include "matrix_stages.h"
+#include "select_stages.h"
 #include "gemm_dmma.h"
 #include "gemm_tma.h"
 #include "host_twins.h"
@@ -28,7 +29,7 @@ static double wall_now() {
 }
 
 // ---- per-category device timers (CUDA events on the solver's stream) ---------------------------
-enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_NCAT };
+enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_APPLY, T_NCAT };
 struct PhaseTimers {
     double acc[T_NCAT] = {0};
     bool capturing = false;     // stream capture in progress: record events as external graph nodes
@@ -70,6 +71,7 @@ struct PhaseTimers {
 struct Solver {
     int n = 0, P = 1, flags = 0, device = 0;
     bool want_vectors = false;
+    bool select_mode = false;     // CUPPEN_FLAG_SELECT: eigenvalue-only solve + back-application of the selected columns
     Comm comm;
     Plan plan;
     bool have_matrix = false, solved = false;
@@ -96,7 +98,19 @@ struct Solver {
     DevBuf<double> dDm, dE, dOD, dOE;
     DevBuf<double> lam, lam_sorted, frow, lrow, frow2, lrow2, fpack, lpack;
     DevBuf<double> d, z, dn, zn, gc, gs, dl, wl, zl, tau, zhat, nrm, res2, halo, halo_all;
-    DevBuf<int> G_, lsort, head, sup, tpos, bpos, lidx, org, toplist, botlist, perm, fail;
+    DevBuf<int> G_, lsort, head, sup, prev, tpos, bpos, lidx, org, toplist, botlist, perm, fail;
+    // selected-eigenvector mode: the per-level scratch vectors above get one slice per level (stride
+    // lvl_stride) so that every level's U stays defined after the solve
+    size_t lvl_stride = 0;
+    int lvl_cap = 1;
+    std::vector<int> h_sel;                  // requested ranks (ascending-lambda order), caller's order
+    DevBuf<int> sel_dev, leaf_off_dev, leaf_n_dev;
+    DevBuf<double> Qleaf, selX, selY, selXS, selGam, sel_dorg, Vsel, res_sel;
+    std::vector<double> h_res_sel;
+    void enqueue_apply();
+#if CUPPEN_CUDA
+    cudaEvent_t ev_ap0 = nullptr, ev_ap1 = nullptr;
+#endif
     DevBuf<double> Qa, Qb, Apack, B;
     DevBuf<LeafDesc> leaves;
     DevBuf<GemmProblem> probs;
@@ -211,11 +225,23 @@ void Solver::init_layout() {
 
 void Solver::allocate() {
     const size_t N = (size_t)n;
-    for (DevBuf<double>* b : {&dDm, &dE, &dOD, &dOE, &lam, &lam_sorted, &frow, &lrow, &frow2, &lrow2, &fpack, &lpack, &d, &z,
-                              &dn, &zn, &gc, &gs, &dl, &wl, &zl, &tau, &zhat, &nrm, &res2})
+    for (DevBuf<double>* b : {&dDm, &dE, &dOD, &dOE, &lam, &lam_sorted, &frow, &lrow, &frow2, &lrow2, &fpack, &lpack, &res2})
         b->alloc(N + 64);
-    for (DevBuf<int>* b : {&G_, &lsort, &head, &sup, &tpos, &bpos, &lidx, &org, &toplist, &botlist, &perm})
-        b->alloc(N + 64);
+    perm.alloc(N + 64);
+    // scratch vectors of a level: shared by all levels, or one slice per level in selected-eigenvector mode
+    lvl_stride = N + 64;
+    lvl_cap = select_mode ? (int)plan.by_height.size() + 1 : 1;
+    for (DevBuf<double>* b : {&d, &z, &dn, &zn, &gc, &gs, &dl, &wl, &zl, &tau, &zhat, &nrm})
+        b->alloc(lvl_stride * lvl_cap);
+    for (DevBuf<int>* b : {&G_, &lsort, &head, &sup, &prev, &tpos, &bpos, &lidx, &org, &toplist, &botlist})
+        b->alloc(lvl_stride * lvl_cap);
+    if (select_mode) {
+        Qleaf.alloc(N * LEAF_MAX + 64);
+        leaf_off_dev.alloc(N + 64);
+        leaf_n_dev.alloc(N + 64);
+        for (DevBuf<double>* b : {&selX, &selY, &selXS, &selGam}) b->alloc(N * SEL_NV + 64);
+        sel_dorg.alloc(N + 64);
+    }
     fail.alloc(4);
     halo.alloc(2 * N * (size_t)std::max(1, G) + 64);
     halo_all.alloc(2 * N * (size_t)G * (size_t)G + 64);
@@ -268,6 +294,8 @@ Solver::~Solver() {
     if (pin_desc) cudaFreeHost(pin_desc);
     if (ev_begin) cudaEventDestroy(ev_begin);
     if (ev_end) cudaEventDestroy(ev_end);
+    if (ev_ap0) cudaEventDestroy(ev_ap0);
+    if (ev_ap1) cudaEventDestroy(ev_ap1);
 #else
     free(pin_lam); free(pin_res); free(pin_fail); free(pin_desc);
 #endif
@@ -307,11 +335,13 @@ void Solver::set_matrix(const double* D, const double* E) {
 
 LevelCtx Solver::level_ctx(int li) {
     LevelCtx c;
+    if (select_mode && li >= lvl_cap) CUPPEN_THROW(CUPPEN_ERR_STATE, "level %d beyond the %d per-level slices", li, lvl_cap);
+    const size_t o = select_mode ? (size_t)li * lvl_stride : 0;
     c.n = n; c.desc = desc_all.p + levels[li].desc_off; c.node_of = node_of_all.p + (size_t)li * n; c.lam = lam.p; c.frow = frow.p; c.lrow = lrow.p;
-    c.d = d.p; c.z = z.p; c.dn = dn.p; c.zn = zn.p; c.G = G_.p; c.gc = gc.p; c.gs = gs.p; c.lsort = lsort.p;
-    c.head = head.p; c.sup = sup.p; c.tpos = tpos.p; c.bpos = bpos.p; c.dl = dl.p; c.wl = wl.p; c.zl = zl.p;
-    c.lidx = lidx.p; c.org = org.p; c.tau = tau.p; c.zhat = zhat.p; c.nrm = nrm.p; c.toplist = toplist.p;
-    c.botlist = botlist.p;
+    c.d = d.p + o; c.z = z.p + o; c.dn = dn.p + o; c.zn = zn.p + o; c.G = G_.p + o; c.gc = gc.p + o; c.gs = gs.p + o; c.lsort = lsort.p + o;
+    c.head = head.p + o; c.sup = sup.p + o; c.prev = prev.p + o; c.tpos = tpos.p + o; c.bpos = bpos.p + o; c.dl = dl.p + o; c.wl = wl.p + o; c.zl = zl.p + o;
+    c.lidx = lidx.p + o; c.org = org.p + o; c.tau = tau.p + o; c.zhat = zhat.p + o; c.nrm = nrm.p + o; c.toplist = toplist.p + o;
+    c.botlist = botlist.p + o;
     return c;
 }
 
@@ -327,13 +357,16 @@ void Solver::run_leaves() {
     dev_zero(fail.p, sizeof(int) * 4, stream);
     if (hl.empty()) return;
     pt.begin(T_LEAF, stream);
-    double* Q = want_vectors ? Qcur : nullptr;
+    // selected-eigenvector mode keeps the leaf eigenvectors compactly: (row, column c of its leaf) at row + c*n
+    double* Q = want_vectors ? Qcur : (select_mode ? Qleaf.p : nullptr);
+    const long ldleaf = select_mode ? (long)n : ldq;
+    const int compact = select_mode ? 1 : 0;
 #if CUPPEN_CUDA
     leaf_ql_kernel<<<(unsigned)((hl.size() + 3) / 4), 128, 0, stream>>>(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p,
-                                                                       lrow.p, Q, ldq, R0, fail.p);
+                                                                       lrow.p, Q, ldleaf, R0, fail.p, compact);
     CUDA_CHECK(cudaGetLastError());
 #else
-    leaf_ql_host(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p, lrow.p, Q, ldq, R0, fail.p);
+    leaf_ql_host(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p, lrow.p, Q, ldleaf, R0, fail.p, compact);
 #endif
     g_launches.launches++;
     pt.end(stream);
@@ -382,6 +415,14 @@ void Solver::prepare_levels() {
         else if (nd.off < R1 && nd.off + nd.n > R0) CUPPEN_THROW(CUPPEN_ERR_STATE, "leaf straddles a rank boundary");
     }
     if (!h_leaves.empty()) dev_h2d(leaves.p, h_leaves.data(), sizeof(LeafDesc) * h_leaves.size(), stream);
+    if (select_mode) {
+        std::vector<int> lo(n, 0), ln(n, 0);
+        for (const LeafDesc& lf : h_leaves)
+            for (int r = lf.off; r < lf.off + lf.n; ++r) { lo[r] = lf.off; ln[r] = lf.n; }
+        dev_h2d(leaf_off_dev.p, lo.data(), sizeof(int) * n, stream);
+        dev_h2d(leaf_n_dev.p, ln.data(), sizeof(int) * n, stream);
+        dev_sync(stream);
+    }
     // (phase, height) -> level; phase 0: nodes inside my subtree, phase 1: nodes above the subtrees
     std::map<std::pair<int, int>, std::vector<int>> groups;
     for (size_t id = 0; id < plan.nodes.size(); ++id) {
@@ -783,6 +824,46 @@ void Solver::materialise_sorted() {
     sorted_materialised = true;
 }
 
+// selected-eigenvector mode: push the unit vectors of the requested columns of the root down the tree
+// (select_stages.h).  Runs after the (possibly graph-replayed) eigenvalue solve on the same stream.
+void Solver::enqueue_apply() {
+    const int cnt = (int)h_sel.size();
+    if (!select_mode || cnt == 0) return;
+#if CUPPEN_CUDA
+    if (!ev_ap0) { CUDA_CHECK(cudaEventCreate(&ev_ap0)); CUDA_CHECK(cudaEventCreate(&ev_ap1)); }
+    CUDA_CHECK(cudaEventRecord(ev_ap0, stream));
+#endif
+    for (int v0 = 0; v0 < cnt; v0 += SEL_NV) {
+        SelCtx s;
+        s.n = n; s.nv = std::min((int)SEL_NV, cnt - v0); s.sel = sel_dev.p + v0; s.perm = perm.p;
+        s.X = selX.p; s.Y = selY.p; s.XS = selXS.p; s.Gam = selGam.p; s.dorg = sel_dorg.p;
+        launch_items(stream, n, ApplyInit{s});
+        for (int li = (int)levels.size() - 1; li >= 0; --li) {
+            const LevelInfo& L = levels[li];
+            if (L.ids.empty()) continue;
+            LevelCtx c = level_ctx(li);
+            launch_items(stream, n, ApplyPrep{c, s});
+#if CUPPEN_CUDA
+            {
+                dim3 grid((unsigned)((L.maxm + CA_TJ - 1) / CA_TJ), (unsigned)L.ids.size());
+                cauchy_apply_kernel<<<grid, CA_TJ, 0, stream>>>(c, s);
+                CUDA_CHECK(cudaGetLastError());
+            }
+#else
+            cauchy_apply_host(c, s, (int)L.ids.size());
+#endif
+            g_launches.launches++;
+            launch_items(stream, n, ApplyChains{c, s});
+            std::swap(s.X, s.Y);
+        }
+        launch_items(stream, n, LeafApply{s, leaf_off_dev.p, leaf_n_dev.p, Qleaf.p, Vsel.p + (size_t)v0 * n});
+    }
+    launch_warps(stream, cnt, SelResidual{n, Vsel.p, dOD.p, dOE.p, lam_sorted.p, sel_dev.p, res_sel.p});
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaEventRecord(ev_ap1, stream));
+#endif
+}
+
 // everything a solve does on the device, enqueued on `stream` without a single host synchronisation
 void Solver::enqueue_solve() {
 #if CUPPEN_CUDA
@@ -845,10 +926,18 @@ void Solver::solve() {
     }
 #endif
     if (!replayed) enqueue_solve();
+    const double t_ap = wall_now();
+    enqueue_apply();
     const double t1 = wall_now();
     dev_sync(stream);
     pt.collect();
     const double t2 = wall_now();
+    if (select_mode && !h_sel.empty()) {
+        h_res_sel.resize(h_sel.size());
+        dev_d2h(h_res_sel.data(), res_sel.p, sizeof(double) * h_sel.size(), stream);
+        dev_sync(stream);
+        for (double& r : h_res_sel) r = sqrt(r);
+    }
     solves_done++;
     h_lam_sorted.assign(pin_lam, pin_lam + n);
     h_resid.clear();
@@ -889,7 +978,14 @@ void Solver::solve() {
     timers.gemm_flop = acc_gemm_flop;
 #if CUPPEN_CUDA
     { float ms = 0; cudaEventElapsedTime(&ms, ev_begin, ev_end); timers.device_s = ms * 1e-3; }
+    if (select_mode && !h_sel.empty()) {
+        float ms = 0; cudaEventElapsedTime(&ms, ev_ap0, ev_ap1);
+        timers.apply_s = ms * 1e-3;
+        timers.device_s += timers.apply_s;
+        timers.backtransform_s = timers.apply_s;
+    }
 #else
+    if (select_mode && !h_sel.empty()) { timers.apply_s = t2 - t_ap; timers.backtransform_s = timers.apply_s; }
     timers.device_s = t2 - t0;
 #endif
 #if CUPPEN_CUDA
@@ -922,6 +1018,10 @@ static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int
     CUPPEN_API_BEGIN
     if (!h || n < 1 || ref_leaves < 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument (n=%d, ref_leaves=%d)", n, ref_leaves);
     if (n / ref_leaves == 0) CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
+    if ((flags & CUPPEN_FLAG_SELECT) && (flags & CUPPEN_FLAG_VECTORS))
+        CUPPEN_THROW(CUPPEN_ERR_ARG, "CUPPEN_FLAG_SELECT and CUPPEN_FLAG_VECTORS are exclusive");
+    if ((flags & CUPPEN_FLAG_SELECT) && comm.world > 1)
+        CUPPEN_THROW(CUPPEN_ERR_ARG, "selected-eigenvector mode runs on one GPU (it needs O(n) memory per vector)");
 #if CUPPEN_CUDA
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -933,6 +1033,7 @@ static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int
     cuppen_handle_s* hs = new cuppen_handle_s();
     Solver& s = hs->s;
     s.n = n; s.P = ref_leaves; s.flags = flags; s.device = device; s.want_vectors = (flags & CUPPEN_FLAG_VECTORS) != 0;
+    s.select_mode = (flags & CUPPEN_FLAG_SELECT) != 0;
     s.comm = comm;
     try {
 #if CUPPEN_CUDA
@@ -1042,6 +1143,21 @@ int cuppen_get_residuals(cuppen_handle h, const int* idx, int cnt, double* out) 
     if (!h || !out) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
     Solver& s = h->s;
     if (!s.solved) CUPPEN_THROW(CUPPEN_ERR_STATE, "not solved");
+    if (s.select_mode) {
+        // residuals exist for the selected ranks only; idx == NULL: length-n array, NaN where not selected
+        std::map<int, double> have;
+        for (size_t t = 0; t < s.h_sel.size() && t < s.h_res_sel.size(); ++t) have[s.h_sel[t]] = s.h_res_sel[t];
+        if (!idx) {
+            for (int i = 0; i < s.n; ++i) out[i] = NAN;
+            for (auto& kv : have) out[kv.first] = kv.second;
+        } else
+            for (int i = 0; i < cnt; ++i) {
+                auto it = have.find(idx[i]);
+                if (it == have.end()) CUPPEN_THROW(CUPPEN_ERR_ARG, "eigenvector %d was not selected", idx[i]);
+                out[i] = it->second;
+            }
+        return CUPPEN_OK;
+    }
     if ((int)s.h_resid.size() != s.n) CUPPEN_THROW(CUPPEN_ERR_STATE, "residuals need CUPPEN_FLAG_VECTORS");
     if (!idx) { memcpy(out, s.h_resid.data(), sizeof(double) * s.n); }
     else
@@ -1104,6 +1220,47 @@ int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld) {
     dev_sync(s.stream);
 #else
     for (int c = 0; c < s.n; ++c) memcpy(V + (long)c * ld, s.Qcur + (long)c * s.ldq, sizeof(double) * s.nloc_final);
+#endif
+    CUPPEN_API_END
+}
+
+int cuppen_select_eigenvectors(cuppen_handle h, const int* idx, int cnt) {
+    CUPPEN_API_BEGIN
+    if (!h || cnt < 0 || (cnt > 0 && !idx)) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
+    Solver& s = h->s;
+    if (!s.select_mode) CUPPEN_THROW(CUPPEN_ERR_STATE, "the handle was not created with CUPPEN_FLAG_SELECT");
+    for (int i = 0; i < cnt; ++i)
+        if (idx[i] < 0 || idx[i] >= s.n) CUPPEN_THROW(CUPPEN_ERR_ARG, "eigenvector index %d out of range", idx[i]);
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(s.device));
+#endif
+    s.h_sel.assign(idx, idx + cnt);
+    s.h_res_sel.clear();
+    if (cnt > 0) {
+        if (s.sel_dev.n < (size_t)cnt + SEL_NV) { s.sel_dev.alloc((size_t)cnt + SEL_NV); s.res_sel.alloc((size_t)cnt + SEL_NV); }
+        if (s.Vsel.n < (size_t)cnt * s.n) s.Vsel.alloc((size_t)cnt * s.n);
+        dev_h2d(s.sel_dev.p, s.h_sel.data(), sizeof(int) * cnt, s.stream);
+        dev_sync(s.stream);
+    }
+    s.solved = false;
+    CUPPEN_API_END
+}
+
+int cuppen_copy_selected_eigenvectors(cuppen_handle h, double* V, long ld) {
+    CUPPEN_API_BEGIN
+    if (!h || !V) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    Solver& s = h->s;
+    if (!s.select_mode || !s.solved) CUPPEN_THROW(CUPPEN_ERR_STATE, "no selected eigenvectors (CUPPEN_FLAG_SELECT, select, solve)");
+    if (ld < s.n) CUPPEN_THROW(CUPPEN_ERR_ARG, "ld too small");
+    const size_t cnt = s.h_sel.size();
+    if (cnt == 0) return CUPPEN_OK;
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(s.device));
+    CUDA_CHECK(cudaMemcpy2DAsync(V, sizeof(double) * ld, s.Vsel.p, sizeof(double) * s.n, sizeof(double) * s.n, cnt,
+                                 cudaMemcpyDeviceToHost, s.stream));
+    dev_sync(s.stream);
+#else
+    for (size_t t = 0; t < cnt; ++t) memcpy(V + (long)t * ld, s.Vsel.p + t * s.n, sizeof(double) * s.n);
 #endif
     CUPPEN_API_END
 }

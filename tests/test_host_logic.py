@@ -181,3 +181,57 @@ def test_hostemu_edge_cases(hostemu):
     with pytest.raises(se.CuppenError) as ei:
         s.set_tridiagonal(D, E)
     assert ei.value.code == -3
+
+
+# ---- selected-eigenvector mode (-eFILE): back-application of the implicit U factors ---------------------
+@pytest.mark.parametrize("gen,n,P", [("goe", 300, 4), ("s1", 500, 8), ("s2", 256, 4), ("rand_u", 333, 1), ("wilk", 257, 2),
+                                     ("goe", 40, 1), ("s2", 1000, 3), ("goe", 1, 1)])
+def test_hostemu_select_mode_matches_full_mode(hostemu, oracle, gen, n, P):
+    """The selected columns must be the same vectors the full back-transformation produces (same formulas,
+    different association order: a few ulp), with the same residuals, and the eigenvalue path must not change."""
+    D, E = {"goe": oracle.goe, "rand_u": oracle.rand_u, "wilk": lambda k: oracle.wilkinson(k, norm=64.0),
+            "s1": lambda k: oracle.scheme(1, k), "s2": lambda k: oracle.scheme(2, k)}[gen](n)
+    full = se.cuppens(D, E, ref_leaves=P, lib=hostemu)
+    rng = np.random.default_rng(n)
+    sel = [0, n - 1] + rng.integers(0, n, size=min(n, 19)).tolist()          # unsorted, duplicates, > SEL_NV: three passes
+    out = se.cuppens(D, E, ref_leaves=P, lib=hostemu, select=sel)
+    assert np.array_equal(out["lam"], full["lam"])
+    assert ref_stats(out["stats"]) == ref_stats(full["stats"])
+    assert out["V"].shape == (n, len(sel))
+    assert np.abs(out["V"] - full["V"][:, sel]).max() < 5e-14
+    assert np.allclose(out["resid"], full["resid"][sel], rtol=1e-3, atol=1e-13 * norm_T(D, E))
+
+
+def test_hostemu_select_mode_api(hostemu, oracle):
+    D, E = oracle.goe(200)
+    s = se.CuppenSolver(200, ref_leaves=2, lib=hostemu, select=True)
+    s.set_tridiagonal(D, E)
+    s.solve()                                        # nothing selected: eigenvalues only
+    lam = s.eigenvalues()
+    assert s.selected_eigenvectors().shape == (200, 0)
+    with pytest.raises(se.CuppenError) as ei:
+        s.select([200])
+    assert ei.value.code == -1
+    s.select([5, 7])
+    with pytest.raises(se.CuppenError) as ei:       # a new selection needs a new solve
+        s.eigenvalues()
+    assert ei.value.code == -5
+    s.solve()
+    assert np.array_equal(lam, s.eigenvalues())
+    r = s.residuals()
+    assert np.isfinite(r[[5, 7]]).all() and np.isnan(np.delete(r, [5, 7])).all()
+    assert np.array_equal(s.residuals([7, 5]), r[[7, 5]])
+    with pytest.raises(se.CuppenError) as ei:
+        s.residuals([6])
+    assert ei.value.code == -1
+    V = s.selected_eigenvectors()
+    T = np.diag(D) + np.diag(E, 1) + np.diag(E, -1)
+    assert np.allclose(np.linalg.norm(T @ V - V * lam[[5, 7]], axis=0), r[[5, 7]], rtol=1e-6, atol=1e-14)
+    s.close()
+    full = se.CuppenSolver(200, ref_leaves=2, lib=hostemu)
+    with pytest.raises(se.CuppenError) as ei:       # not a select handle
+        full.select([1])
+    assert ei.value.code == -5
+    full.close()
+    h = __import__("ctypes").c_void_p()
+    assert hostemu.cuppen_create(__import__("ctypes").byref(h), 64, 1, api.FLAG_VECTORS | api.FLAG_SELECT, 0) == -1
