@@ -293,6 +293,11 @@ def run_ours(a):
         "clocks": clocks,
         "check": {"max_residual": float(res.max()), "lambda_min": float(lam[0]), "lambda_max": float(lam[-1])},
     }
+    if world == 1:
+        dev, sec = solver.orthogonality()              # on-GPU max|V^T V - I| of the last decomposition (gram_check_kernel)
+        line["check"]["orthogonality_max_abs"] = dev
+        line["check"]["orthogonality_check_s"] = sec
+        line["check"]["orthogonality_check_tflops"] = (a.n ** 3 + a.n ** 2 * 128.0) / sec * 1e-12 if sec > 0 else None
     if world == 1 and a.select > 0:
         line["selected_mode"] = selected_mode(a, D, E, local, res)
     if world == 1 and not a.no_cpu_baseline:

@@ -153,6 +153,13 @@ int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld);
  * cuppen_copy_selected_eigenvectors returns the n x cnt matrix (column t = eigenvector of rank idx[t], column-major, ld >= n). */
 int cuppen_select_eigenvectors(cuppen_handle h, const int* idx, int cnt);
 int cuppen_copy_selected_eigenvectors(cuppen_handle h, double* V, long ld);
+/* max_ij |(V^T V - I)_ij| of the computed eigenvector matrix, evaluated on the GPU by a DMMA Gram kernel that never
+ * writes the product (BASELINE's orthogonality criterion; no counterpart in the reference, which cannot emit V).
+ * One GPU, CUPPEN_FLAG_VECTORS.  seconds (may be NULL): device time of the check. */
+int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds);
+/* Eigenvector file (binary): "CUPPENV1" | int64 n | int64 ncols | int64 rank[ncols] | double lambda[ncols] |
+ * double V[ncols][n].  All n vectors (CUPPEN_FLAG_VECTORS, ascending lambda) or the selected ones (CUPPEN_FLAG_SELECT). */
+int cuppen_write_eigenvectors(cuppen_handle h, const char* filename);
 const char* cuppen_last_error(void);
 
 /* FP64 yardsticks measured on the device: register-resident DMMA.8x8x4 issue loop and DFMA loop,

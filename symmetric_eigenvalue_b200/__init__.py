@@ -8,11 +8,11 @@ There is no CPU implementation in this package: without the CUDA library every c
 from .api import (  # noqa: F401
     CuppenError, CuppenSolver, MergeStat, createMatrixScheme1, createMatrixScheme2,
     readSymmTriadiagonalMatrixFromSparseMTX, determineEigenvectorsToCompute, writeResults,
-    nccl_unique_id, load_library, library_path, cuppens,
+    nccl_unique_id, load_library, library_path, cuppens, read_eigenvector_file,
 )
 
 __all__ = [
     "CuppenError", "CuppenSolver", "MergeStat", "createMatrixScheme1", "createMatrixScheme2",
     "readSymmTriadiagonalMatrixFromSparseMTX", "determineEigenvectorsToCompute", "writeResults",
-    "nccl_unique_id", "load_library", "library_path", "cuppens",
+    "nccl_unique_id", "load_library", "library_path", "cuppens", "read_eigenvector_file",
 ]

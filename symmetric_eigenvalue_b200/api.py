@@ -78,6 +78,8 @@ def _declare(lib):
         "cuppen_copy_eigenvectors": [H, dp, ctypes.c_long],
         "cuppen_select_eigenvectors": [H, ip, ctypes.c_int],
         "cuppen_copy_selected_eigenvectors": [H, dp, ctypes.c_long],
+        "cuppen_orthogonality": [H, dp, dp],
+        "cuppen_write_eigenvectors": [H, ctypes.c_char_p],
         "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_selftest_gemm": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
@@ -98,7 +100,7 @@ EXPORTED_SYMBOLS = (
     "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors",
-    "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors",
+    "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors", "cuppen_orthogonality", "cuppen_write_eigenvectors",
     "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_selftest_gemm", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
@@ -219,6 +221,15 @@ class CuppenSolver:
             _chk(self.lib, self.lib.cuppen_copy_selected_eigenvectors(self._h, _dp(V), self.n))
         return V
 
+    def orthogonality(self):
+        """(max |V^T V - I|, device seconds) -- evaluated on the GPU, the product is never formed."""
+        a, b = ctypes.c_double(0), ctypes.c_double(0)
+        _chk(self.lib, self.lib.cuppen_orthogonality(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def write_eigenvectors(self, filename):
+        _chk(self.lib, self.lib.cuppen_write_eigenvectors(self._h, os.fsencode(filename)))
+
     def eigenvalues(self):
         out = np.empty(self.n)
         _chk(self.lib, self.lib.cuppen_get_eigenvalues(self._h, _dp(out)))
@@ -329,6 +340,20 @@ def writeResults(filename, lam, resid=None, indices=None, lib=None):
         rc = lib.cuppen_write_results(os.fsencode(filename), n, _dp(lam), rp, 0,
                                       idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), idx.size)
     _chk(lib, rc)
+
+
+def read_eigenvector_file(filename):
+    """Reader of the CUPPENV1 file written by cuppen_write_eigenvectors / `cuppens -v`: (ranks, lam, V[n, ncols])."""
+    with open(filename, "rb") as f:
+        if f.read(8) != b"CUPPENV1":
+            raise CuppenError(-2, "%s is not a CUPPENV1 eigenvector file" % filename)
+        n, ncols = (int(x) for x in np.fromfile(f, dtype="<i8", count=2))
+        ranks = np.fromfile(f, dtype="<i8", count=ncols)
+        lam = np.fromfile(f, dtype="<f8", count=ncols)
+        V = np.fromfile(f, dtype="<f8", count=n * ncols)
+    if V.size != n * ncols:
+        raise CuppenError(-2, "%s is truncated" % filename)
+    return ranks, lam, V.reshape(ncols, n).T
 
 
 def cuppens(D, E, ref_leaves=1, vectors=True, device=0, lib=None, select=None):

@@ -6,10 +6,13 @@
  *   stdout   the progress / timer lines of main.c:149-163,193-194,224,241,329,435,485,675-678,
  *            683-684,695 and filehandling.c:566-568
  *   exit     1 bad option, 2 unreadable input, 3 output / -e file, 4 "Leaf Size is too small"
- * Two additions that do not collide with the reference's options:
+ * Additions that do not collide with the reference's options:
  *   -p P     number of reference MPI tasks whose divide tree is reproduced (what `mpirun -n P`
  *            was; default 1 or $CUPPENS_NUMTASKS)
  *   -g G     number of B200s (one process per GPU is forked, vectors travel over NCCL)
+ *   -v FILE  write the computed eigenvectors (all with -e, the selected ones with -eFILE) to FILE
+ *            (binary CUPPENV1 layout, include/cuppen_b200.h) -- the reference cannot emit V
+ *   -c       print max|V^T V - I| of the computed eigenvectors (evaluated on the GPU; needs -e, one GPU)
  * With -eFILE and few requested indices (count <= n/16, one GPU) the library's selected-eigenvector
  * mode is used: no n x n matrix is formed (filehandling.c:339-345 computes one vector at a time too).
  */
@@ -60,6 +63,10 @@ static void showHelp(void) {
     printf("    rules are reproduced (default 1: accurate tolerances on all levels).\n");
     printf(" -g NUM\n");
     printf("    Number of GPUs (power of two; one process per GPU).\n");
+    printf(" -v FILENAME\n");
+    printf("    Write the computed eigenvectors to this file (binary; needs -e and one GPU).\n");
+    printf(" -c\n");
+    printf("    Check the orthogonality of the computed eigenvectors (needs -e, one GPU).\n");
     printf("\n");
 }
 
@@ -80,7 +87,8 @@ static void xread(int fd, void* p, size_t n) {
 
 int main(int argc, char** argv) {
     int n = 1000, usedScheme = 1, computeEV = 0, writeOutput = 0, numtasks = 1, gpus = 1;
-    char *inputfile = NULL, *outputfile = NULL, *evFile = NULL;
+    char *inputfile = NULL, *outputfile = NULL, *evFile = NULL, *vecFile = NULL;
+    int checkOrth = 0;
     double *D = NULL, *E = NULL;
     int c, i, rc;
     const char* envp = getenv("CUPPENS_NUMTASKS");
@@ -88,7 +96,7 @@ int main(int argc, char** argv) {
 
     if (argc == 1) { showHelp(); return 0; }
     opterr = 0;
-    while ((c = getopt(argc, argv, "hi:n:s:e::p:g:")) != -1) switch (c) {
+    while ((c = getopt(argc, argv, "hi:n:s:e::p:g:v:c")) != -1) switch (c) {
         case 'h': showHelp(); return 0;
         case 'i': inputfile = optarg; break;
         case 's':
@@ -104,6 +112,8 @@ int main(int argc, char** argv) {
             numtasks = atoi(optarg);
             if (numtasks < 1) { fprintf(stderr, "Invalid argument for option -p. See help.\n"); return 1; }
             break;
+        case 'v': vecFile = optarg; break;
+        case 'c': checkOrth = 1; break;
         case 'g':
             gpus = atoi(optarg);
             if (gpus < 1 || (gpus & (gpus - 1))) { fprintf(stderr, "Invalid argument for option -g. See help.\n"); return 1; }
@@ -180,7 +190,7 @@ int main(int argc, char** argv) {
             fflush(stdout);
             dup2(keep, 1);
             if (ok == 0 && selCount == 0) vectors = 0;                       /* nothing valid requested */
-            else if (ok == 0 && selCount <= n / 16) { selectMode = 1; vectors = 0; }
+            else if (ok == 0 && selCount <= n / 16 && !checkOrth) { selectMode = 1; vectors = 0; }
         }
         if (keep >= 0) close(keep);
         if (nul >= 0) close(nul);
@@ -248,6 +258,15 @@ int main(int argc, char** argv) {
                    tm.backtransform_ev_s, tm.backtransform_s > 0 ? 100 * tm.backtransform_ev_s / tm.backtransform_s : 0.0);
         }
         free(lambda); free(resid); free(indices); free(selIdx);
+    }
+    if ((vectors || selectMode) && vecFile != NULL) {
+        if (cuppen_write_eigenvectors(h, vecFile) != 0) { fprintf(stderr, "cuppens: %s\n", cuppen_last_error()); return 3; }
+        printf("\nEigenvectors written to: %s\n", vecFile);
+    }
+    if (vectors && checkOrth) {
+        double dev = 0, sec = 0;
+        if (cuppen_orthogonality(h, &dev, &sec) != 0) { fprintf(stderr, "cuppens: %s\n", cuppen_last_error()); return 5; }
+        printf("\nOrthogonality max|V^T V - I|: %.3e (checked in %f seconds)\n", dev, sec);
     }
     cuppen_destroy(h);
     for (i = 1; i < gpus; ++i) { int st; waitpid(kids[i], &st, 0); }

@@ -14,6 +14,7 @@
 #include "merge_stages.h"
 #include "matrix_stages.h"
 #include "select_stages.h"
+#include "orth_check.h"
 #include "gemm_dmma.h"
 #include "gemm_tma.h"
 #include "host_twins.h"
@@ -1262,6 +1263,92 @@ int cuppen_copy_selected_eigenvectors(cuppen_handle h, double* V, long ld) {
 #else
     for (size_t t = 0; t < cnt; ++t) memcpy(V + (long)t * ld, s.Vsel.p + t * s.n, sizeof(double) * s.n);
 #endif
+    CUPPEN_API_END
+}
+
+int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds) {
+    CUPPEN_API_BEGIN
+    if (!h || !max_abs_dev) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    Solver& s = h->s;
+    if (!s.solved || !s.want_vectors) CUPPEN_THROW(CUPPEN_ERR_STATE, "no eigenvectors (solve with CUPPEN_FLAG_VECTORS)");
+    if (s.G > 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "the orthogonality check runs on one GPU (rows of V are distributed over %d)", s.G);
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(s.device));
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_CHECK(cudaFuncSetAttribute(gram_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes()));
+        attr_set = true;
+    }
+    DevBuf<unsigned long long> res;
+    res.alloc(1);
+    dev_zero(res.p, sizeof(unsigned long long), s.stream);
+    const long T = (s.n + GR_BT - 1) / GR_BT, ntiles = T * (T + 1) / 2;
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, s.stream));
+    gram_check_kernel<<<(unsigned)std::min<long>(ntiles, s.num_sms), GR_THREADS, gram_smem_bytes(), s.stream>>>(
+        s.Qcur, s.ldq, s.nloc_final, s.n, res.p);
+    CUDA_CHECK(cudaGetLastError());
+    g_launches.launches++;
+    CUDA_CHECK(cudaEventRecord(e1, s.stream));
+    unsigned long long bits = 0;
+    dev_d2h(&bits, res.p, sizeof bits, s.stream);
+    dev_sync(s.stream);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    memcpy(max_abs_dev, &bits, sizeof(double));
+    if (seconds) *seconds = ms * 1e-3;
+#else
+    const double t0 = wall_now();
+    *max_abs_dev = gram_check_host(s.Qcur, s.ldq, s.nloc_final, s.n);
+    if (seconds) *seconds = wall_now() - t0;
+#endif
+    CUPPEN_API_END
+}
+
+// Eigenvector file (the reference cannot emit V, SURVEY.md finding 6).  Layout, little endian:
+//   char[8] "CUPPENV1" | int64 n | int64 ncols | int64 rank[ncols] (0-based, ascending lambda) |
+//   double lambda[ncols] | double V[ncols][n] (one eigenvector after the other)
+int cuppen_write_eigenvectors(cuppen_handle h, const char* filename) {
+    CUPPEN_API_BEGIN
+    if (!h || !filename) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    Solver& s = h->s;
+    if (!s.solved || !(s.want_vectors || s.select_mode)) CUPPEN_THROW(CUPPEN_ERR_STATE, "no eigenvectors to write");
+    if (s.G > 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "eigenvector output runs on one GPU");
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(s.device));
+#endif
+    const long long n = s.n;
+    std::vector<long long> ranks;
+    if (s.select_mode) ranks.assign(s.h_sel.begin(), s.h_sel.end());
+    else { ranks.resize(n); for (long long i = 0; i < n; ++i) ranks[i] = i; }
+    const long long ncols = (long long)ranks.size();
+    std::vector<double> lam(ncols);
+    for (long long t = 0; t < ncols; ++t) lam[t] = s.h_lam_sorted[ranks[t]];
+    FILE* f = fopen(filename, "wb");
+    if (!f) { fprintf(stderr, "Could not open file\n"); CUPPEN_THROW(CUPPEN_ERR_IO, "cannot open %s", filename); }
+    bool ok = fwrite("CUPPENV1", 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1 && fwrite(&ncols, 8, 1, f) == 1;
+    ok = ok && (ncols == 0 || (fwrite(ranks.data(), 8, ncols, f) == (size_t)ncols && fwrite(lam.data(), 8, ncols, f) == (size_t)ncols));
+    const double* src = nullptr;
+    long ld = 0;
+    if (s.select_mode) { src = s.Vsel.p; ld = s.n; }
+    else { s.materialise_sorted(); src = s.Qcur; ld = s.ldq; }
+    const long long panel = std::max<long long>(1, (64LL << 20) / (8 * n));        // <= 64 MB of host staging
+    std::vector<double> buf((size_t)std::min(panel, std::max<long long>(ncols, 1)) * n);
+    for (long long c0 = 0; ok && c0 < ncols; c0 += panel) {
+        const long long w = std::min(panel, ncols - c0);
+#if CUPPEN_CUDA
+        CUDA_CHECK(cudaMemcpy2DAsync(buf.data(), sizeof(double) * n, src + c0 * ld, sizeof(double) * ld, sizeof(double) * n, w,
+                                     cudaMemcpyDeviceToHost, s.stream));
+        dev_sync(s.stream);
+#else
+        for (long long c = 0; c < w; ++c) memcpy(buf.data() + c * n, src + (c0 + c) * ld, sizeof(double) * n);
+#endif
+        ok = fwrite(buf.data(), 8, (size_t)(w * n), f) == (size_t)(w * n);
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) CUPPEN_THROW(CUPPEN_ERR_IO, "write error on %s", filename);
     CUPPEN_API_END
 }
 

@@ -217,3 +217,57 @@ def test_select_mode_baseline_size_against_lapack(lib, oracle):
     check_against_golden(g, out, False)
     full = se.cuppens(g["D"], g["E"], ref_leaves=8, lib=lib)
     assert np.abs(out["V"] - full["V"][:, sel]).max() < 1e-12
+
+
+# ---- on-GPU orthogonality check (gram_check_kernel) and eigenvector output ------------------------------
+@pytest.mark.parametrize("gen,n,P", [("goe", 1001, 4), ("s1", 4096, 8), ("s2", 130, 1), ("wilk", 2049, 2), ("goe", 5, 1)])
+def test_orthogonality_kernel_against_numpy(lib, oracle, gen, n, P):
+    D, E = {"goe": oracle.goe, "wilk": lambda k: oracle.wilkinson(k, norm=64.0),
+            "s1": lambda k: oracle.scheme(1, k), "s2": lambda k: oracle.scheme(2, k)}[gen](n)
+    s = se.CuppenSolver(n, ref_leaves=P, lib=lib)
+    s.set_tridiagonal(D, E)
+    s.solve()
+    dev, _ = s.orthogonality()                      # storage order
+    V = s.eigenvectors()
+    dev2, _ = s.orthogonality()                     # after the sorted gather
+    want = np.abs(V.T @ V - np.eye(n)).max()
+    s.close()
+    assert abs(dev - want) <= 64 * 2.2e-16 and abs(dev2 - want) <= 64 * 2.2e-16, (dev, dev2, want)
+    assert dev < 1e-12
+
+
+def test_orthogonality_at_baseline_size(lib, oracle):
+    """BASELINE configs[2]/[3] size: ||V^T V - I|| of the n=16384 decompositions without moving V off the GPU."""
+    for gen in ("goe", "wilk"):
+        D, E = (oracle.goe(16384) if gen == "goe" else oracle.wilkinson(16384, norm=64.0))
+        s = se.CuppenSolver(16384, ref_leaves=8, lib=lib)
+        s.set_tridiagonal(D, E)
+        s.solve()
+        dev, sec = s.orthogonality()
+        r = s.residuals()
+        s.close()
+        assert dev < 1e-12, (gen, dev)              # the reference: 1e-8 ... 1e-10 (SURVEY.md finding 4)
+        assert r.max() < 1e-5 * norm_T(D, E)
+
+
+def test_cli_eigenvector_file_and_orthogonality(lib, tmp_path):
+    exe = os.path.join(ROOT, "cuppens")
+    out, vf, ev = tmp_path / "out.txt", tmp_path / "v.bin", tmp_path / "ev.txt"
+    r = subprocess.run([exe, "-p", "4", "-s", "1", "-n", "512", "-e", "-c", "-v", str(vf), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "Eigenvectors written to: " in r.stdout and "Orthogonality max|V^T V - I|: " in r.stdout
+    dev = float(r.stdout.split("Orthogonality max|V^T V - I|: ")[1].split()[0])
+    ranks, lam, V = se.read_eigenvector_file(str(vf))
+    assert V.shape == (512, 512) and abs(np.abs(V.T @ V - np.eye(512)).max() - dev) < 1e-14
+    rows = np.array([[float(x) for x in l.split()] for l in out.read_text().splitlines()])
+    assert np.array_equal(rows[:, 0], lam)
+    D, E = se.createMatrixScheme1(512, lib=lib)
+    TV = D[:, None] * V
+    TV[1:] += E[:, None] * V[:-1]
+    TV[:-1] += E[:, None] * V[1:]
+    assert np.allclose(np.linalg.norm(TV - V * lam[None, :], axis=0), rows[:, 1], rtol=1e-6, atol=1e-13)
+    ev.write_text("512\n7\n")
+    r = subprocess.run([exe, "-p", "4", "-s", "1", "-n", "512", "-e" + str(ev), "-v", str(vf), str(out)], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    ranks2, lam2, V2 = se.read_eigenvector_file(str(vf))                     # selected-eigenvector mode: 2 <= 512/16
+    assert ranks2.tolist() == [6, 511] and np.abs(V2 - V[:, [6, 511]]).max() < 1e-12

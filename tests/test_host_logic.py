@@ -235,3 +235,29 @@ def test_hostemu_select_mode_api(hostemu, oracle):
     full.close()
     h = __import__("ctypes").c_void_p()
     assert hostemu.cuppen_create(__import__("ctypes").byref(h), 64, 1, api.FLAG_VECTORS | api.FLAG_SELECT, 0) == -1
+
+
+def test_hostemu_orthogonality_and_eigenvector_file(hostemu, oracle, tmp_path):
+    D, E = oracle.goe(150)
+    s = se.CuppenSolver(150, ref_leaves=2, lib=hostemu)
+    s.set_tridiagonal(D, E)
+    s.solve()
+    V = s.eigenvectors()
+    dev, _ = s.orthogonality()
+    assert abs(dev - np.abs(V.T @ V - np.eye(150)).max()) < 1e-15 and dev < 1e-13
+    f = tmp_path / "v.bin"
+    s.write_eigenvectors(str(f))
+    ranks, lam, W = se.read_eigenvector_file(str(f))
+    assert ranks.tolist() == list(range(150)) and np.array_equal(lam, s.eigenvalues()) and np.array_equal(W, V)
+    s.close()
+    s = se.CuppenSolver(150, ref_leaves=2, lib=hostemu, select=True)
+    s.set_tridiagonal(D, E)
+    s.select([149, 3])
+    s.solve()
+    s.write_eigenvectors(str(f))
+    ranks, lam, W = se.read_eigenvector_file(str(f))
+    assert ranks.tolist() == [149, 3] and np.array_equal(lam, s.eigenvalues()[[149, 3]])
+    assert np.array_equal(W, s.selected_eigenvectors()) and np.abs(W - V[:, [149, 3]]).max() < 1e-13
+    with pytest.raises(se.CuppenError):
+        s.orthogonality()
+    s.close()
