@@ -171,6 +171,11 @@ int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* df
  * max_abs_err: against an fp64 FMA dot product on 8192 sampled entries; tflops: best of `reps`. */
 int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps, double* max_abs_err, double* tflops);
 
+/* Residual-kernel self-test / micro-benchmark on random data (n columns): one slice of rows [g0, g0+cnt) of an n-row
+ * problem stored at local rows [l0, l0+cnt) with halo rows (the multi-GPU slice layout), against a plain per-column
+ * loop.  variant: 0 = the default, else 10*columns-per-block + min-blocks-per-SM.  seconds (may be NULL): best of 3. */
+int cuppen_selftest_residual(int device, int n, int variant, int g0, int l0, int cnt, double* max_rel_err, double* seconds);
+
 /* ---- host-side helpers of the CLI (no GPU involved) ------------------------------------------- */
 int cuppen_scheme(int scheme, int n, double* D, double* E);
 int cuppen_read_mtx(const char* filename, double** D, double** E, int* n);   /* callee allocates (malloc) */

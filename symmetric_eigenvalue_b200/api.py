@@ -82,6 +82,7 @@ def _declare(lib):
         "cuppen_write_eigenvectors": [H, ctypes.c_char_p],
         "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_selftest_gemm": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
+        "cuppen_selftest_residual": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_read_mtx": [ctypes.c_char_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ip],
         "cuppen_read_ev_file": [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ip), ip],
@@ -101,7 +102,7 @@ EXPORTED_SYMBOLS = (
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors",
     "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors", "cuppen_orthogonality", "cuppen_write_eigenvectors",
-    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_selftest_gemm", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
+    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_selftest_gemm", "cuppen_selftest_residual", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
 
@@ -148,6 +149,14 @@ def selftest_gemm(variant, M, N, K, reps=3, device=0, lib=None):
     lib = lib or load_library()
     e, t = ctypes.c_double(0), ctypes.c_double(0)
     _chk(lib, lib.cuppen_selftest_gemm(device, variant, M, N, K, reps, ctypes.byref(e), ctypes.byref(t)))
+    return e.value, t.value
+
+
+def selftest_residual(n, g0, l0, cnt, variant=0, device=0, lib=None):
+    """(max relative error, seconds) of residual_kernel on one slice of rows (multi-GPU layout) of random data."""
+    lib = lib or load_library()
+    e, t = ctypes.c_double(0), ctypes.c_double(0)
+    _chk(lib, lib.cuppen_selftest_residual(device, n, variant, g0, l0, cnt, ctypes.byref(e), ctypes.byref(t)))
     return e.value, t.value
 
 

@@ -229,9 +229,60 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
         for (int c = 0; c < nl; ++c) Q[(long)(grow - R0) + (long)(compact ? c : off + c) * ldq] = q[lane][c];   // compact: (row, c) at row + c*ldq
 }
 
-// K3: one warp per secular root; poles and weights of the merge staged in shared memory when
-// they fit (k <= SEC_SMEM_K), otherwise read through L1/L2.
+// K3: one warp per secular root.  The poles and weights of the merge are staged in shared memory: all of
+// them when they fit (k <= kcap <= SEC_SMEM_K), otherwise chunk by chunk through a CTA-collective evaluator --
+// the SEC_WARPS roots of a CTA then iterate in lockstep (a warp whose root has converged keeps taking part in
+// the chunk loads and barriers until the slowest root of the CTA is done), so every chunk is read from L2 once
+// per CTA and evaluation instead of once per warp.
 enum { SEC_SMEM_K = 14336, SEC_WARPS = 16 };
+
+struct SecularStagedEval {
+    const double* d;       // global poles / weights of the merge
+    const double* w;
+    int k, cap;
+    double* sm;            // [2][cap] chunk buffer
+    // CTA-collective; `math` = false for a drained warp (takes part in loads and barriers only)
+    __device__ __forceinline__ SecularSums run(double dorg, double tau, int split, bool math) const {
+        const int lane = threadIdx.x & 31;
+        double psi = 0, dpsi = 0, phi = 0, dphi = 0, err = 0;
+        for (int c0 = 0; c0 < k; c0 += cap) {
+            const int cnt = min(cap, k - c0);
+            __syncthreads();                                   // the previous chunk has been consumed by every warp
+            for (int t = threadIdx.x; t < cnt; t += blockDim.x) { sm[t] = d[c0 + t]; sm[cap + t] = w[c0 + t]; }
+            __syncthreads();
+            if (!math) continue;
+            const int npsi = max(0, min(cnt, split + 1 - c0));  // poles of this chunk that belong to psi
+            int j = lane;
+#pragma unroll 4
+            for (; j < npsi; j += 32) {
+                const double t = (sm[j] - dorg) - tau;
+                const double inv = 1.0 / t;
+                const double r = sm[cap + j] * inv;
+                psi += r; dpsi += r * inv; err += fabs(r);
+            }
+#pragma unroll 4
+            for (; j < cnt; j += 32) {
+                const double t = (sm[j] - dorg) - tau;
+                const double inv = 1.0 / t;
+                const double r = sm[cap + j] * inv;
+                phi += r; dphi += r * inv; err += fabs(r);
+            }
+        }
+        SecularSums s;
+        WarpLanes L;
+        s.psi = L.sum(psi); s.dpsi = L.sum(dpsi); s.phi = L.sum(phi); s.dphi = L.sum(dphi); s.err = L.sum(err);
+        return s;
+    }
+    // an active warp announces itself (the drained ones are waiting in the same vote), then evaluates
+    __device__ __forceinline__ SecularSums operator()(double dorg, double tau, int split) const {
+        __syncthreads_or(1);
+        return run(dorg, tau, split, true);
+    }
+    __device__ __forceinline__ void drain() const {
+        while (__syncthreads_or(0)) run(0.0, 0.0, 0, false);
+    }
+};
+
 __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int kcap, int part, int nparts) {
     extern __shared__ double sec_smem[];
     const int id = blockIdx.y;
@@ -244,16 +295,238 @@ __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int
     if (i0 + (int)blockIdx.x * SEC_WARPS >= i1) return;
     const double* dl = c.dl + D.off;
     const double* wl = c.wl + D.off;
+    WarpLanes L;
     if (k <= kcap) {
         for (int t = threadIdx.x; t < k; t += blockDim.x) { sec_smem[t] = dl[t]; sec_smem[kcap + t] = wl[t]; }
         __syncthreads();
-        dl = sec_smem;
-        wl = sec_smem + kcap;
+        if (i >= i1) return;
+        SecularRoot r = secular_solve(L, k, sec_smem, sec_smem + kcap, fabs(D.rho), D.sumw, i);
+        if (L.lane() == 0) { c.org[D.off + i] = r.origin; c.tau[D.off + i] = r.tau; }
+        return;
     }
-    if (i >= i1) return;
-    WarpLanes L;
-    SecularRoot r = secular_solve(L, k, dl, wl, fabs(D.rho), D.sumw, i);
-    if (L.lane() == 0) { c.org[D.off + i] = r.origin; c.tau[D.off + i] = r.tau; }
+    const SecularStagedEval ev{dl, wl, k, kcap, sec_smem};
+    if (i < i1) {
+        SecularRoot r = secular_solve_ev(ev, k, dl, wl, fabs(D.rho), D.sumw, i);
+        if (L.lane() == 0) { c.org[D.off + i] = r.origin; c.tau[D.off + i] = r.tau; }
+    }
+    ev.drain();
+}
+
+// Compact as a scan: the canonical index of a live element is the number of live elements before it in the
+// sorted z-live list -- a prefix sum, not the O(m^2) count of the per-warp Compact functor (which stays in use
+// for the small merges of fused_front_kernel and in the host test build).  One CTA per merge: a reduction pass
+// for the totals (k is needed up front: rho < 0 problems are stored reflected), then a tiled exclusive scan of
+// the three flags (live, top-supported, bottom-supported) with running carries.
+enum { CS_THREADS = 1024 };
+__global__ void __launch_bounds__(CS_THREADS) compact_scan_kernel(LevelCtx c) {
+    MergeDesc& D = c.desc[blockIdx.x];
+    const int off = D.off, nl = D.nlive1, n1 = D.n1;
+    const int* ls = c.lsort + off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int s_cnt[3][32];
+    __shared__ double s_sw[32];
+    __shared__ int s_tot[3];
+    // ---- pass 1: totals -------------------------------------------------------------------------------
+    int k = 0, kt = 0, kb = 0;
+    double sw = 0;
+    for (int q = tid; q < nl; q += CS_THREADS) {
+        const int eq = ls[q];
+        if (c.G[off + eq] != -1) continue;
+        const int sp = c.sup[off + eq];
+        const double zq = c.zn[off + eq];
+        sw += zq * zq;
+        k++; kt += (sp & SUP_TOP) ? 1 : 0; kb += (sp & SUP_BOT) ? 1 : 0;
+    }
+    k = __reduce_add_sync(0xffffffffu, k); kt = __reduce_add_sync(0xffffffffu, kt); kb = __reduce_add_sync(0xffffffffu, kb);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sw += __shfl_xor_sync(0xffffffffu, sw, o);
+    if (lane == 0) { s_cnt[0][warp] = k; s_cnt[1][warp] = kt; s_cnt[2][warp] = kb; s_sw[warp] = sw; }
+    __syncthreads();
+    if (warp == 0) {
+        int a = s_cnt[0][lane], b = s_cnt[1][lane], d3 = s_cnt[2][lane];
+        double w = s_sw[lane];
+        a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b); d3 = __reduce_add_sync(0xffffffffu, d3);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+        if (lane == 0) { s_tot[0] = a; s_tot[1] = b; s_tot[2] = d3; D.k = a; D.ktop = b; D.kbot = d3; D.sumw = w; }
+    }
+    __syncthreads();
+    const int ktot = s_tot[0];
+    const bool neg = D.rho < 0;
+    // ---- pass 2: tiled exclusive scan -------------------------------------------------------------------
+    int carry0 = 0, carry1 = 0, carry2 = 0;
+    for (int base = 0; base < nl; base += CS_THREADS) {
+        const int q = base + tid;
+        int e = -1, sp = 0, f0 = 0, f1 = 0, f2 = 0;
+        if (q < nl) {
+            e = ls[q];
+            if (c.G[off + e] == -1) { sp = c.sup[off + e]; f0 = 1; f1 = (sp & SUP_TOP) ? 1 : 0; f2 = (sp & SUP_BOT) ? 1 : 0; }
+        }
+        // warp-level inclusive scans
+        int i0 = f0, i1 = f1, i2 = f2;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o), t2 = __shfl_up_sync(0xffffffffu, i2, o);
+            if (lane >= o) { i0 += t0; i1 += t1; i2 += t2; }
+        }
+        __syncthreads();                                   // previous tile's s_cnt reads are done
+        if (lane == 31) { s_cnt[0][warp] = i0; s_cnt[1][warp] = i1; s_cnt[2][warp] = i2; }
+        __syncthreads();
+        int w0 = 0, w1 = 0, w2 = 0, t0 = 0, t1 = 0, t2 = 0;       // offsets of this warp, totals of the tile
+#pragma unroll 8
+        for (int w = 0; w < CS_THREADS / 32; ++w) {
+            const int a0 = s_cnt[0][w], a1 = s_cnt[1][w], a2 = s_cnt[2][w];
+            if (w < warp) { w0 += a0; w1 += a1; w2 += a2; }
+            t0 += a0; t1 += a1; t2 += a2;
+        }
+        if (f0) {
+            const int cnt = carry0 + w0 + i0 - 1, tcnt = carry1 + w1 + i1 - f1, bcnt = carry2 + w2 + i2 - f2;
+            const int ci = neg ? (ktot - 1 - cnt) : cnt;
+            const double dv = c.dn[off + e], zv = c.zn[off + e];
+            c.dl[off + ci] = neg ? -dv : dv;
+            c.zl[off + ci] = zv;
+            c.wl[off + ci] = zv * zv;
+            c.lidx[off + ci] = e;
+            if (f1) { c.tpos[off + e] = tcnt; c.toplist[off + tcnt] = ci; }
+            if (f2) { c.bpos[off + e] = bcnt; c.botlist[off + n1 + bcnt] = ci; }
+        }
+        carry0 += t0; carry1 += t1; carry2 += t2;
+    }
+}
+
+// ---- the O(k^2) stages as tiled kernels -----------------------------------------------------------------
+// Loewner, Norms and RowGemv (merge_stages.h) are Cauchy-like sums/products: every output (a pole or a root)
+// visits every item of the other kind with one fp64 division.  The per-warp functors stream the k-vectors
+// through L1/L2 once per output; here a CTA owns TL_TJ outputs, stages the other side in shared memory TL_RC
+// items at a time (L2 traffic / TL_TJ, broadcast LDS in the inner loop, FP64-pipe bound) and splits every
+// chunk over TL_SL slices of threads (thread = (output, slice)) so that small problems still fill the SMs and no
+// thread walks more than k / TL_SL items; the slices are combined through shared memory in a fixed order.
+// grid.x = tile of outputs, grid.y = merge.  The functors stay in use inside fused_front_kernel (m <= 128) and
+// in the host test build.
+enum { TL_TJ = 64, TL_SL = 8, TL_THREADS = TL_TJ * TL_SL, TL_RC = 512, TL_SUB = TL_RC / TL_SL };
+
+// zhat_j = sign(z_j) sqrt( |prod_i (lambda_i - d_j) / prod_{i != j} (d_i - d_j)| / |rho| )
+__global__ void __launch_bounds__(TL_THREADS) loewner_tiled_kernel(LevelCtx c) {
+    __shared__ double s_lam_org[TL_RC], s_tau[TL_RC], s_dl[TL_RC];
+    __shared__ double s_part[TL_SL][TL_TJ];
+    const MergeDesc& D = c.desc[blockIdx.y];
+    const int k = D.k, off = D.off;
+    const int j0 = blockIdx.x * TL_TJ;
+    if (j0 >= k) return;
+    const int out = threadIdx.x & (TL_TJ - 1), slice = threadIdx.x / TL_TJ;
+    const int j = j0 + out;
+    const double* dl = c.dl + off;
+    const double dj = dl[j < k ? j : k - 1];
+    double prod = 1.0;
+    for (int i0 = 0; i0 < k; i0 += TL_RC) {
+        const int cnt = min((int)TL_RC, k - i0);
+        for (int t = threadIdx.x; t < cnt; t += TL_THREADS) {
+            s_lam_org[t] = dl[c.org[off + i0 + t]];
+            s_tau[t] = c.tau[off + i0 + t];
+            s_dl[t] = dl[i0 + t];
+        }
+        __syncthreads();
+        const int t1 = min(cnt, (slice + 1) * TL_SUB);
+#pragma unroll 4
+        for (int t = slice * TL_SUB; t < t1; ++t) {
+            const double num = (s_lam_org[t] - dj) + s_tau[t];
+            const double den = s_dl[t] - dj;
+            prod *= (i0 + t == j) ? num : num / den;
+        }
+        __syncthreads();
+    }
+    s_part[slice][out] = prod;
+    __syncthreads();
+    if (slice == 0 && j < k) {
+        double p = s_part[0][out];
+#pragma unroll
+        for (int q = 1; q < TL_SL; ++q) p *= s_part[q][out];
+        const double zh = sqrt(fabs(p) / fabs(D.rho));
+        c.zhat[off + j] = (c.zl[off + j] < 0) ? -zh : zh;
+    }
+}
+
+// N_i = || zhat / (d - lambda_i) ||_2
+__global__ void __launch_bounds__(TL_THREADS) norms_tiled_kernel(LevelCtx c) {
+    __shared__ double s_dl[TL_RC], s_zh[TL_RC];
+    __shared__ double s_part[TL_SL][TL_TJ];
+    const MergeDesc& D = c.desc[blockIdx.y];
+    const int k = D.k, off = D.off;
+    const int i0 = blockIdx.x * TL_TJ;
+    if (i0 >= k) return;
+    const int out = threadIdx.x & (TL_TJ - 1), slice = threadIdx.x / TL_TJ;
+    const int i = i0 + out;
+    const double* dl = c.dl + off;
+    const int ii = i < k ? i : k - 1;
+    const double dorg = dl[c.org[off + ii]], t = c.tau[off + ii];
+    double s = 0.0;
+    for (int q0 = 0; q0 < k; q0 += TL_RC) {
+        const int cnt = min((int)TL_RC, k - q0);
+        for (int q = threadIdx.x; q < cnt; q += TL_THREADS) { s_dl[q] = dl[q0 + q]; s_zh[q] = c.zhat[off + q0 + q]; }
+        __syncthreads();
+        const int q1 = min(cnt, (slice + 1) * TL_SUB);
+#pragma unroll 4
+        for (int q = slice * TL_SUB; q < q1; ++q) {
+            const double u = s_zh[q] / ((s_dl[q] - dorg) - t);
+            s = fma(u, u, s);
+        }
+        __syncthreads();
+    }
+    s_part[slice][out] = s;
+    __syncthreads();
+    if (slice == 0 && i < k) {
+        double a = s_part[0][out];
+#pragma unroll
+        for (int q = 1; q < TL_SL; ++q) a += s_part[q][out];
+        c.nrm[off + i] = sqrt(a);
+    }
+}
+
+// boundary rows of the merged node (eigenvalue-only mode, src/main.c:613-639): first row over the top-supported
+// live columns, last row over the bottom-supported ones
+__global__ void __launch_bounds__(TL_THREADS) rowgemv_tiled_kernel(LevelCtx c, RowCtx r) {
+    __shared__ double s_dl[TL_RC], s_w[TL_RC];
+    __shared__ double s_part[2][TL_SL][TL_TJ];
+    const MergeDesc& D = c.desc[blockIdx.y];
+    const int k = D.k, off = D.off;
+    const int i0 = blockIdx.x * TL_TJ;
+    if (i0 >= k) return;
+    const int out = threadIdx.x & (TL_TJ - 1), slice = threadIdx.x / TL_TJ;
+    const int i = i0 + out;
+    const double* dl = c.dl + off;
+    const double* zh = c.zhat + off;
+    const int ii = i < k ? i : k - 1;
+    const double dorg = dl[c.org[off + ii]], t = c.tau[off + ii];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        const int kh = half ? D.kbot : D.ktop;
+        const int* list = half ? c.botlist + off + D.n1 : c.toplist + off;
+        const double* pk = half ? r.lpack + off + D.n1 : r.fpack + off;
+        double s = 0.0;
+        for (int q0 = 0; q0 < kh; q0 += TL_RC) {
+            const int cnt = min((int)TL_RC, kh - q0);
+            for (int q = threadIdx.x; q < cnt; q += TL_THREADS) {
+                const int jq = list[q0 + q];
+                s_dl[q] = dl[jq];
+                s_w[q] = pk[q0 + q] * zh[jq];
+            }
+            __syncthreads();
+            const int q1 = min(cnt, (slice + 1) * TL_SUB);
+#pragma unroll 4
+            for (int q = slice * TL_SUB; q < q1; ++q) s += s_w[q] / ((s_dl[q] - dorg) - t);
+            __syncthreads();
+        }
+        s_part[half][slice][out] = s;
+    }
+    __syncthreads();
+    if (slice == 0 && i < k) {
+        double a = s_part[0][0][out], b = s_part[1][0][out];
+#pragma unroll
+        for (int q = 1; q < TL_SL; ++q) { a += s_part[0][q][out]; b += s_part[1][q][out]; }
+        const double rn = 1.0 / c.nrm[off + i];
+        r.frow_new[off + c.lidx[off + i]] = a * rn;
+        r.lrow_new[off + c.lidx[off + i]] = b * rn;
+    }
 }
 
 // Fused front end for the small merges at the bottom of the tree: one CTA per merge runs every vector
@@ -399,49 +672,112 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
     }
 }
 
-// K8: one block per output column over one contiguous slice of rows: global rows [g0, g0+cnt) stored
-// at local rows [l0, l0+cnt).  Output column c (ascending lambda) is storage column perm[c] of V.  Four
-// independent rows per thread and iteration keep enough loads in flight to stream from HBM.
-// `accumulate` adds to res2 (a rank holds several slices when the rows are distributed).
-__global__ void __launch_bounds__(256) residual_kernel(const double* __restrict__ V, long ldq, int n, int g0, int l0, int cnt,
-                                                       const double* __restrict__ OD, const double* __restrict__ OE,
-                                                       const double* __restrict__ lam_sorted, const int* __restrict__ perm,
-                                                       const double* __restrict__ halo_lo, const double* __restrict__ halo_hi,
-                                                       double* __restrict__ res2, int accumulate) {
-    const int col = blockIdx.x;
-    const double* x = V + (long)perm[col] * ldq + l0 - g0;      // x[r] = element of global row r
-    const double lambda = lam_sorted[col];
+// K8: residuals of RES_NC output columns per block over one contiguous slice of rows: global rows
+// [g0, g0+cnt) stored at local rows [l0, l0+cnt).  Output column c (ascending lambda) is storage column
+// perm[c] of V.  A thread owns two consecutive rows per step.  Interior pairs take a branch-free fast path:
+// the diagonal / off-diagonal entries are loaded once (16 bytes each) and reused for all RES_NC columns; per
+// column one 16-byte load of (x[r], x[r+1]) plus the two neighbours x[r-1], x[r+2] (L1 hits: the adjacent
+// threads' lines) and ten FP64 instructions -- few enough instructions per byte that the kernel is bound by HBM
+// and not by the issue rate (the first version spent ~80 instructions per 16 bytes on boundary predicates).
+// Pairs that touch the slice boundary (halo rows of the multi-GPU layout, first / last row of T, odd offsets)
+// take a general per-row path.  `accumulate` adds to res2 (a rank holds several slices when the rows are
+// distributed).  RES_NC and the minimum resident blocks per SM are template parameters: the variants were timed
+// on the B200 (cuppen_selftest_residual, profiles/README.md) and launch_residual() picks the default.
+enum { RES_DEFAULT_VARIANT = 25 };
+template <int RES_NC, int MINB>
+__global__ void __launch_bounds__(256, MINB) residual_kernel(const double* __restrict__ V, long ldq, int n, int g0, int l0, int cnt,
+                                                             const double* __restrict__ OD, const double* __restrict__ OE,
+                                                             const double* __restrict__ lam_sorted, const int* __restrict__ perm,
+                                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi,
+                                                             double* __restrict__ res2, int accumulate) {
+    const int col0 = blockIdx.x * RES_NC;
     const int g1 = g0 + cnt;
-    double acc = 0;
-    for (int r0 = g0 + threadIdx.x; r0 < g1; r0 += 4 * 256) {
-        double xm[4], xc[4], xp[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * 256;
-            xc[u] = (r < g1) ? x[r] : 0.0;
-            xm[u] = (r < g1 && r > 0) ? ((r > g0) ? x[r - 1] : halo_lo[col]) : 0.0;
-            xp[u] = (r < g1 && r < n - 1) ? ((r + 1 < g1) ? x[r + 1] : halo_hi[col]) : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int r = r0 + u * 256;
-            if (r >= g1) continue;
-            double y = OD[r] * xc[u] - lambda * xc[u];
-            if (r > 0) y += OE[r - 1] * xm[u];
-            if (r < n - 1) y += OE[r] * xp[u];
-            acc += y * y;
-        }
-    }
-    __shared__ double red[8];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    const int lane = threadIdx.x & 31;
+    // per-column constants live in shared memory (broadcast reads) to keep the register budget for loads in flight
+    __shared__ const double* x[RES_NC];
+    __shared__ double lambda[RES_NC];
+    __shared__ int s_vec_ok;
+    double acc[RES_NC];
+    if (threadIdx.x == 0) s_vec_ok = 1;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0;
-        for (int w = 0; w < 8; ++w) s += red[w];
-        res2[col] = accumulate ? res2[col] + s : s;
+    if (threadIdx.x < RES_NC) {
+        const int col = min(col0 + (int)threadIdx.x, n - 1);      // columns past the end repeat the last one (not stored)
+        const long xoff = (long)perm[col] * ldq + l0 - g0;
+        x[threadIdx.x] = V + xoff;                                // x[c][r] = element of global row r
+        if (xoff & 1) s_vec_ok = 0;                               // 16-byte loads of (x[r], x[r+1]) with r even
+        lambda[threadIdx.x] = lam_sorted[col];
     }
+    __syncthreads();
+    const bool vec_ok = s_vec_ok != 0;
+#pragma unroll
+    for (int c = 0; c < RES_NC; ++c) acc[c] = 0.0;
+    for (int r = (g0 & ~1) + 2 * (int)threadIdx.x; r < g1; r += 2 * 256) {
+        if (vec_ok && r - 1 >= g0 && r + 2 < g1) {
+            // interior pair: rows r-1 .. r+2 are all inside the slice (so 0 < r and r + 1 < n - 1)
+            const double2 dv = *reinterpret_cast<const double2*>(OD + r);
+            const double2 ev = *reinterpret_cast<const double2*>(OE + r);
+            const double em = OE[r - 1];
+#pragma unroll
+            for (int c = 0; c < RES_NC; ++c) {
+                const double* xc = x[c];
+                const double2 xv = *reinterpret_cast<const double2*>(xc + r);
+                const double xm = xc[r - 1], xp = xc[r + 2];
+                const double lam = lambda[c];
+                const double y0 = fma(dv.x - lam, xv.x, fma(em, xm, ev.x * xv.y));
+                const double y1 = fma(dv.y - lam, xv.y, fma(ev.x, xv.x, ev.y * xp));
+                acc[c] = fma(y0, y0, fma(y1, y1, acc[c]));
+            }
+        } else {
+#pragma unroll 1
+            for (int rr = max(r, g0); rr < min(r + 2, g1); ++rr) {
+                const double dr = OD[rr];
+                const double el = (rr > 0) ? OE[rr - 1] : 0.0, eu = (rr < n - 1) ? OE[rr] : 0.0;
+#pragma unroll
+                for (int c = 0; c < RES_NC; ++c) {                  // (unrolled: acc[] must stay in registers)
+                    const int col = min(col0 + c, n - 1);
+                    const double* xc = x[c];
+                    const double xr = xc[rr];
+                    double y = (dr - lambda[c]) * xr;
+                    if (rr > 0) y = fma(el, (rr > g0) ? xc[rr - 1] : halo_lo[col], y);
+                    if (rr < n - 1) y = fma(eu, (rr + 1 < g1) ? xc[rr + 1] : halo_hi[col], y);
+                    acc[c] = fma(y, y, acc[c]);
+                }
+            }
+        }
+    }
+    __shared__ double red[8][RES_NC];
+#pragma unroll
+    for (int c = 0; c < RES_NC; ++c) {
+        double a = acc[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) red[threadIdx.x >> 5][c] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < RES_NC && col0 + (int)threadIdx.x < n) {
+        double sum = 0;
+        for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
+        const int col = col0 + threadIdx.x;
+        res2[col] = accumulate ? res2[col] + sum : sum;
+    }
+}
+
+// variant: 0 default, else NC*10 + MINB
+inline void launch_residual(Stream st, int variant, const double* V, long ldq, int n, int g0, int l0, int cnt, const double* OD,
+                            const double* OE, const double* lam_sorted, const int* perm, const double* halo_lo,
+                            const double* halo_hi, double* res2, int accumulate) {
+#define CUPPEN_RES_CASE(NC, MB)                                                                                          \
+    case NC * 10 + MB:                                                                                                   \
+        residual_kernel<NC, MB><<<(unsigned)((n + NC - 1) / NC), 256, 0, st>>>(V, ldq, n, g0, l0, cnt, OD, OE, lam_sorted, \
+                                                                               perm, halo_lo, halo_hi, res2, accumulate); \
+        break;
+    switch (variant == 0 ? RES_DEFAULT_VARIANT : variant) {
+        CUPPEN_RES_CASE(1, 4) CUPPEN_RES_CASE(1, 6) CUPPEN_RES_CASE(2, 4) CUPPEN_RES_CASE(2, 5) CUPPEN_RES_CASE(4, 3)
+        CUPPEN_RES_CASE(4, 4) CUPPEN_RES_CASE(8, 2) CUPPEN_RES_CASE(8, 3) CUPPEN_RES_CASE(4, 2) CUPPEN_RES_CASE(2, 3)
+        default: CUPPEN_THROW(-1, "unknown residual kernel variant %d", variant);
+    }
+#undef CUPPEN_RES_CASE
+    CUDA_CHECK(cudaGetLastError());
 }
 
 __global__ void __launch_bounds__(256) gather_cols_kernel(const double* __restrict__ src, double* __restrict__ dst,

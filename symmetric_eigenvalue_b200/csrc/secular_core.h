@@ -73,10 +73,21 @@ struct SecularRoot {
     int iters;      // function evaluations spent
 };
 
-// Solve for root i.  sumw = sum_j w[j] (only needed for the last root).
+// The default evaluator: every call streams the k poles through the lanes of one warp (or one host thread).
 template <class Lanes>
-CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restrict__ d,
-                                    const double* __restrict__ w, double rho, double sumw, int i) {
+struct SecularStreamEval {
+    const Lanes& L;
+    int k;
+    const double* d;
+    const double* w;
+    CUPPEN_HD SecularSums operator()(double dorg, double tau, int split) const { return secular_eval(L, k, d, w, dorg, tau, split); }
+};
+
+// Solve for root i.  sumw = sum_j w[j] (only needed for the last root).  `ev(dorg, tau, split)` evaluates the
+// sums over all k poles (secular_kernel passes a CTA-collective evaluator that stages the poles in shared memory).
+template <class Eval>
+CUPPEN_HD SecularRoot secular_solve_ev(const Eval& ev, int k, const double* __restrict__ d,
+                                       const double* __restrict__ w, double rho, double sumw, int i) {
     const double eps = 2.220446049250313e-16;
     const double rhoinv = 1.0 / rho;
     SecularRoot out;
@@ -94,7 +105,7 @@ CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restr
     if (!last) {
         // decide the origin from the sign of g at the midpoint (evaluated relative to pole i)
         const double half = 0.5 * gap;
-        SecularSums s = secular_eval(L, k, d, w, d[i], half, i);
+        SecularSums s = ev(d[i], half, i);
         out.iters++;
         const double gmid = rhoinv + s.psi + s.phi;              // full secular function at the midpoint
         const double c = gmid - w[ip0] / (-half) - w[ip1] / half;   // without the two nearest poles (initial guess only)
@@ -115,7 +126,7 @@ CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restr
         org = k - 1;
         const double R = rho * sumw;
         const double mid = 0.5 * R;
-        SecularSums s = secular_eval(L, k, d, w, d[org], mid, k);
+        SecularSums s = ev(d[org], mid, k);
         out.iters++;
         const double w0 = w[ip0], w1 = w[ip1];
         const double gmid = rhoinv + s.psi;                      // full secular function at the midpoint
@@ -139,7 +150,7 @@ CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restr
     double prevabs = INFINITY;
     int slow = 0;
     for (int it = 0; it < 80; ++it) {
-        SecularSums s = secular_eval(L, k, d, w, dorg, tau, split);
+        SecularSums s = ev(dorg, tau, split);
         out.iters++;
         const double h = rhoinv + s.psi + s.phi;
         const double errb = eps * (8.0 * s.err + fabs(rhoinv) + fabs(tau) * (s.dpsi + s.dphi));
@@ -176,6 +187,12 @@ CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restr
     out.origin = org;
     out.tau = tau;
     return out;
+}
+
+template <class Lanes>
+CUPPEN_HD SecularRoot secular_solve(const Lanes& L, int k, const double* __restrict__ d,
+                                    const double* __restrict__ w, double rho, double sumw, int i) {
+    return secular_solve_ev(SecularStreamEval<Lanes>{L, k, d, w}, k, d, w, rho, sumw, i);
 }
 
 }  // namespace cuppen

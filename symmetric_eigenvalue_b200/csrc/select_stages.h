@@ -162,7 +162,7 @@ struct SelResidual {
 // right-hand sides of a root are contiguous, so the inner loop is broadcast LDS.128 + one fp64
 // reciprocal + SEL_NV DFMA per pair).  Chunks whose right-hand sides are all zero are skipped: at the
 // root of the tree X is a set of unit vectors, so only the chunks holding a selected root do work.
-enum { CA_TJ = 128, CA_RC = 256 };
+enum { CA_TJ = 64, CA_SL = 8, CA_THREADS = CA_TJ * CA_SL, CA_RC = 512, CA_SUB = CA_RC / CA_SL };
 
 CUPPEN_HD double cauchy_recip(double dj, double dorg, double tau) {
     double diff = (dj - dorg) - tau;
@@ -171,14 +171,18 @@ CUPPEN_HD double cauchy_recip(double dj, double dorg, double tau) {
 }
 
 #if CUPPEN_CUDA
-__global__ void __launch_bounds__(CA_TJ) cauchy_apply_kernel(LevelCtx c, SelCtx s) {
+// thread = (pole of the CTA's tile, slice of every staged chunk); the CA_SL partial sums of a pole are combined
+// through shared memory in a fixed order
+__global__ void __launch_bounds__(CA_THREADS) cauchy_apply_kernel(LevelCtx c, SelCtx s) {
     __shared__ double2 sdt[CA_RC];                       // (dorg, tau)
     __shared__ __align__(16) double sx[CA_RC][SEL_NV];
+    __shared__ double s_part[CA_SL][CA_TJ];
     const MergeDesc& D = c.desc[blockIdx.y];
     const int k = D.k, off = D.off;
     const int j0 = blockIdx.x * CA_TJ;
     if (j0 >= k) return;
-    const int j = j0 + threadIdx.x;
+    const int out = threadIdx.x & (CA_TJ - 1), slice = threadIdx.x / CA_TJ;
+    const int j = j0 + out;
     const double dj = c.dl[off + (j < k ? j : k - 1)];
     double acc[SEL_NV];
 #pragma unroll
@@ -186,7 +190,7 @@ __global__ void __launch_bounds__(CA_TJ) cauchy_apply_kernel(LevelCtx c, SelCtx 
     for (int i0 = 0; i0 < k; i0 += CA_RC) {
         const int cnt = min((int)CA_RC, k - i0);
         int nz = 0;
-        for (int t = threadIdx.x; t < cnt; t += CA_TJ) {
+        for (int t = threadIdx.x; t < cnt; t += CA_THREADS) {
             sdt[t] = make_double2(s.dorg[off + i0 + t], c.tau[off + i0 + t]);
 #pragma unroll
             for (int v = 0; v < SEL_NV; ++v) {
@@ -197,8 +201,9 @@ __global__ void __launch_bounds__(CA_TJ) cauchy_apply_kernel(LevelCtx c, SelCtx 
         }
         nz = __syncthreads_or(nz);
         if (nz) {
+            const int t1 = min(cnt, (slice + 1) * CA_SUB);
 #pragma unroll 4
-            for (int t = 0; t < cnt; ++t) {
+            for (int t = slice * CA_SUB; t < t1; ++t) {
                 const double2 q = sdt[t];
                 const double r = cauchy_recip(dj, q.x, q.y);
                 const double2* xv = reinterpret_cast<const double2*>(sx[t]);
@@ -212,11 +217,19 @@ __global__ void __launch_bounds__(CA_TJ) cauchy_apply_kernel(LevelCtx c, SelCtx 
         }
         __syncthreads();
     }
-    if (j < k) {
-        const double zh = c.zhat[off + j];
+    const double zh = c.zhat[off + (j < k ? j : k - 1)];
 #pragma unroll
-        for (int v = 0; v < SEL_NV; ++v)
-            if (v < s.nv) s.Gam[(long)v * s.n + off + j] = zh * acc[v];
+    for (int v = 0; v < SEL_NV; ++v) {
+        if (v >= s.nv) break;                                   // block-uniform
+        s_part[slice][out] = acc[v];
+        __syncthreads();
+        if (slice == 0 && j < k) {
+            double a = s_part[0][out];
+#pragma unroll
+            for (int q = 1; q < CA_SL; ++q) a += s_part[q][out];
+            s.Gam[(long)v * s.n + off + j] = zh * a;
+        }
+        __syncthreads();
     }
 }
 #else

@@ -145,6 +145,7 @@ struct Solver {
     PhaseTimers pt;
     cuppen_timers timers;
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
+    int resid_variant = 0;        // residual_kernel variant (0: default); env CUPPEN_RESID
     int gemm_variant = 1;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA kernel (gemm_tma.h); env CUPPEN_GEMM
     int num_sms = 148;
 #if CUPPEN_CUDA
@@ -262,6 +263,8 @@ void Solver::allocate() {
         dev_zero(Qa.p, Qa.bytes(), stream);
         dev_zero(Qb.p, Qb.bytes(), stream);
 #if CUPPEN_CUDA
+        const char* rv = getenv("CUPPEN_RESID");
+        if (rv && atoi(rv) > 0) resid_variant = atoi(rv);
         const char* gv = getenv("CUPPEN_GEMM");
         if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
         cudaDeviceProp prop;
@@ -630,7 +633,13 @@ void Solver::run_level(int li) {
         launch_items(stream, n, FlagDeflate{c});
         launch_warps(stream, n, RankLive{c});
         launch_items(stream, n, GivensSweep{c});
+#if CUPPEN_CUDA
+        compact_scan_kernel<<<(unsigned)nd_cnt, CS_THREADS, 0, stream>>>(c);
+        CUDA_CHECK(cudaGetLastError());
+        g_launches.launches++;
+#else
         launch_warps(stream, n, Compact{c});
+#endif
         pt.end(stream);
 
         // secular roots: worst-case grid, the kernel reads the live count k of every merge on the device.
@@ -667,14 +676,29 @@ void Solver::run_level(int li) {
             comm.allreduce_sum_i32(org.p + lo_idx, hi_idx - lo_idx, stream);
         }
         pt.begin(T_EVX, stream);
+#if CUPPEN_CUDA
+        const dim3 tl_grid((unsigned)((L.maxm + TL_TJ - 1) / TL_TJ), (unsigned)nd_cnt);
+        loewner_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
+        CUDA_CHECK(cudaGetLastError());
+        norms_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
+        CUDA_CHECK(cudaGetLastError());
+        g_launches.launches += 2;
+#else
         launch_warps(stream, n, Loewner{c});
         launch_warps(stream, n, Norms{c});
+#endif
         launch_items(stream, n, NewLambda{c});
         pt.end(stream);
         if (!want_vectors) {
             pt.begin(T_EVX, stream);
             launch_items(stream, n, RowPack{c, rowc});
+#if CUPPEN_CUDA
+            rowgemv_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c, rowc);
+            CUDA_CHECK(cudaGetLastError());
+            g_launches.launches++;
+#else
             launch_warps(stream, n, RowGemv{c, rowc});
+#endif
             launch_items(stream, n, RowCommit{c, rowc, frow.p, lrow.p});
             pt.end(stream);
         }
@@ -792,9 +816,8 @@ void Solver::finish() {
             }
             for (size_t i = 0; i < sl.size(); ++i) {
 #if CUPPEN_CUDA
-                residual_kernel<<<(unsigned)n, 256, 0, stream>>>(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p,
-                                                                 perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
-                CUDA_CHECK(cudaGetLastError());
+                launch_residual(stream, resid_variant, Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p,
+                                perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
 #else
                 residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
 #endif
@@ -847,7 +870,7 @@ void Solver::enqueue_apply() {
 #if CUPPEN_CUDA
             {
                 dim3 grid((unsigned)((L.maxm + CA_TJ - 1) / CA_TJ), (unsigned)L.ids.size());
-                cauchy_apply_kernel<<<grid, CA_TJ, 0, stream>>>(c, s);
+                cauchy_apply_kernel<<<grid, CA_THREADS, 0, stream>>>(c, s);
                 CUDA_CHECK(cudaGetLastError());
             }
 #else
@@ -1374,6 +1397,22 @@ __global__ void sample_check_kernel(const GemmProblem P, int samples, double* er
     atomicMax((unsigned long long*)err, (unsigned long long)__double_as_longlong(fabs(got - s)));
 }
 __global__ void iota_rev_kernel(int* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = n - 1 - i; }
+// plain one-thread-per-column restatement of the residual, for cuppen_selftest_residual
+__global__ void residual_check_kernel(const double* V, long ldq, int n, int ncols, int g0, int l0, int cnt, const double* OD, const double* OE,
+                                      const double* lam, const int* perm, const double* hlo, const double* hhi, const double* got, double* err) {
+    int col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= ncols) return;
+    const double* x = V + (long)perm[col] * ldq + l0 - g0;
+    double acc = 0;
+    for (int r = g0; r < g0 + cnt; ++r) {
+        double y = OD[r] * x[r] - lam[col] * x[r];
+        if (r > 0) y += OE[r - 1] * (r > g0 ? x[r - 1] : hlo[col]);
+        if (r < n - 1) y += OE[r] * (r + 1 < g0 + cnt ? x[r + 1] : hhi[col]);
+        acc += y * y;
+    }
+    double rel = fabs(got[col] - acc) / fmax(acc, 1e-300);
+    atomicMax((unsigned long long*)err, (unsigned long long)__double_as_longlong(rel));
+}
 }  // namespace cuppen
 #endif
 
@@ -1438,6 +1477,49 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     cudaEventDestroy(e0); cudaEventDestroy(e1);
 #else
     (void)device; (void)variant; (void)M; (void)N; (void)K; (void)reps; (void)max_abs_err; (void)tflops;
+    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
+#endif
+    CUPPEN_API_END
+}
+
+int cuppen_selftest_residual(int device, int n, int variant, int g0, int l0, int cnt, double* max_rel_err, double* seconds) {
+    CUPPEN_API_BEGIN
+#if CUPPEN_CUDA
+    if (n < 1 || g0 < 0 || l0 < 0 || cnt < 1 || g0 + cnt > n || !max_rel_err) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
+    const int ncols = n;
+    CUDA_CHECK(cudaSetDevice(device));
+    long ldq = round_up(l0 + cnt, 16);
+    if (getenv("CUPPEN_LDPAD")) ldq += atoi(getenv("CUPPEN_LDPAD"));      // experiment: column stride away from a power of two
+    DevBuf<double> V, OD, OE, lam, hlo, hhi, res, err;
+    DevBuf<int> perm;
+    V.alloc((size_t)ldq * ncols + 64); OD.alloc(n + 64); OE.alloc(n + 64); lam.alloc(ncols); hlo.alloc(ncols); hhi.alloc(ncols);
+    res.alloc(ncols); err.alloc(1); perm.alloc(ncols);
+    fill_kernel<<<(unsigned)((V.n + 255) / 256), 256>>>(V.p, (long)V.n, 11u);
+    fill_kernel<<<(unsigned)((OD.n + 255) / 256), 256>>>(OD.p, (long)OD.n, 12u);
+    fill_kernel<<<(unsigned)((OE.n + 255) / 256), 256>>>(OE.p, (long)OE.n, 13u);
+    fill_kernel<<<(unsigned)((ncols + 255) / 256), 256>>>(lam.p, ncols, 14u);
+    fill_kernel<<<(unsigned)((ncols + 255) / 256), 256>>>(hlo.p, ncols, 15u);
+    fill_kernel<<<(unsigned)((ncols + 255) / 256), 256>>>(hhi.p, ncols, 16u);
+    iota_rev_kernel<<<(ncols + 255) / 256, 256>>>(perm.p, ncols);
+    CUDA_CHECK(cudaMemset(err.p, 0, sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; ++rep) {
+        CUDA_CHECK(cudaEventRecord(e0, 0));
+        launch_residual(0, variant, V.p, ldq, n, g0, l0, cnt, OD.p, OE.p, lam.p, perm.p, hlo.p, hhi.p, res.p, 0);
+        CUDA_CHECK(cudaEventRecord(e1, 0));
+        CUDA_CHECK(cudaEventSynchronize(e1));
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (seconds) *seconds = best * 1e-3;
+    residual_check_kernel<<<(ncols + 127) / 128, 128>>>(V.p, ldq, n, ncols, g0, l0, cnt, OD.p, OE.p, lam.p, perm.p, hlo.p, hhi.p, res.p, err.p);
+    CUDA_CHECK(cudaDeviceSynchronize());
+    CUDA_CHECK(cudaMemcpy(max_rel_err, err.p, sizeof(double), cudaMemcpyDeviceToHost));
+#else
+    (void)device; (void)n; (void)variant; (void)g0; (void)l0; (void)cnt; (void)max_rel_err; (void)seconds;
     CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
 #endif
     CUPPEN_API_END

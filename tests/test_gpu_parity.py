@@ -169,6 +169,10 @@ def test_tma_and_cpasync_gemm_paths_agree(lib, oracle):
 
 
 # ---- selected-eigenvector mode (-eFILE) ---------------------------------------------------------------
+def sign_invariant_diff(A, B):
+    return float(np.minimum(np.abs(A - B).max(axis=0), np.abs(A + B).max(axis=0)).max()) if A.size else 0.0
+
+
 @pytest.mark.parametrize("gen,n,P", [("goe", 700, 4), ("s1", 1000, 8), ("s2", 512, 8), ("rand_u", 1500, 1), ("wilk", 1001, 4),
                                      ("goe", 3000, 2), ("goe", 1, 1), ("s2", 33, 1)])
 def test_select_mode_matches_full_mode(lib, oracle, gen, n, P):
@@ -183,7 +187,10 @@ def test_select_mode_matches_full_mode(lib, oracle, gen, n, P):
     # (the solve runs in eigenvalue-only mode: boundary rows by RowGemv instead of being read from the GEMM result)
     assert np.abs(out["lam"] - full["lam"]).max() <= 1e-13 * norm_T(D, E)
     assert ref_stats(out["stats"]) == ref_stats(full["stats"])
-    assert np.abs(out["V"] - full["V"][:, sel]).max() < 1e-12
+    # the same vectors up to sign: a z component that is zero by symmetry but rounds to +-1e-15 (live under the
+    # accurate rule) decides the sign of "its" eigenvector, and the two paths feed the merges boundary rows that
+    # differ in the last bits (DMMA GEMM result vs RowGemv) -- seen on the Poisson matrix
+    assert sign_invariant_diff(out["V"], full["V"][:, sel]) < 1e-12
     assert np.allclose(out["resid"], full["resid"][sel], rtol=1e-3, atol=1e-13 * norm_T(D, E))
 
 
@@ -216,7 +223,7 @@ def test_select_mode_baseline_size_against_lapack(lib, oracle):
     out = se.cuppens(g["D"], g["E"], ref_leaves=8, lib=lib, select=sel)
     check_against_golden(g, out, False)
     full = se.cuppens(g["D"], g["E"], ref_leaves=8, lib=lib)
-    assert np.abs(out["V"] - full["V"][:, sel]).max() < 1e-12
+    assert sign_invariant_diff(out["V"], full["V"][:, sel]) < 1e-12
 
 
 # ---- on-GPU orthogonality check (gram_check_kernel) and eigenvector output ------------------------------
@@ -270,4 +277,14 @@ def test_cli_eigenvector_file_and_orthogonality(lib, tmp_path):
     r = subprocess.run([exe, "-p", "4", "-s", "1", "-n", "512", "-e" + str(ev), "-v", str(vf), str(out)], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     ranks2, lam2, V2 = se.read_eigenvector_file(str(vf))                     # selected-eigenvector mode: 2 <= 512/16
-    assert ranks2.tolist() == [6, 511] and np.abs(V2 - V[:, [6, 511]]).max() < 1e-12
+    assert ranks2.tolist() == [6, 511] and sign_invariant_diff(V2, V[:, [6, 511]]) < 1e-12
+
+
+@pytest.mark.parametrize("n,g0,l0,cnt", [(4096, 0, 0, 4096), (4097, 0, 0, 4097), (1000, 0, 0, 1000), (5000, 1250, 0, 1250), (5000, 1251, 313, 1249),
+                                         (5000, 3750, 7, 1250), (5000, 4999, 0, 1), (3, 0, 0, 3), (1, 0, 0, 1), (2049, 1024, 512, 1025), (700, 1, 1, 698)])
+def test_residual_kernel_slices(lib, n, g0, l0, cnt):
+    """residual_kernel (paired rows, neighbour shuffles, halo rows) on every slice shape of the multi-GPU layout:
+    odd / even first rows, odd local offsets (scalar-load path), single rows, slices touching row 0 and n-1."""
+    from symmetric_eigenvalue_b200 import api
+    for variant in (0, 14, 83):
+        assert api.selftest_residual(n, g0, l0, cnt, variant=variant, lib=lib)[0] < 1e-13
