@@ -166,6 +166,10 @@ const char* cuppen_last_error(void);
  * TFLOP/s with all SMs busy for ~`ms` milliseconds each (the FP64 peak is not in MEASURED_PEAKS.json). */
 int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* dfma_tflops);
 
+/* DMMA and DFMA issue loops sharing every SM (4 warps each per block): TFLOP/s of each kind alone and over the common
+ * window when both run together -- do the two instruction kinds share the FP64 units? */
+int cuppen_measure_fp64_mix(int device, double* dmma_alone, double* dfma_alone, double* dmma_mixed, double* dfma_mixed);
+
 /* GEMM self-test / micro-benchmark of the back-transformation kernels on random data:
  * variant 0 = cp.async DMMA kernel 128x128, 1 = TMA DMMA kernel 128x128, 2 = cp.async 64x64.
  * max_abs_err: against an fp64 FMA dot product on 8192 sampled entries; tflops: best of `reps`. */

@@ -81,6 +81,7 @@ def _declare(lib):
         "cuppen_orthogonality": [H, dp, dp],
         "cuppen_write_eigenvectors": [H, ctypes.c_char_p],
         "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
+        "cuppen_measure_fp64_mix": [ctypes.c_int, dp, dp, dp, dp],
         "cuppen_selftest_gemm": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_selftest_residual": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
@@ -102,7 +103,7 @@ EXPORTED_SYMBOLS = (
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors",
     "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors", "cuppen_orthogonality", "cuppen_write_eigenvectors",
-    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_selftest_gemm", "cuppen_selftest_residual", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
+    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_measure_fp64_mix", "cuppen_selftest_gemm", "cuppen_selftest_residual", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
 
@@ -142,6 +143,14 @@ def measure_fp64_peak(device=0, ms=200, lib=None):
     a, b = ctypes.c_double(0), ctypes.c_double(0)
     _chk(lib, lib.cuppen_measure_fp64_peak(device, ms, ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value
+
+
+def measure_fp64_mix(device=0, lib=None):
+    """dict of TFLOP/s: DMMA / DFMA issue loops alone and sharing the SMs (do they share the FP64 units?)."""
+    lib = lib or load_library()
+    v = [ctypes.c_double(0) for _ in range(4)]
+    _chk(lib, lib.cuppen_measure_fp64_mix(device, *[ctypes.byref(x) for x in v]))
+    return dict(zip(("dmma_alone", "dfma_alone", "dmma_mixed", "dfma_mixed"), (x.value for x in v)))
 
 
 def selftest_gemm(variant, M, N, K, reps=3, device=0, lib=None):

@@ -73,6 +73,38 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) 
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// DMMA and DFMA issued from the same SM at the same time (warps 0-3 DMMA, warps 4-7 DFMA): if the two
+// instruction kinds share the FP64 units, the mixed rates add up to one peak -- the evidence behind the decision
+// not to generate U inside the GEMM producer.
+__global__ void __launch_bounds__(256) fp64_mix_kernel(double* out, int iters_dmma, int iters_dfma) {
+    const bool is_dmma = (threadIdx.x >> 5) < 4;
+    double s = 0;
+    if (is_dmma) {
+        double acc[16][2];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) acc[j][0] = acc[j][1] = 0.0;
+        const double a = 1e-9 * threadIdx.x, b = 1.0 + 1e-9 * blockIdx.x;
+        for (int it = 0; it < iters_dmma; ++it) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) dmma884(acc[j][0], acc[j][1], a, b);
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) s += acc[j][0] + acc[j][1];
+    } else {
+        double acc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = 1e-3 * j;
+        const double a = 1.0 + 1e-12 * threadIdx.x, b = 1e-9 * blockIdx.x;
+        for (int it = 0; it < iters_dfma; ++it) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = fma(acc[j], a, b);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s += acc[j];
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // CTA tile BM x BN x BK, WARPS_M x WARPS_N warps, each warp (BM/WARPS_M) x (BN/WARPS_N).
 template <int BM, int BN, int BK, int WARPS_M, int WARPS_N, int STAGES>
 struct DmmaCfg {

@@ -230,11 +230,13 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
 }
 
 // K3: one warp per secular root.  The poles and weights of the merge are staged in shared memory: all of
-// them when they fit (k <= kcap <= SEC_SMEM_K), otherwise chunk by chunk through a CTA-collective evaluator --
+// them when they fit (k <= kcap <= SEC_SMEM_K; 64 KB, three CTAs per SM -- with the whole 227 KB per CTA the
+// 16 warps of the single resident CTA left the FP64 pipe 32 % active, ncu), otherwise chunk by chunk through a
+// CTA-collective evaluator --
 // the SEC_WARPS roots of a CTA then iterate in lockstep (a warp whose root has converged keeps taking part in
 // the chunk loads and barriers until the slowest root of the CTA is done), so every chunk is read from L2 once
 // per CTA and evaluation instead of once per warp.
-enum { SEC_SMEM_K = 14336, SEC_WARPS = 16 };
+enum { SEC_SMEM_K = 4096, SEC_WARPS = 16 };
 
 struct SecularStagedEval {
     const double* d;       // global poles / weights of the merge
@@ -403,7 +405,7 @@ __global__ void __launch_bounds__(CS_THREADS) compact_scan_kernel(LevelCtx c) {
 // thread walks more than k / TL_SL items; the slices are combined through shared memory in a fixed order.
 // grid.x = tile of outputs, grid.y = merge.  The functors stay in use inside fused_front_kernel (m <= 128) and
 // in the host test build.
-enum { TL_TJ = 64, TL_SL = 8, TL_THREADS = TL_TJ * TL_SL, TL_RC = 512, TL_SUB = TL_RC / TL_SL };
+enum { TL_TJ = 32, TL_SL = 16, TL_THREADS = TL_TJ * TL_SL, TL_RC = 512, TL_SUB = TL_RC / TL_SL, TILED_MIN_M = 2048 };
 
 // zhat_j = sign(z_j) sqrt( |prod_i (lambda_i - d_j) / prod_{i != j} (d_i - d_j)| / |rho| )
 __global__ void __launch_bounds__(TL_THREADS) loewner_tiled_kernel(LevelCtx c) {
@@ -526,6 +528,43 @@ __global__ void __launch_bounds__(TL_THREADS) rowgemv_tiled_kernel(LevelCtx c, R
         const double rn = 1.0 / c.nrm[off + i];
         r.frow_new[off + c.lidx[off + i]] = a * rn;
         r.lrow_new[off + c.lidx[off + i]] = b * rn;
+    }
+}
+
+// RankLive (stable enumeration sort, merge_stages.h) in the same tiled shape: a thread owns one
+// element and one slice of every staged chunk of keys; z-deflated entries are staged as NaN (never "before").
+__global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
+    __shared__ double s_d[TL_RC];
+    __shared__ int s_cnt[TL_SL][TL_TJ], s_tot[TL_SL][TL_TJ];
+    MergeDesc& D = c.desc[blockIdx.y];
+    const int m = D.m, off = D.off;
+    const int j0 = blockIdx.x * TL_TJ;
+    if (j0 >= m) return;
+    const int out = threadIdx.x & (TL_TJ - 1), slice = threadIdx.x / TL_TJ;
+    const int j = j0 + out;
+    const double dj = (j < m) ? c.d[off + j] : 0.0;
+    int cnt = 0, tot = 0;
+    for (int t0 = 0; t0 < m; t0 += TL_RC) {
+        const int n_here = min((int)TL_RC, m - t0);
+        for (int t = threadIdx.x; t < n_here; t += TL_THREADS)
+            s_d[t] = (c.G[off + t0 + t] != -2) ? c.d[off + t0 + t] : __longlong_as_double(0x7ff8000000000000LL);
+        __syncthreads();
+        const int t1 = min(n_here, (slice + 1) * TL_SUB);
+#pragma unroll 4
+        for (int t = slice * TL_SUB; t < t1; ++t) {
+            const double dt = s_d[t];
+            cnt += ((dt < dj) || (dt == dj && t0 + t < j)) ? 1 : 0;
+            tot += (dt == dt) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    s_cnt[slice][out] = cnt; s_tot[slice][out] = tot;
+    __syncthreads();
+    if (slice == 0 && j < m) {
+#pragma unroll
+        for (int q = 1; q < TL_SL; ++q) { cnt += s_cnt[q][out]; tot += s_tot[q][out]; }
+        if (c.G[off + j] != -2) c.lsort[off + cnt] = j;
+        if (j == 0) D.nlive1 = tot;
     }
 }
 

@@ -631,7 +631,16 @@ void Solver::run_level(int li) {
         launch_items(stream, n, ZAssemble{c});
         if (L.any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
         launch_items(stream, n, FlagDeflate{c});
+#if CUPPEN_CUDA
+        {
+            const dim3 rk_grid((unsigned)((L.maxm + TL_TJ - 1) / TL_TJ), (unsigned)nd_cnt);
+            rank_tiled_kernel<<<rk_grid, TL_THREADS, 0, stream>>>(c);
+            CUDA_CHECK(cudaGetLastError());
+            g_launches.launches++;
+        }
+#else
         launch_warps(stream, n, RankLive{c});
+#endif
         launch_items(stream, n, GivensSweep{c});
 #if CUPPEN_CUDA
         compact_scan_kernel<<<(unsigned)nd_cnt, CS_THREADS, 0, stream>>>(c);
@@ -677,12 +686,20 @@ void Solver::run_level(int li) {
         }
         pt.begin(T_EVX, stream);
 #if CUPPEN_CUDA
+        // tiled kernels from m = TILED_MIN_M on; below, the warp-per-output functors are a few microseconds
+        // faster per launch (measured on `-s 1 -n 4096`, profiles/README.md)
+        const bool tiled = L.maxm >= TILED_MIN_M;
         const dim3 tl_grid((unsigned)((L.maxm + TL_TJ - 1) / TL_TJ), (unsigned)nd_cnt);
-        loewner_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
-        CUDA_CHECK(cudaGetLastError());
-        norms_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
-        CUDA_CHECK(cudaGetLastError());
-        g_launches.launches += 2;
+        if (tiled) {
+            loewner_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
+            CUDA_CHECK(cudaGetLastError());
+            norms_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
+            CUDA_CHECK(cudaGetLastError());
+            g_launches.launches += 2;
+        } else {
+            launch_warps(stream, n, Loewner{c});
+            launch_warps(stream, n, Norms{c});
+        }
 #else
         launch_warps(stream, n, Loewner{c});
         launch_warps(stream, n, Norms{c});
@@ -693,9 +710,11 @@ void Solver::run_level(int li) {
             pt.begin(T_EVX, stream);
             launch_items(stream, n, RowPack{c, rowc});
 #if CUPPEN_CUDA
-            rowgemv_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c, rowc);
-            CUDA_CHECK(cudaGetLastError());
-            g_launches.launches++;
+            if (tiled) {
+                rowgemv_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c, rowc);
+                CUDA_CHECK(cudaGetLastError());
+                g_launches.launches++;
+            } else launch_warps(stream, n, RowGemv{c, rowc});
 #else
             launch_warps(stream, n, RowGemv{c, rowc});
 #endif
@@ -785,7 +804,7 @@ void Solver::run_level(int li) {
 // ---- final ordering, eigenvector gather, residuals -------------------------------------------------
 void Solver::finish() {
     if (first_coop < 0 && G > 1) enter_cooperative();         // (cannot happen: G > 1 implies cooperative levels)
-    launch_warps(stream, n, FinalRank{n, lam.p, perm.p, lam_sorted.p});
+    launch_warps(stream, n, FinalRank{n, lam.p, perm.p, lam_sorted.p});     // (a tiled variant measured slower: DSETP-bound either way)
     dev_d2h(pin_lam, lam_sorted.p, sizeof(double) * n, stream);
     if (want_vectors) {
         pt.begin(T_RESID, stream);
@@ -1557,6 +1576,50 @@ int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* df
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
 #else
     (void)device; (void)ms; (void)dmma_tflops; (void)dfma_tflops;
+    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
+#endif
+    CUPPEN_API_END
+}
+
+// DMMA and DFMA loops sharing every SM: rates of each kind alone (half of the warps idle) and together.
+int cuppen_measure_fp64_mix(int device, double* dmma_alone, double* dfma_alone, double* dmma_mixed, double* dfma_mixed) {
+    CUPPEN_API_BEGIN
+#if CUPPEN_CUDA
+    if (!dmma_alone || !dfma_alone || !dmma_mixed || !dfma_mixed) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 2, threads = 256;
+    double* out = nullptr;
+    CUDA_CHECK(cudaMalloc(&out, sizeof(double) * blocks * threads));
+    cudaEvent_t a, b;
+    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
+    // iteration counts sized so that each kind alone runs ~20 ms: DMMA 16 x 512 flop per warp-iteration,
+    // DFMA 32 x 2 flop per thread-iteration
+    const int it_dmma = 100000, it_dfma = 400000;           // ~26 ms each when alone
+    auto run = [&](int i1, int i2) {
+        float best = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            CUDA_CHECK(cudaEventRecord(a));
+            fp64_mix_kernel<<<blocks, threads>>>(out, i1, i2);
+            CUDA_CHECK(cudaEventRecord(b));
+            CUDA_CHECK(cudaEventSynchronize(b));
+            float t = 0; cudaEventElapsedTime(&t, a, b);
+            best = std::min(best, t);
+        }
+        return (double)best * 1e-3;
+    };
+    const double fl_dmma = (double)blocks * 4 * it_dmma * 16.0 * 512.0;          // 4 DMMA warps per block
+    const double fl_dfma = (double)blocks * 128 * it_dfma * 64.0;                // 128 DFMA threads per block
+    const double t1 = run(it_dmma, 0), t2 = run(0, it_dfma), t3 = run(it_dmma, it_dfma);
+    *dmma_alone = fl_dmma / t1 * 1e-12;
+    *dfma_alone = fl_dfma / t2 * 1e-12;
+    // together: both finish inside t3 (the slower kind defines it); report the rates over the common window
+    *dmma_mixed = fl_dmma / t3 * 1e-12;
+    *dfma_mixed = fl_dfma / t3 * 1e-12;
+    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
+#else
+    (void)device; (void)dmma_alone; (void)dfma_alone; (void)dmma_mixed; (void)dfma_mixed;
     CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
 #endif
     CUPPEN_API_END
