@@ -278,7 +278,7 @@ def run_ours(a):
         "value": ms * 1e-3, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
         "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(a), "n": a.n, "matrix": a.matrix, "ref_leaves": a.ref_leaves,
-                   "l2": "256 MiB buffer zeroed between timed steps (untimed); Q working set 3x%.0f MB" % (8e-6 * a.n * a.n / world),
+                   "l2": "256 MiB buffer zeroed between timed steps (untimed); Q working set 2x%.0f MB (in place + packed live columns)" % (8e-6 * a.n * a.n / world),
                    "sharding": "eigenvector row blocks, %d rank(s)" % world},
         "wall_ms_per_step": float(np.mean(wall_ms)),
         "eigenpairs_per_s": a.n / (ms * 1e-3),

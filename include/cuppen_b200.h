@@ -90,7 +90,7 @@ typedef struct {
     double gemm_flop;        /* executed flop: sum 2*M*N*K over GEMM problems */
     double leaf_s, deflation_s, pack_s, residual_s;
     double device_s;         /* CUDA-event time from the first to the last launch of cuppen_solve */
-    double pack_bytes;       /* algorithmic bytes of pack_kernel: 8*rows*(columns read + columns written) */
+    double pack_bytes;       /* algorithmic bytes of pack_kernel (in place): per merge 8*rows*(zdefl/2 + live + 1.5*rotated) */
     double ugen_bytes;       /* algorithmic bytes of ugen_kernel: 8*K*N written */
     double secular_root_iters; /* reserved */
     long   kernel_launches;

@@ -28,7 +28,7 @@ struct MatCtx {
     int n;                // global size
     long ldq;             // leading dimension of the Q buffers and of Apack (local rows, padded)
     const double* Qold;   // children (block diagonal), column-major, local rows
-    double* Qnew;         // parents
+    double* Qnew;         // parents; the solver works in place (Qnew == Qold): every kernel reads a column before writing it
     double* Apack;        // packed live columns (K order), same shape as Q plus K_PAD columns
     double* B;            // U arena, row-major [n + pad][ldb]
     long ldb;
@@ -628,6 +628,17 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
     const int rbase = D.lr0 + blockIdx.y * PACK_ROWS * PACK_THREADS + threadIdx.x;      // local row
     if (rbase >= D.lr1) return;
     const bool etop = e < D.n1;
+    if (zdefl && M.Qnew == M.Qold) {
+        // in place: a z-deflated column keeps its own-half rows where they are; only the other half's rows of the
+        // parent block are new and must read zero (they may hold the previous solve's V)
+        double* dst = M.Qnew + (long)g * M.ldq;
+#pragma unroll
+        for (int t = 0; t < PACK_ROWS; ++t) {
+            const int r = rbase + t * PACK_THREADS;
+            if (r < D.lr1 && ((r < D.lsplit) != etop)) dst[r] = 0.0;
+        }
+        return;
+    }
     if (zdefl || Gg == -1) {
         // plain column move: own-half rows from the child, zeros in the other half (deflated columns
         // go to Q', live ones to their K slot of Apack -- only over the rows of their own half)

@@ -112,20 +112,18 @@ struct Solver {
 #if CUPPEN_CUDA
     cudaEvent_t ev_ap0 = nullptr, ev_ap1 = nullptr;
 #endif
-    DevBuf<double> Qa, Qb, Apack, B;
+    DevBuf<double> Qa, Apack, B;      // the merges work in place on Qa: Apack holds the packed live columns of a level
     DevBuf<LeafDesc> leaves;
     DevBuf<GemmProblem> probs;
     DevBuf<GemmTile> tiles;
-    double* Qcur = nullptr;       // children / final
-    double* Qnext = nullptr;
-    bool sorted_materialised = false;    // Qcur already holds the columns in ascending-lambda order
+    double* Qcur = nullptr;       // block-diagonal eigenvector matrix: children before a level, parents after it, V at the end
+    bool sorted_materialised = false;    // Qcur (= Apack's storage) holds the columns in ascending-lambda order
     void materialise_sorted();
     // one-GPU solves are captured into a CUDA graph on the second call and replayed afterwards
     // (the whole decomposition is enqueued without any host read-back); env CUPPEN_GRAPH=0 disables
     bool use_graph = true, graph_failed = false;
     int solves_done = 0;
     long graph_launches = 0;
-    bool graph_final_is_a = true;
     std::vector<LeafDesc> h_leaves;
     double* pin_lam = nullptr;           // pinned staging of the results read back at the end of a solve
     double* pin_res = nullptr;
@@ -154,10 +152,8 @@ struct Solver {
     std::vector<int> parent_of;              // plan node -> parent node id
 
     // ---- schedule: local levels (by height), then cooperative levels (by height) ------------------
-    struct Carry { int off, n, lr0, lr1; };  // finished block that waits for a higher parent
     struct LevelInfo {
         std::vector<int> ids;                // plan nodes merged at this step
-        std::vector<Carry> carry;            // blocks to copy along into the new Q buffer
         size_t desc_off = 0;                 // offset into desc_all
         int height = 0;
         bool coop = false;
@@ -251,7 +247,6 @@ void Solver::allocate() {
     if (want_vectors) {
         const size_t qelems = (size_t)ldq * (N + K_PAD + 2) + 4096;
         Qa.alloc(qelems);
-        Qb.alloc(qelems);
         Apack.alloc(qelems);
         // U arena: rows indexed by global pole index, W columns per panel (<= 2 GiB)
         const size_t cap = (size_t)1 << 28;
@@ -261,7 +256,6 @@ void Solver::allocate() {
         dev_zero(B.p, B.bytes(), stream);
         dev_zero(Apack.p, Apack.bytes(), stream);
         dev_zero(Qa.p, Qa.bytes(), stream);
-        dev_zero(Qb.p, Qb.bytes(), stream);
 #if CUPPEN_CUDA
         const char* rv = getenv("CUPPEN_RESID");
         if (rv && atoi(rv) > 0) resid_variant = atoi(rv);
@@ -351,7 +345,7 @@ LevelCtx Solver::level_ctx(int li) {
 
 MatCtx Solver::mat_ctx() {
     MatCtx M;
-    M.n = n; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qnext; M.Apack = Apack.p; M.B = B.p; M.ldb = ldb;
+    M.n = n; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qcur; M.Apack = Apack.p; M.B = B.p; M.ldb = ldb;       // in place
     return M;
 }
 
@@ -486,29 +480,6 @@ void Solver::prepare_levels() {
                 L.worst_tiles_small += (long)((re - rs + 63) / 64) * ((N + 63) / 64);
             }
         }
-        // finished blocks that are consumed later than the next step must be carried into the new buffer
-        if (want_vectors)
-            for (size_t id = 0; id < plan.nodes.size(); ++id) {
-                const PlanNode& nd = plan.nodes[id];
-                const int par = parent_of[id];
-                if (par < 0 || level_of[par] <= li) continue;                   // consumed now or earlier
-                int produced;                                                   // schedule index after which the block exists
-                if (!L.coop) {
-                    // layout L: only blocks of my own subtree exist
-                    if (nd.depth < glog || !(nd.off >= R0 && nd.off + nd.n <= R1)) continue;
-                    produced = (nd.left < 0) ? -1 : level_of[id];
-                } else {
-                    // layout C: the subtree roots (all of them, one slice each) and the cooperative nodes
-                    if (nd.depth > glog) continue;
-                    produced = (nd.depth == glog) ? first_coop - 1 : level_of[id];
-                }
-                if (produced >= li) continue;                                   // not there yet
-                Carry c;
-                c.off = nd.off; c.n = nd.n;
-                int ls;
-                local_rows(nd, L.coop, c.lr0, ls, c.lr1);
-                if (c.lr1 > c.lr0) L.carry.push_back(c);
-            }
     }
     if (desc_all.n < h_desc_all.size() + 1) desc_all.alloc(h_desc_all.size() + 1);
     if (node_of_all.n < hnode.size()) node_of_all.alloc(hnode.size());
@@ -549,7 +520,8 @@ void Solver::enter_cooperative() {
     }
     if (!want_vectors) return;
     // rows: my subtree block (nlocL x nlocL at columns [R0,R1)) is cut into G slices; slice j goes to rank j.
-    // staging: Apack (send, one contiguous len x nlocL block per destination), Qnext (receive)
+    // staging inside Apack: first the send blocks (one contiguous len x nlocL block per destination), then the
+    // receive blocks; Apack holds ldq*n >= 2 (n/G)^2 doubles for G >= 2
     const int me = comm.rank;
     std::vector<const void*> sp(G, nullptr);
     std::vector<void*> rp(G, nullptr);
@@ -570,21 +542,24 @@ void Solver::enter_cooperative() {
         }
         sofs += (size_t)len * nlocL;
     }
+    double* const rstage = Apack.p + round_up((long)sofs, 32);
     for (int s = 0; s < G; ++s) {
         const int len = crow0[s + 1] - crow0[s];
         rofs_of[s] = rofs;
-        rp[s] = Qnext + rofs; rb[s] = sizeof(double) * (size_t)len * sub_n[s];
+        rp[s] = rstage + rofs; rb[s] = sizeof(double) * (size_t)len * sub_n[s];
         rofs += (size_t)len * sub_n[s];
     }
+    if ((size_t)round_up((long)sofs, 32) + rofs > Apack.n)
+        CUPPEN_THROW(CUPPEN_ERR_STATE, "row redistribution needs %zu doubles of staging, Apack has %zu", (size_t)round_up((long)sofs, 32) + rofs, Apack.n);
     // my own slice moves inside the buffer: stage it like a received block
     {
         const int lo = slice_lo(me, me), len = slice_lo(me, me + 1) - lo;
 #if CUPPEN_CUDA
-        CUDA_CHECK(cudaMemcpy2DAsync(Qnext + rofs_of[me], sizeof(double) * len, Qcur + (long)R0 * ldq + lo, sizeof(double) * ldq,
+        CUDA_CHECK(cudaMemcpy2DAsync(rstage + rofs_of[me], sizeof(double) * len, Qcur + (long)R0 * ldq + lo, sizeof(double) * ldq,
                                      sizeof(double) * len, nlocL, cudaMemcpyDeviceToDevice, stream));
 #else
         for (int col = 0; col < nlocL; ++col)
-            memcpy(Qnext + rofs_of[me] + (size_t)col * len, Qcur + (long)(R0 + col) * ldq + lo, sizeof(double) * len);
+            memcpy(rstage + rofs_of[me] + (size_t)col * len, Qcur + (long)(R0 + col) * ldq + lo, sizeof(double) * len);
 #endif
     }
     comm.alltoallv(sp, sb, rp, rb, stream);
@@ -593,11 +568,11 @@ void Solver::enter_cooperative() {
         const int len = crow0[s + 1] - crow0[s];
         if (len <= 0) continue;
 #if CUPPEN_CUDA
-        CUDA_CHECK(cudaMemcpy2DAsync(Qcur + (long)sub_off[s] * ldq + crow0[s], sizeof(double) * ldq, Qnext + rofs_of[s],
+        CUDA_CHECK(cudaMemcpy2DAsync(Qcur + (long)sub_off[s] * ldq + crow0[s], sizeof(double) * ldq, rstage + rofs_of[s],
                                      sizeof(double) * len, sizeof(double) * len, sub_n[s], cudaMemcpyDeviceToDevice, stream));
 #else
         for (int col = 0; col < sub_n[s]; ++col)
-            memcpy(Qcur + (long)(sub_off[s] + col) * ldq + crow0[s], Qnext + rofs_of[s] + (size_t)col * len, sizeof(double) * len);
+            memcpy(Qcur + (long)(sub_off[s] + col) * ldq + crow0[s], rstage + rofs_of[s] + (size_t)col * len, sizeof(double) * len);
 #endif
     }
 }
@@ -763,7 +738,7 @@ void Solver::run_level(int li) {
 
         WorkCtx w;
         w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN;
-        w.ldq = ldq; w.ldb = ldb; w.Apack = Apack.p; w.B = B.p; w.Qnext = Qnext; w.lidx = lidx.p;
+        w.ldq = ldq; w.ldb = ldb; w.Apack = Apack.p; w.B = B.p; w.Qnext = Qcur; w.lidx = lidx.p;
         w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
         const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
         pt.begin(T_GEMM, stream);
@@ -783,22 +758,13 @@ void Solver::run_level(int li) {
         pt.end(stream);
     }
 
-    launch_items(stream, n, ExtractRows{c, Qnext, ldq, frow.p, lrow.p});
+    launch_items(stream, n, ExtractRows{c, Qcur, ldq, frow.p, lrow.p});
     if (coop && li + 1 < (int)levels.size()) {
         // first rows live on rank 0, last rows on rank G-1 (slice layout): replicate them for the next level
         comm.group_bcast(frow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), 0, 0, G, stream);
         comm.group_bcast(lrow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), G - 1, 0, G, stream);
     }
-    for (const Carry& cb : L.carry) {
-#if CUPPEN_CUDA
-        CUDA_CHECK(cudaMemcpy2DAsync(Qnext + (long)cb.off * ldq + cb.lr0, sizeof(double) * ldq, Qcur + (long)cb.off * ldq + cb.lr0,
-                                     sizeof(double) * ldq, sizeof(double) * (cb.lr1 - cb.lr0), cb.n, cudaMemcpyDeviceToDevice, stream));
-#else
-        for (int col = cb.off; col < cb.off + cb.n; ++col)
-            dev_d2d(Qnext + (long)col * ldq + cb.lr0, Qcur + (long)col * ldq + cb.lr0, sizeof(double) * (cb.lr1 - cb.lr0), stream);
-#endif
-    }
-    std::swap(Qcur, Qnext);
+    // in place: blocks that wait for a higher parent simply stay where they are
 }
 
 // ---- final ordering, eigenvector gather, residuals -------------------------------------------------
@@ -855,14 +821,14 @@ void Solver::materialise_sorted() {
 #if CUPPEN_CUDA
     {
         dim3 grid((unsigned)n, (unsigned)std::max(1, std::min(64, (nloc_final + 255) / 256)));
-        gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Qnext, ldq, nloc_final, perm.p);
+        gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Apack.p, ldq, nloc_final, perm.p);
         CUDA_CHECK(cudaGetLastError());
     }
 #else
-    gather_cols_host(Qcur, Qnext, ldq, nloc_final, perm.p, n);
+    gather_cols_host(Qcur, Apack.p, ldq, nloc_final, perm.p, n);
 #endif
     g_launches.launches++;
-    std::swap(Qcur, Qnext);
+    Qcur = Apack.p;                  // until the next solve, which starts from Qa again
     dev_sync(stream);
     sorted_materialised = true;
 }
@@ -912,7 +878,7 @@ void Solver::enqueue_solve() {
 #if CUPPEN_CUDA
     pt.record(ev_begin, stream);
 #endif
-    Qcur = Qa.p; Qnext = Qb.p;
+    Qcur = Qa.p;
     run_leaves();
     for (int li = 0; li < (int)levels.size(); ++li) run_level(li);
     if (!h_desc_all.empty()) dev_d2h(pin_desc, desc_all.p, sizeof(MergeDesc) * h_desc_all.size(), stream);
@@ -939,8 +905,7 @@ void Solver::solve() {
 #if CUPPEN_CUDA
     if (use_graph && !graph_failed && graph_exec) {
         CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
-        Qcur = graph_final_is_a ? Qa.p : Qb.p;
-        Qnext = graph_final_is_a ? Qb.p : Qa.p;
+        Qcur = Qa.p;
         g_launches.launches += graph_launches;
         replayed = true;
     } else if (use_graph && !graph_failed && solves_done >= 1) {
@@ -956,7 +921,6 @@ void Solver::solve() {
         if (ce == cudaSuccess && graph) ce = cudaGraphInstantiate(&graph_exec, graph, 0);
         if (ce == cudaSuccess && graph_exec) {
             graph_launches = g_launches.launches - l0;
-            graph_final_is_a = (Qcur == Qa.p);
             pt.keep = true;
             CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
             replayed = true;
@@ -1001,7 +965,10 @@ void Solver::solve() {
             stats.push_back(st);
             if (!want_vectors) continue;
             const double rows = D.lr1 - D.lr0;
-            acc_pack_bytes += 8.0 * rows * D.m + 8.0 * (rows / 2) * D.m;
+            // in place: a z-deflated column only gets zeros in the other half's rows; every other column is read over
+            // its own half and written either in full (deflated by a rotation) or over its own half into Apack (live)
+            const double zd = D.m - D.nlive1, rot = D.nlive1 - D.k, live = D.k;
+            acc_pack_bytes += 8.0 * rows * (0.5 * zd + 0.5 * (rot + live) + 1.0 * rot + 0.5 * live);
             acc_gemm_flop += 2.0 * D.k * ((double)(D.lsplit - D.lr0) * D.ktop + (double)(D.lr1 - D.lsplit) * D.kbot);
             acc_ugen_bytes += 8.0 * D.k * ((double)D.ktop + D.kbot);
         }
