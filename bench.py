@@ -273,6 +273,17 @@ def run_ours(a):
                 "peak_source": peak_src, "dominant_by_time": dom,
                 "gemm": {"achieved_tflops": gemm_tflops, "fp64_peak_tflops": fp64_peak,
                          "frac": gemm_tflops / fp64_peak if fp64_peak else None}}
+    # DRAM traffic of the roofline kernel from a committed `ncu --set full` capture of the same command, when there is one
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s|%d" % (workload_name(a), world))
+        if tr and tr["kernel"] == roof["kernel"]:
+            roof["traffic"] = tr["dram_bytes_per_launch"]
+            roof["traffic_source"] = tr["source"]
+    except Exception:
+        pass
+    if dom not in ("gemm", "pack", "ugen", "residual"):
+        roof["note"] = ("latency-bound configuration: %d launches per step, the largest phase (%s) is %.0f %% of it; the roofline "
+                        "is quoted for the only tensor-bound kernel" % (int(tsum["kernel_launches"]) // a.steps, dom, 100 * cats[dom] / ms))
     line = {
         "metric": "eigenpairs wall-time (s), full eigendecomposition (eigenvalues + eigenvectors + residuals)",
         "value": ms * 1e-3, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
