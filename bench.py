@@ -7,9 +7,11 @@ FP64 TFLOP/s of the full eigendecomposition of a synthetic symmetric tridiagonal
                                                            (oracle/_ref/cuppens_ref, else the oracle port)
 
 A "step" is one complete decomposition (leaves, all merges, back-transformation GEMMs, residuals) of
-the workload: at N=1 BASELINE configs[1] `-s 1 -n 4096 -e` with the reference tree of `mpirun -n 8`;
-at N>1 the same decomposition sharded by eigenvector row blocks (strong scaling).  `--size/--matrix/
---ref-leaves` select the other BASELINE configurations.  One JSON line is printed by rank 0.
+the workload: BASELINE configs[1] `-s 1 -n 4096 -e` with the reference tree of `mpirun -n 8`, at N>1 the same
+decomposition sharded by eigenvector row blocks (strong scaling; this small problem is latency-bound and does
+not speed up).  At N>1 the same run also measures BASELINE configs[2] -- the seeded random symmetric tridiagonal
+matrix of size 16384 sharded over the N ranks -- and reports it, with its own 1-GPU time, under "config2_sharded".
+`--size/--matrix/--ref-leaves` select the other BASELINE configurations.  One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -219,6 +221,52 @@ def run_ours(a):
             e2e.append(float(dt[0]))
     e2e_s = float(np.mean(e2e))
 
+    # ---- N > 1 with the default workload: BASELINE configs[2] (seeded random symmetric tridiagonal n=16384, divide tree
+    # sharded across the ranks) as an extra key next to the headline series, which keeps configs[1] at every N
+    config2 = None
+    if world > 1 and getattr(a, "secondary", False):
+        n2, kind2 = 16384, "goe"
+        idt = torch.zeros(api.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(se.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        D2, E2 = make_matrix(kind2, n2)
+        s2 = se.CuppenSolver(n2, ref_leaves=a.ref_leaves, vectors=True, device=local, rank=rank, world=world,
+                             nccl_id=bytes(idt.cpu().numpy().tobytes()))
+        s2.set_tridiagonal(D2, E2)
+        for _ in range(3):
+            s2.solve()
+        ms2, t2sum = [], None
+        for _ in range(3):
+            flush.zero_()
+            barrier()
+            s2.solve()
+            t2 = s2.timers()
+            v = torch.tensor([t2["device_s"] * 1e3], dtype=torch.float64, device="cuda")
+            dist.all_reduce(v, op=dist.ReduceOp.MAX)
+            ms2.append(float(v[0]))
+            t2sum = t2 if t2sum is None else {k: t2sum[k] + t2[k] for k in t2}
+        res2 = float(s2.residuals().max())
+        s2.close()
+        solo_s = None
+        if rank == 0:
+            solo = se.CuppenSolver(n2, ref_leaves=a.ref_leaves, vectors=True, device=local)
+            solo.set_tridiagonal(D2, E2)
+            tt = []
+            for it in range(3):
+                solo.solve()
+                if it > 0:
+                    tt.append(solo.timers()["device_s"])
+            solo.close()
+            solo_s = float(np.mean(tt))
+        barrier()
+        if rank == 0:
+            v2 = float(np.mean(ms2)) * 1e-3
+            config2 = {"workload": "cuppens -i goe(seeded) -n %d -e, reference tree mpirun -n %d, sharded over %d GPUs" % (n2, a.ref_leaves, world),
+                       "value": v2, "unit": "s", "steps": 3, "same_workload_1gpu_s": solo_s, "speedup_vs_1gpu": solo_s / v2,
+                       "gemm_tflops_executed_rank0": t2sum["gemm_flop"] / t2sum["gemm_s"] * 1e-12 if t2sum["gemm_s"] > 0 else None,
+                       "tflops_fp64_nominal_4n3_over_3": (4.0 / 3.0) * n2 ** 3 / v2 * 1e-12, "max_residual": res2}
+
     if rank != 0:
         solver.close()
         if world > 1:
@@ -283,7 +331,7 @@ def run_ours(a):
         pass
     if dom not in ("gemm", "pack", "ugen", "residual"):
         roof["note"] = ("latency-bound configuration: %d launches per step, the largest phase (%s) is %.0f %% of it; the roofline "
-                        "is quoted for the only tensor-bound kernel" % (int(tsum["kernel_launches"]) // a.steps, dom, 100 * cats[dom] / ms))
+                        "is quoted for the only tensor-bound kernel" % (int(tsum["kernel_launches"]) // a.steps, dom, 100 * cats[dom] / (ms * 1e-3)))
     line = {
         "metric": "eigenpairs wall-time (s), full eigendecomposition (eigenvalues + eigenvectors + residuals)",
         "value": ms * 1e-3, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
@@ -302,6 +350,7 @@ def run_ours(a):
         "roofline": roof,
         "fp64_yardsticks_tflops": {"dmma_issue_loop": dmma_tf, "dfma_issue_loop": dfma_tf, "cublas_dgemm_8192": dgemm_tf},
         "clocks": clocks,
+        "config2_sharded": config2,
         "check": {"max_residual": float(res.max()), "lambda_min": float(lam[0]), "lambda_max": float(lam[-1])},
     }
     if world == 1:
@@ -454,12 +503,14 @@ def main():
     ap.add_argument("--no-single-gpu-compare", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=25.0, help="seconds of CPU work per reference step")
     a = ap.parse_args()
-    # default workload: BASELINE configs[1] (`-s 1 -n 4096`, one B200) at N=1; configs[2] (seeded random
-    # symmetric tridiagonal n=16384, divide tree sharded across 2/4/8 B200) at N>1
+    # default workload: BASELINE configs[1] (`-s 1 -n 4096`) at every N, so that the per-N values form one strong-scaling
+    # series; at N>1 BASELINE configs[2] (seeded random symmetric tridiagonal n=16384, divide tree sharded across
+    # 2/4/8 B200) is measured in the same run and reported under "config2_sharded"
+    a.secondary = (a.n is None and a.matrix is None and a.gpus > 1 and a.impl == "ours")
     if a.n is None:
-        a.n = 4096 if a.gpus == 1 else 16384
+        a.n = 4096
     if a.matrix is None:
-        a.matrix = "s1" if a.gpus == 1 else "goe"
+        a.matrix = "s1"
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference_arm(a)

@@ -16,6 +16,9 @@
 #include "merge_stages.h"
 #include "secular_core.h"
 #include "gemm_dmma.h"
+#if CUPPEN_CUDA
+#include <cooperative_groups.h>
+#endif
 
 namespace cuppen {
 
@@ -568,27 +571,45 @@ __global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
     }
 }
 
-// Fused front end for the small merges at the bottom of the tree: one CTA per merge runs every vector
-// stage (z assembly ... new eigenvalues, and in eigenvalue-only mode the boundary-row update) back
-// to back with block barriers in between, instead of ~12 separate launches per level.
+// Fused front end for the small merges at the bottom of the tree: a thread-block CLUSTER of FUSE_CL CTAs per
+// merge runs every vector stage (z assembly ... new eigenvalues, and in eigenvalue-only mode the boundary-row
+// update) back to back with cluster barriers in between, instead of ~12 separate launches per level.  The stages
+// communicate through global memory (L2); the hardware cluster barrier (release/acquire at cluster scope) orders
+// it.  One CTA per merge left 3/4 of the SMs idle at these levels (32 ... 128 merges at n = 4096) and spent
+// ~20 us per level in the secular stage alone (8 roots per warp, one after the other).  Levels with more merges
+// than SMs keep one CTA per merge and plain __syncthreads (launch_fused_front) -- measured: n=4096 deflation phase
+// 0.33 -> 0.29 ms with clusters of 4, while clusters of 4 on the 512- and 256-merge levels of n=16384 cost
+// 0.85 -> 1.07 ms.
 enum { FUSE_MAXM = 128, FUSE_THREADS = 512 };
-__global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, RowCtx rc, int rows_mode) {
-    const int id = blockIdx.x;
+template <int FUSE_CL>
+struct FuseSync {
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    __device__ __forceinline__ void sync() { cl.sync(); }
+};
+template <>
+struct FuseSync<1> {
+    __device__ __forceinline__ void sync() { __syncthreads(); }
+};
+template <int FUSE_CL>
+__device__ __forceinline__ void fused_front_body(LevelCtx c, RowCtx rc, int rows_mode) {
+    FuseSync<FUSE_CL> cl;
+    const int id = blockIdx.x / FUSE_CL;
     const int off = c.desc[id].off, m = c.desc[id].m;
-    const int tid = threadIdx.x, warp = tid >> 5, nwarps = FUSE_THREADS / 32;
+    const int nthreads = FUSE_THREADS * FUSE_CL;
+    const int tid = (blockIdx.x % FUSE_CL) * FUSE_THREADS + threadIdx.x, warp = tid >> 5, nwarps = nthreads / 32;
     const WarpLanes L;
-    for (int g = off + tid; g < off + m; g += FUSE_THREADS) ZAssemble{c}(g);
-    __syncthreads();
+    for (int g = off + tid; g < off + m; g += nthreads) ZAssemble{c}(g);
+    cl.sync();
     if (warp == 0) MergeTol{c}(id, L);
-    __syncthreads();
-    for (int g = off + tid; g < off + m; g += FUSE_THREADS) FlagDeflate{c}(g);
-    __syncthreads();
+    cl.sync();
+    for (int g = off + tid; g < off + m; g += nthreads) FlagDeflate{c}(g);
+    cl.sync();
     for (int g = off + warp; g < off + m; g += nwarps) RankLive{c}(g, L);
-    __syncthreads();
-    for (int g = off + tid; g < off + m; g += FUSE_THREADS) GivensSweep{c}(g);
-    __syncthreads();
+    cl.sync();
+    for (int g = off + tid; g < off + m; g += nthreads) GivensSweep{c}(g);
+    cl.sync();
     for (int g = off + warp; g < off + m; g += nwarps) Compact{c}(g, L);
-    __syncthreads();
+    cl.sync();
     {
         const MergeDesc& D = c.desc[id];
         const int k = D.k;
@@ -597,19 +618,29 @@ __global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, R
             if (L.lane() == 0) { c.org[off + i] = r.origin; c.tau[off + i] = r.tau; }
         }
     }
-    __syncthreads();
+    cl.sync();
     for (int g = off + warp; g < off + m; g += nwarps) Loewner{c}(g, L);
-    __syncthreads();
+    cl.sync();
     for (int g = off + warp; g < off + m; g += nwarps) Norms{c}(g, L);
-    __syncthreads();
-    for (int g = off + tid; g < off + m; g += FUSE_THREADS) NewLambda{c}(g);
+    cl.sync();
+    for (int g = off + tid; g < off + m; g += nthreads) NewLambda{c}(g);
     if (!rows_mode) return;
-    __syncthreads();
-    for (int g = off + tid; g < off + m; g += FUSE_THREADS) RowPack{c, rc}(g);
-    __syncthreads();
+    cl.sync();
+    for (int g = off + tid; g < off + m; g += nthreads) RowPack{c, rc}(g);
+    cl.sync();
     for (int g = off + warp; g < off + m; g += nwarps) RowGemv{c, rc}(g, L);
-    __syncthreads();
-    for (int g = off + tid; g < off + m; g += FUSE_THREADS) RowCommit{c, rc, const_cast<double*>(c.frow), const_cast<double*>(c.lrow)}(g);
+    cl.sync();
+    for (int g = off + tid; g < off + m; g += nthreads) RowCommit{c, rc, const_cast<double*>(c.frow), const_cast<double*>(c.lrow)}(g);
+}
+__global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, RowCtx rc, int rows_mode) { fused_front_body<1>(c, rc, rows_mode); }
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FUSE_THREADS) fused_front_cl4_kernel(LevelCtx c, RowCtx rc, int rows_mode) { fused_front_body<4>(c, rc, rows_mode); }
+
+// a cluster of 4 CTAs per merge when one CTA per merge cannot fill the SMs (measured on the B200: -s 1 -n 4096,
+// levels of 128 / 64 / 32 merges, step 1.29 -> 1.23 ms; clusters of 8 or clusters on fuller levels were slower)
+inline void launch_fused_front(Stream st, int num_sms, int merges, LevelCtx c, RowCtx rc, int rows_mode) {
+    if (merges <= num_sms) fused_front_cl4_kernel<<<(unsigned)merges * 4, FUSE_THREADS, 0, st>>>(c, rc, rows_mode);
+    else fused_front_kernel<<<(unsigned)merges, FUSE_THREADS, 0, st>>>(c, rc, rows_mode);
+    CUDA_CHECK(cudaGetLastError());
 }
 
 // K5a: walk every rotation chain once per row.  grid.x = global column, grid.y = row chunk.

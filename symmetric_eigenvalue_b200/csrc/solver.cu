@@ -596,8 +596,7 @@ void Solver::run_level(int li) {
     if (fused) {
 #if CUPPEN_CUDA
         pt.begin(T_DEFL, stream);
-        fused_front_kernel<<<(unsigned)nd_cnt, FUSE_THREADS, 0, stream>>>(c, rowc, want_vectors ? 0 : 1);
-        CUDA_CHECK(cudaGetLastError());
+        launch_fused_front(stream, num_sms, nd_cnt, c, rowc, want_vectors ? 0 : 1);
         g_launches.launches++;
         pt.end(stream);
 #endif
