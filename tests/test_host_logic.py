@@ -261,3 +261,27 @@ def test_hostemu_orthogonality_and_eigenvector_file(hostemu, oracle, tmp_path):
     with pytest.raises(se.CuppenError):
         s.orthogonality()
     s.close()
+
+
+def test_hostemu_select_mode_baseline_config(hostemu):
+    """BASELINE configs[1] (`-s 1 -n 4096`, reference tree P=8) with `-eFILE`-style selection: eigenvalues and
+    deflation counts as the reference printed them, residuals of the selected vectors at the level the
+    reference's 1e-6 z-deflation allows (golden s1_n1024_p4: 1.3e-6)."""
+    g = load_golden("s1_n4096_p8")
+    sel = list(range(0, 4096, 256)) + [4095]
+    out = se.cuppens(g["D"], g["E"], ref_leaves=8, lib=hostemu, select=sel)
+    check_against_golden(g, out, False)
+    assert out["V"].shape == (4096, len(sel)) and np.abs(np.linalg.norm(out["V"], axis=0) - 1).max() < 1e-12
+    assert out["resid"].max() < 2e-6
+    D, E, V, lam = g["D"], g["E"], out["V"], out["lam"][sel]
+    TV = D[:, None] * V
+    TV[1:] += E[:, None] * V[:-1]
+    TV[:-1] += E[:, None] * V[1:]
+    assert np.allclose(np.linalg.norm(TV - V * lam[None, :], axis=0), out["resid"], rtol=1e-6, atol=1e-13)
+
+
+def test_cli_help_lists_every_option(product_lib):
+    exe = os.path.join(ROOT, "cuppens")
+    r = subprocess.run([exe, "-h"], capture_output=True, text=True)
+    for opt in (" -h", " -i FILENAME", " -s NUM", " -n NUM", " -e(FILENAME)", " -p NUM", " -g NUM", " -v FILENAME", " -c"):
+        assert opt + "\n" in r.stdout, opt
