@@ -46,7 +46,18 @@ def golden_cases():
 
 def load_golden(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
-    return dict(D=z["D"], E=z["E"], P=int(z["P"]), lam=z["lam"], resid=z["resid"], merges=z["merges"], rhos=z["rhos"])
+    return dict(D=z["D"], E=z["E"], P=int(z["P"]), lam=z["lam"], resid=z["resid"], merges=z["merges"], rhos=z["rhos"],
+                sel=(z["sel"] if "sel" in z.files else None))
+
+
+def check_select_against_efile_golden(g, out):
+    """Selected-eigenvector mode against the reference's own `-eFILE` run (golden `*_sel`): eigenvalues within
+    1e-12*||T||, identical deflation counts, residuals of the selected vectors at or below the reference's."""
+    check_against_golden(g, out, False)
+    nT = norm_T(g["D"], g["E"])
+    ref = g["resid"][g["sel"] - 1]
+    assert np.isfinite(ref).all()
+    assert (out["resid"] <= ref.max() * 1.05 + 4 * 2.2e-16 * nT).all(), (out["resid"], ref)
 
 
 def norm_T(D, E):

@@ -4,7 +4,7 @@ oracle/Makefile from /root/reference with the MPI/MKL shims) on the inputs liste
 Run in the build container (needs /root/reference):   python tests/golden/make_golden.py
 Each file holds: D, E (input), P, lam (column 1 of the reference's output file), resid (column 2,
 NaN where the reference printed none), merges (m, offset, zdefl, givens per merge from the
-CUPPEN_ORACLE_STATS hook) and rhos.
+CUPPEN_ORACLE_STATS hook) and rhos; the `*_sel` cases also hold sel, the 1-based indices of the -eFILE run.
 """
 import os
 import sys
@@ -41,6 +41,10 @@ CASES = [
     ("goe_n4096_p8", ("goe", 4096), 8, False),
     ("wilk64_n16384_p8", ("wilk", 16384), 8, False),
     ("randu_n16384_p8", ("randu", 16384), 8, False),
+    # -eFILE at BASELINE configs[1] / a GEMM-heavy input: the reference back-transforms only the listed (1-based)
+    # indices (src/filehandling.c:165-239,339-345; ~4 s per vector here) -- pins the selected-eigenvector mode
+    ("s1_n4096_p8_sel", ("scheme", 1, 4096), 8, [1, 1000, 2048, 4096]),
+    ("goe_n4096_p8_sel", ("goe", 4096), 8, [2, 2049, 4095]),
 ]
 
 
@@ -68,12 +72,20 @@ def main():
                 oracle.write_mtx(mtx, D, E)
                 args = ["-i", mtx]
             out = os.path.join(td, "out.txt")
-            r = oracle.run_reference(args + (["-e"] if vec else []) + [out], P=P, threads=1, timeout=1800)
+            sel = vec if isinstance(vec, list) else None
+            if sel is not None:
+                evf = os.path.join(td, "ev.txt")
+                open(evf, "w").write("".join("%d\n" % i for i in sel))
+                eopt = ["-e" + evf]
+            else:
+                eopt = ["-e"] if vec else []
+            r = oracle.run_reference(args + eopt + [out], P=P, threads=2 if sel is not None else 1, timeout=1800)
             assert r["rc"] == 0 and "Program finished successfully!" in r["stdout"], (name, r["rc"], r["stderr"])
             lam, res = read_output(out)
         merges = np.array([[m["m"], m["off"], m["zdefl"], m["givens"]] for m in r["merges"]], dtype=np.int32).reshape(-1, 4)
         rhos = np.array([m["rho"] for m in r["merges"]])
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), D=D, E=E, P=P, lam=lam, resid=res, merges=merges, rhos=rhos)
+        extra = {"sel": np.array(sel, dtype=np.int32)} if sel is not None else {}
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), D=D, E=E, P=P, lam=lam, resid=res, merges=merges, rhos=rhos, **extra)
         print(name, "n=%d P=%d merges=%s max resid=%s" % (len(D), P, merges[:, [0, 2, 3]].tolist()[-1:] if len(merges) else [],
                                                            np.nanmax(res) if vec else None), flush=True)
 

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import symmetric_eigenvalue_b200 as se
-from conftest import ROOT, check_against_golden, golden_cases, load_golden, norm_T, ref_stats
+from conftest import ROOT, check_against_golden, check_select_against_efile_golden, golden_cases, load_golden, norm_T, ref_stats
 
 pytestmark = pytest.mark.gpu
 
@@ -288,3 +288,11 @@ def test_residual_kernel_slices(lib, n, g0, l0, cnt):
     from symmetric_eigenvalue_b200 import api
     for variant in (0, 14, 83):
         assert api.selftest_residual(n, g0, l0, cnt, variant=variant, lib=lib)[0] < 1e-13
+
+
+@pytest.mark.parametrize("name", ["s1_n4096_p8_sel", "goe_n4096_p8_sel"])
+def test_select_mode_against_reference_efile_goldens(lib, name):
+    """Selected-eigenvector mode against the reference's own `-eFILE` output at n=4096, P=8."""
+    g = load_golden(name)
+    out = se.cuppens(g["D"], g["E"], ref_leaves=g["P"], lib=lib, select=(g["sel"] - 1).tolist())
+    check_select_against_efile_golden(g, out)

@@ -11,7 +11,7 @@ import pytest
 
 import symmetric_eigenvalue_b200 as se
 from symmetric_eigenvalue_b200 import api
-from conftest import ROOT, check_against_golden, golden_cases, load_golden, norm_T, ref_stats
+from conftest import ROOT, check_against_golden, check_select_against_efile_golden, golden_cases, load_golden, norm_T, ref_stats
 
 
 # ---- the shipped library -----------------------------------------------------------------------------
@@ -285,3 +285,11 @@ def test_cli_help_lists_every_option(product_lib):
     r = subprocess.run([exe, "-h"], capture_output=True, text=True)
     for opt in (" -h", " -i FILENAME", " -s NUM", " -n NUM", " -e(FILENAME)", " -p NUM", " -g NUM", " -v FILENAME", " -c"):
         assert opt + "\n" in r.stdout, opt
+
+
+@pytest.mark.parametrize("name", ["s1_n4096_p8_sel", "goe_n4096_p8_sel"])
+def test_hostemu_select_mode_against_reference_efile_goldens(hostemu, name):
+    """The reference's own `-eFILE` output at n=4096, P=8 (tests/golden/make_golden.py, ~4 s per vector there)."""
+    g = load_golden(name)
+    out = se.cuppens(g["D"], g["E"], ref_leaves=g["P"], lib=hostemu, select=(g["sel"] - 1).tolist())
+    check_select_against_efile_golden(g, out)
