@@ -125,6 +125,10 @@ int main(int argc, char** argv) {
         default: return 1;
     }
     if (argc - optind > 1) { fprintf(stderr, "Invalid number of positional arguments. See help.\n"); return 1; }
+    if (gpus > 1 && (vecFile != NULL || checkOrth)) {
+        fprintf(stderr, "Options -v and -c need a single GPU (the rows of V are distributed over the GPUs). See help.\n");
+        return 1;
+    }
     outputfile = argv[optind];
 
     if (inputfile != NULL) printf("Input file: %s\n", inputfile);
