@@ -655,10 +655,30 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
     const int off = D.off, e = g - off;
     const int Gg = c.G[g];
     const bool zdefl = (Gg == -2);
-    if (!zdefl && !c.head[g]) return;
     const int rbase = D.lr0 + blockIdx.y * PACK_ROWS * PACK_THREADS + threadIdx.x;      // local row
     if (rbase >= D.lr1) return;
     const bool etop = e < D.n1;
+    // (the zdefl / head early return was moved below the tail zeroing)
+    {
+        // zero the K tail of Apack: columns [kh, round_up(kh, K_PAD)) of each half -- the GEMM reads K in multiples
+        // of K_PAD.  Column off+e is handled by this block; a tail that runs past the node's last column (m not a
+        // multiple of K_PAD) is finished by the block of the last column.  (Was a separate launch, pack_tail_kernel.)
+        const int kt = D.ktop, kb = D.kbot;
+        const int kt_end = (kt + K_PAD - 1) / K_PAD * K_PAD, kb_end = (kb + K_PAD - 1) / K_PAD * K_PAD;
+        const int last = (e == D.m - 1) ? max(kt_end, kb_end) : e + 1;
+        for (int kk = e; kk < last; ++kk) {
+            if (!((kk >= kt && kk < kt_end) || (kk >= kb && kk < kb_end))) continue;
+#pragma unroll
+            for (int t = 0; t < PACK_ROWS; ++t) {
+                const int r = rbase + t * PACK_THREADS;
+                if (r >= D.lr1) break;
+                const bool rtop = r < D.lsplit;
+                const int kh = rtop ? kt : kb, kend = rtop ? kt_end : kb_end;
+                if (kk >= kh && kk < kend) M.Apack[(long)r + (long)(off + kk) * M.ldq] = 0.0;
+            }
+        }
+    }
+    if (!zdefl && !c.head[g]) return;
     if (zdefl && M.Qnew == M.Qold) {
         // in place: a z-deflated column keeps its own-half rows where they are; only the other half's rows of the
         // parent block are new and must read zero (they may hold the previous solve's V)
@@ -713,18 +733,6 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
         const int pos = rtop ? c.tpos[off + a] : c.bpos[off + a];
         if (pos >= 0) M.Apack[rl + (long)(off + pos) * M.ldq] = carry;
     }
-}
-
-// zero the K tail of Apack: columns [kh, round_up(kh,K_PAD)) of each half.  grid.x = descriptor,
-// grid.y = row chunk.
-__global__ void __launch_bounds__(128) pack_tail_kernel(LevelCtx c, MatCtx M) {
-    const MergeDesc& D = c.desc[blockIdx.x];
-    const int r = D.lr0 + blockIdx.y * 128 + threadIdx.x;      // local row
-    if (r >= D.lr1) return;
-    const bool rtop = r < D.lsplit;
-    const int kh = rtop ? D.ktop : D.kbot;
-    const int kend = (kh + K_PAD - 1) / K_PAD * K_PAD;
-    for (int kk = kh; kk < kend; ++kk) M.Apack[(long)r + (long)(D.off + kk) * M.ldq] = 0.0;
 }
 
 // K5b: B[row = arena row of pole j][col = root i - p0] = zhat_j / (((d_j - d_org(i)) - tau_i) N_i)

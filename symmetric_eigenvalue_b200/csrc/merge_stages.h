@@ -51,6 +51,8 @@ struct LevelCtx {
     double* lam;           // [n] eigenvalues of the current nodes (children in, parents out)
     const double* frow;    // [n] first row of each current node's Q
     const double* lrow;    // [n] last row
+    const double* Qz;      // vector mode on one GPU: the children's Q itself (boundary rows are read from it, no
+    long ldqz;             //   ExtractRows pass); nullptr: use frow / lrow
     double* d;             // [n] poles in child order
     double* z;             // [n]
     double* dn;            // [n] poles after the Givens sweep
@@ -93,7 +95,11 @@ struct ZAssemble {
             W.nlive1 = 0; W.k = 0; W.ktop = 0; W.kbot = 0; W.sumw = 0.0;
         }
         c.d[g] = c.lam[g];
-        double zv = (j < D.n1) ? c.lrow[g] : c.frow[g] / D.theta;
+        double zv;
+        if (c.Qz != nullptr)    // last row of the upper child / first row of the lower child, straight from Q
+            zv = (j < D.n1) ? c.Qz[(long)(D.lsplit - 1) + g * c.ldqz] : c.Qz[(long)D.lsplit + g * c.ldqz] / D.theta;
+        else
+            zv = (j < D.n1) ? c.lrow[g] : c.frow[g] / D.theta;
         c.z[g] = zv * D.zscale;
         c.G[g] = -1;
         c.head[g] = 0;
@@ -141,6 +147,15 @@ struct FlagDeflate {
             c.dn[g] = c.d[g];
             c.zn[g] = zg;
         }
+    }
+};
+
+// levels without accurate-rule merges (no tolerance reduction needed): z assembly and deflation flags in one pass
+struct ZAssembleFlag {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        ZAssemble{c}(g);
+        FlagDeflate{c}(g);
     }
 };
 

@@ -336,6 +336,9 @@ LevelCtx Solver::level_ctx(int li) {
     if (select_mode && li >= lvl_cap) CUPPEN_THROW(CUPPEN_ERR_STATE, "level %d beyond the %d per-level slices", li, lvl_cap);
     const size_t o = select_mode ? (size_t)li * lvl_stride : 0;
     c.n = n; c.desc = desc_all.p + levels[li].desc_off; c.node_of = node_of_all.p + (size_t)li * n; c.lam = lam.p; c.frow = frow.p; c.lrow = lrow.p;
+    // one GPU with eigenvectors: z is read from the rows of Q directly (no ExtractRows pass between the levels)
+    c.Qz = (want_vectors && G == 1) ? Qcur : nullptr;
+    c.ldqz = ldq;
     c.d = d.p + o; c.z = z.p + o; c.dn = dn.p + o; c.zn = zn.p + o; c.G = G_.p + o; c.gc = gc.p + o; c.gs = gs.p + o; c.lsort = lsort.p + o;
     c.head = head.p + o; c.sup = sup.p + o; c.prev = prev.p + o; c.tpos = tpos.p + o; c.bpos = bpos.p + o; c.dl = dl.p + o; c.wl = wl.p + o; c.zl = zl.p + o;
     c.lidx = lidx.p + o; c.org = org.p + o; c.tau = tau.p + o; c.zhat = zhat.p + o; c.nrm = nrm.p + o; c.toplist = toplist.p + o;
@@ -602,9 +605,11 @@ void Solver::run_level(int li) {
 #endif
     } else {
         pt.begin(T_DEFL, stream);
-        launch_items(stream, n, ZAssemble{c});
-        if (L.any_accurate) launch_warps(stream, nd_cnt, MergeTol{c});
-        launch_items(stream, n, FlagDeflate{c});
+        if (L.any_accurate) {
+            launch_items(stream, n, ZAssemble{c});
+            launch_warps(stream, nd_cnt, MergeTol{c});
+            launch_items(stream, n, FlagDeflate{c});
+        } else launch_items(stream, n, ZAssembleFlag{c});
 #if CUPPEN_CUDA
         {
             const dim3 rk_grid((unsigned)((L.maxm + TL_TJ - 1) / TL_TJ), (unsigned)nd_cnt);
@@ -703,17 +708,18 @@ void Solver::run_level(int li) {
 #if CUPPEN_CUDA
     if (L.maxm_rows > 0) {
         dim3 grid((unsigned)n, (unsigned)((L.maxm_rows + PACK_THREADS * PACK_ROWS - 1) / (PACK_THREADS * PACK_ROWS)));
-        pack_kernel<<<grid, PACK_THREADS, 0, stream>>>(c, M);
-        CUDA_CHECK(cudaGetLastError());
-        dim3 grid2((unsigned)nd_cnt, (unsigned)((L.maxm_rows + 127) / 128));
-        pack_tail_kernel<<<grid2, 128, 0, stream>>>(c, M);
+        pack_kernel<<<grid, PACK_THREADS, 0, stream>>>(c, M);          // (also zeroes the K tail of Apack)
         CUDA_CHECK(cudaGetLastError());
     }
 #else
     pack_host(c, M);
     pack_tail_host(c, M, nd_cnt);
 #endif
+#if CUPPEN_CUDA
+    g_launches.launches += 1;
+#else
     g_launches.launches += 2;
+#endif
     pt.end(stream);
 
     // panels of W root columns: U generation, device-built work list, one GEMM launch over all
@@ -757,7 +763,7 @@ void Solver::run_level(int li) {
         pt.end(stream);
     }
 
-    launch_items(stream, n, ExtractRows{c, Qcur, ldq, frow.p, lrow.p});
+    if (c.Qz == nullptr) launch_items(stream, n, ExtractRows{c, Qcur, ldq, frow.p, lrow.p});
     if (coop && li + 1 < (int)levels.size()) {
         // first rows live on rank 0, last rows on rank G-1 (slice layout): replicate them for the next level
         comm.group_bcast(frow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), 0, 0, G, stream);
@@ -1420,7 +1426,7 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     Stream s = 0;
     fill_kernel<<<(unsigned)((A.n + 255) / 256), 256>>>(A.p, (long)A.n, 1u);
     fill_kernel<<<(unsigned)((Bm.n + 255) / 256), 256>>>(Bm.p, (long)Bm.n, 2u);
-    // zero the K tail of A (columns K..Kp) as pack_tail_kernel does
+    // zero the K tail of A (columns K..Kp) as pack_kernel does
     if (Kp > K) CUDA_CHECK(cudaMemset(A.p + (size_t)K * lda, 0, sizeof(double) * (size_t)(Kp - K) * lda));
     CUDA_CHECK(cudaMemset(C.p, 0, C.bytes()));
     CUDA_CHECK(cudaMemset(err.p, 0, sizeof(double)));
