@@ -188,8 +188,10 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
                         early = true;
                         break;
                     }
-                    r = sqrt(h2);
-                    const double rinv = 1.0 / r;
+                    // one reciprocal square root instead of a square root followed by a division: the scalar
+                    // recurrence is the serial chain that bounds the kernel
+                    const double rinv = rsqrt(h2);
+                    r = h2 * rinv;
                     e[i + 1] = r;
                     s = f * rinv;
                     c = g * rinv;
@@ -738,8 +740,11 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
 // K5b: B[row = arena row of pole j][col = root i - p0] = zhat_j / (((d_j - d_org(i)) - tau_i) N_i)
 // grid.x = arena row (global index), grid.y = a few column lanes; a block strides over the 256-wide
 // column chunks of its row (the live count k is only known on the device).
-__global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width) {
+__global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width, int new_lambda) {
     const int row = blockIdx.x;
+    // the new eigenvalues of the level (NewLambda, one thread per index) ride along with the first panel: nothing
+    // between here and the next level's z assembly reads lam
+    if (new_lambda && blockIdx.y == 0 && threadIdx.x == 0) NewLambda{c}(row);
     const int id = c.node_of[row];
     if (id < 0) return;
     const MergeDesc& D = c.desc[id];

@@ -683,7 +683,11 @@ void Solver::run_level(int li) {
         launch_warps(stream, n, Loewner{c});
         launch_warps(stream, n, Norms{c});
 #endif
+#if CUPPEN_CUDA
+        if (!want_vectors) launch_items(stream, n, NewLambda{c});      // with eigenvectors: inside the first ugen_kernel launch
+#else
         launch_items(stream, n, NewLambda{c});
+#endif
         pt.end(stream);
         if (!want_vectors) {
             pt.begin(T_EVX, stream);
@@ -732,7 +736,7 @@ void Solver::run_level(int li) {
 #if CUPPEN_CUDA
         {
             dim3 grid((unsigned)n, (unsigned)std::min(4, (width + 255) / 256));
-            ugen_kernel<<<grid, 256, 0, stream>>>(c, M, p0, width);
+            ugen_kernel<<<grid, 256, 0, stream>>>(c, M, p0, width, (!fused && p0 == 0) ? 1 : 0);
             CUDA_CHECK(cudaGetLastError());
         }
 #else
