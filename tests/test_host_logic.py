@@ -295,3 +295,20 @@ def test_hostemu_select_mode_against_reference_efile_goldens(hostemu, name):
     g = load_golden(name)
     out = se.cuppens(g["D"], g["E"], ref_leaves=g["P"], lib=hostemu, select=(g["sel"] - 1).tolist())
     check_select_against_efile_golden(g, out)
+
+
+@pytest.mark.parametrize("name", __import__("families").FAMILIES)
+def test_hostemu_select_mode_matrix_families(hostemu, name):
+    """The coefficient-space back-application on graded, glued, clustered, badly scaled ... inputs (accurate rule):
+    residuals, norms and mutual orthogonality of the selected vectors at working precision."""
+    import families
+    D, E = families.family(name, 200)
+    n = len(D)
+    nT = np.abs(D).max() + 2 * np.abs(E).max()
+    sel = list(range(0, n, 7)) + [n - 1]
+    out = se.cuppens(D, E, ref_leaves=1, lib=hostemu, select=sel)
+    from scipy.linalg import eigh_tridiagonal
+    assert np.abs(out["lam"] - eigh_tridiagonal(D, E, eigvals_only=True)).max() <= 5e-14 * nT
+    V = out["V"]
+    assert out["resid"].max() <= 5e-14 * nT
+    assert np.abs(V.T @ V - np.eye(len(sel))).max() <= 5e-13
