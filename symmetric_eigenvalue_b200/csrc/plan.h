@@ -78,19 +78,10 @@ inline int set_heights(Plan& p, int id) {
 }
 }  // namespace detail
 
-// Returns 0, or 4 when n < P ("Leaf Size is too small", src/main.c:324-327).
-inline int build_plan(Plan& p, int n, const double* D, const double* E, int P, int leaf_max) {
-    p = Plan();
-    p.n = n; p.P = P; p.leaf_max = leaf_max;
-    if (P < 1 || n < 1 || n / P == 0) return 4;
-    std::vector<int> loff(P), lsz(P);
-    int leafSize = n / P, rem = n % P, off = 0;                 // backtransformation.c:85-96
-    for (int i = 0; i < P; ++i) { lsz[i] = leafSize + (i < rem ? 1 : 0); loff[i] = off; off += lsz[i]; }
-    int span = 1;
-    while (span < P) span *= 2;                                 // main.c:274-281
-    p.root = detail::build_reference(p, loff, lsz, 0, P, span, 0);
-    detail::set_heights(p, p.root);
-    // divide phase, top-down on the already modified diagonal (main.c:339-421)
+// The divide phase on an existing tree: top-down on the already modified diagonal (main.c:339-421).  The tree
+// shape depends on (n, P, leaf_max) only, so a new matrix on the same handle needs nothing but this pass.
+inline void plan_divide(Plan& p, const double* D, const double* E) {
+    const int n = p.n;
     p.D.assign(D, D + n);
     std::vector<int> order;
     order.push_back(p.root);
@@ -122,6 +113,21 @@ inline int build_plan(Plan& p, int n, const double* D, const double* E, int P, i
         order.push_back(nd.left);
         order.push_back(nd.right);
     }
+}
+
+// Returns 0, or 4 when n < P ("Leaf Size is too small", src/main.c:324-327).
+inline int build_plan(Plan& p, int n, const double* D, const double* E, int P, int leaf_max) {
+    p = Plan();
+    p.n = n; p.P = P; p.leaf_max = leaf_max;
+    if (P < 1 || n < 1 || n / P == 0) return 4;
+    std::vector<int> loff(P), lsz(P);
+    int leafSize = n / P, rem = n % P, off = 0;                 // backtransformation.c:85-96
+    for (int i = 0; i < P; ++i) { lsz[i] = leafSize + (i < rem ? 1 : 0); loff[i] = off; off += lsz[i]; }
+    int span = 1;
+    while (span < P) span *= 2;                                 // main.c:274-281
+    p.root = detail::build_reference(p, loff, lsz, 0, P, span, 0);
+    detail::set_heights(p, p.root);
+    plan_divide(p, D, E);
     return 0;
 }
 

@@ -142,6 +142,21 @@ struct Solver {
     std::vector<cuppen_merge_stat> stats;
     PhaseTimers pt;
     cuppen_timers timers;
+    // graph replays: the ~60 per-phase event pairs are only read when somebody asks for the timers
+    bool phase_timers_pending = false;
+    double bt_wall_extra = 0;
+    void fill_phase_timers() {
+        timers.root_finding_s = pt.acc[T_ROOT];
+        timers.ev_extract_s = pt.acc[T_EVX] + pt.acc[T_UGEN];
+        timers.backtransform_s = pt.acc[T_PACK] + pt.acc[T_GEMM] + pt.acc[T_UGEN] + bt_wall_extra;
+        timers.backtransform_ev_s = pt.acc[T_UGEN];
+        timers.gemm_s = pt.acc[T_GEMM];
+        timers.leaf_s = pt.acc[T_LEAF];
+        timers.deflation_s = pt.acc[T_DEFL];
+        timers.pack_s = pt.acc[T_PACK];
+        timers.residual_s = pt.acc[T_RESID];
+        if (select_mode && !h_sel.empty()) timers.backtransform_s = timers.apply_s;
+    }
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
     int resid_variant = 0;        // residual_kernel variant (0: default); env CUPPEN_RESID
     int gemm_variant = 1;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA kernel (gemm_tma.h); env CUPPEN_GEMM
@@ -311,10 +326,10 @@ void Solver::drop_graph() {
 void Solver::set_matrix(const double* D, const double* E) {
     hD.assign(D, D + n);
     hE.assign(E, E + std::max(0, n - 1));
-    Plan fresh;
-    int rc = build_plan(fresh, n, hD.data(), hE.data(), P, leaf_max);
-    if (rc != 0) CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
-    plan = fresh;
+    // the tree was built in cuppen_create (its shape depends on (n, P, leaf size) only): a new matrix needs the
+    // divide pass alone
+    if (plan.n != n || plan.P != P || plan.nodes.empty()) CUPPEN_THROW(CUPPEN_ERR_STATE, "handle without a divide tree");
+    plan_divide(plan, hD.data(), hE.data());
     // only the reference-rule splits need beta != 0 (assert at src/main.c:196-200, src/eigenvalues.c:68)
     for (const PlanNode& nd : plan.nodes)
         if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.rho == 0.0)
@@ -946,7 +961,8 @@ void Solver::solve() {
     enqueue_apply();
     const double t1 = wall_now();
     dev_sync(stream);
-    pt.collect();
+    if (pt.keep) phase_timers_pending = true;          // events of an instantiated graph: read on demand (cuppen_get_timers)
+    else { pt.collect(); phase_timers_pending = false; }
     const double t2 = wall_now();
     if (select_mode && !h_sel.empty()) {
         h_res_sel.resize(h_sel.size());
@@ -982,15 +998,7 @@ void Solver::solve() {
             acc_ugen_bytes += 8.0 * D.k * ((double)D.ktop + D.kbot);
         }
     timers.total_s = t1 - t0;
-    timers.root_finding_s = pt.acc[T_ROOT];
-    timers.ev_extract_s = pt.acc[T_EVX] + pt.acc[T_UGEN];
-    timers.backtransform_s = pt.acc[T_PACK] + pt.acc[T_GEMM] + pt.acc[T_UGEN] + (t2 - t1);
-    timers.backtransform_ev_s = pt.acc[T_UGEN];
-    timers.gemm_s = pt.acc[T_GEMM];
-    timers.leaf_s = pt.acc[T_LEAF];
-    timers.deflation_s = pt.acc[T_DEFL];
-    timers.pack_s = pt.acc[T_PACK];
-    timers.residual_s = pt.acc[T_RESID];
+    bt_wall_extra = t2 - t1;
     timers.kernel_launches = g_launches.launches - l0;
     timers.pack_bytes = acc_pack_bytes;
     timers.ugen_bytes = acc_ugen_bytes;
@@ -1001,12 +1009,12 @@ void Solver::solve() {
         float ms = 0; cudaEventElapsedTime(&ms, ev_ap0, ev_ap1);
         timers.apply_s = ms * 1e-3;
         timers.device_s += timers.apply_s;
-        timers.backtransform_s = timers.apply_s;
     }
 #else
-    if (select_mode && !h_sel.empty()) { timers.apply_s = t2 - t_ap; timers.backtransform_s = timers.apply_s; }
+    if (select_mode && !h_sel.empty()) timers.apply_s = t2 - t_ap;
     timers.device_s = t2 - t0;
 #endif
+    fill_phase_timers();                               // (zeros for now when the phase events are still pending)
 #if CUPPEN_CUDA
     if (want_vectors && gemm_variant == 1) tma_check_abort();
 #endif
@@ -1199,6 +1207,16 @@ int cuppen_get_merge_stats(cuppen_handle h, cuppen_merge_stat* out, int capacity
 int cuppen_get_timers(cuppen_handle h, cuppen_timers* out) {
     CUPPEN_API_BEGIN
     if (!h || !out) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    Solver& s = h->s;
+    if (s.phase_timers_pending) {
+#if CUPPEN_CUDA
+        CUDA_CHECK(cudaSetDevice(s.device));
+#endif
+        s.pt.reset();
+        s.pt.collect();
+        s.fill_phase_timers();
+        s.phase_timers_pending = false;
+    }
     *out = h->s.timers;
     CUPPEN_API_END
 }

@@ -312,3 +312,21 @@ def test_hostemu_select_mode_matrix_families(hostemu, name):
     V = out["V"]
     assert out["resid"].max() <= 5e-14 * nT
     assert np.abs(V.T @ V - np.eye(len(sel))).max() <= 5e-13
+
+
+def test_hostemu_handle_reuse_with_new_matrices(hostemu, oracle):
+    """A handle keeps its divide tree (the shape depends on (n, P) only); every cuppen_set_tridiagonal re-runs only the
+    divide pass (theta rule, rho, modified diagonal).  Results must equal those of a fresh handle, in any order."""
+    n, P = 300, 4
+    mats = [oracle.goe(n), oracle.scheme(1, n), oracle.rand_u(n), oracle.goe(n, seed=3)]
+    fresh = [se.cuppens(D, E, ref_leaves=P, lib=hostemu) for D, E in mats]
+    s = se.CuppenSolver(n, ref_leaves=P, lib=hostemu)
+    for k in (0, 1, 2, 3, 1, 0):
+        s.set_tridiagonal(*mats[k])
+        s.solve()
+        assert np.array_equal(s.eigenvalues(), fresh[k]["lam"])
+        assert np.array_equal(s.residuals(), fresh[k]["resid"])
+        assert s.merge_stats() == fresh[k]["stats"]
+        t = s.timers()
+        assert t["kernel_launches"] > 0 and t["total_s"] > 0
+    s.close()
