@@ -7,13 +7,14 @@ CC       ?= gcc
 CSRC     := symmetric_eigenvalue_b200/csrc
 LIBDIR   := symmetric_eigenvalue_b200/lib
 LIB      := $(LIBDIR)/libcuppen_b200.so
+SELFTEST := $(LIBDIR)/libcuppen_selftest.so
 OBJ_NAME := cuppens
 NVFLAGS  := --extended-lambda -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC \
             -Xcompiler -Wall -Xcompiler -Wno-unused-function --expt-relaxed-constexpr
 HDRS     := $(wildcard $(CSRC)/*.h) include/cuppen_b200.h
 
 all: cuppen
-lib: $(LIB)
+lib: $(LIB) $(SELFTEST)
 
 $(LIBDIR)/hostio.o: $(CSRC)/hostio.c include/cuppen_b200.h
 	@mkdir -p $(LIBDIR)
@@ -25,6 +26,11 @@ $(LIBDIR)/solver.o: $(CSRC)/solver.cu $(HDRS)
 
 $(LIB): $(LIBDIR)/solver.o $(LIBDIR)/hostio.o
 	$(NVCC) -shared -Xlinker -Bsymbolic -o $@ $^ -lcudart -ldl
+
+# test / bench only: kernel self-tests and FP64 yardsticks (not part of the product ABI)
+$(SELFTEST): $(CSRC)/selftest.cu $(HDRS)
+	@mkdir -p $(LIBDIR)
+	$(NVCC) $(NVFLAGS) -shared -o $@ $< -lcudart
 
 cuppen: $(LIB) $(CSRC)/cuppens_main.c
 	$(CC) -O2 -Wall -Iinclude -o $(OBJ_NAME) $(CSRC)/cuppens_main.c -L$(LIBDIR) -lcuppen_b200 \

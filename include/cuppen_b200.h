@@ -126,12 +126,11 @@ int cuppen_create_callbacks(cuppen_handle* h, int n, int ref_leaves, int flags, 
 int cuppen_destroy(cuppen_handle h);
 
 /* ---- the path ------------------------------------------------------------------------------ */
-/* D[n], E[n-1]: host pointers, copied. */
+/* D[n], E[n-1]: host pointers, copied.  Non-finite entries are rejected (CUPPEN_ERR_ARG). */
 int cuppen_set_tridiagonal(cuppen_handle h, const double* D, const double* E);
+/* May be called repeatedly: the matrix stays resident on the device, a second cuppen_solve re-runs the whole
+ * decomposition without any host<->device traffic of the inputs (one-GPU handles replay a CUDA graph). */
 int cuppen_solve(cuppen_handle h);
-/* Device-resident variant used by bench.py: inputs were uploaded by cuppen_set_tridiagonal;
- * re-runs the whole decomposition without any host<->device traffic of the inputs. */
-int cuppen_resolve(cuppen_handle h);
 
 /* ---- results (host pointers) ---------------------------------------------------------------- */
 int cuppen_get_eigenvalues(cuppen_handle h, double* lambda_ascending /* n */);
@@ -161,24 +160,6 @@ int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds);
  * double V[ncols][n].  All n vectors (CUPPEN_FLAG_VECTORS, ascending lambda) or the selected ones (CUPPEN_FLAG_SELECT). */
 int cuppen_write_eigenvectors(cuppen_handle h, const char* filename);
 const char* cuppen_last_error(void);
-
-/* FP64 yardsticks measured on the device: register-resident DMMA.8x8x4 issue loop and DFMA loop,
- * TFLOP/s with all SMs busy for ~`ms` milliseconds each (the FP64 peak is not in MEASURED_PEAKS.json). */
-int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* dfma_tflops);
-
-/* DMMA and DFMA issue loops sharing every SM (4 warps each per block): TFLOP/s of each kind alone and over the common
- * window when both run together -- do the two instruction kinds share the FP64 units? */
-int cuppen_measure_fp64_mix(int device, double* dmma_alone, double* dfma_alone, double* dmma_mixed, double* dfma_mixed);
-
-/* GEMM self-test / micro-benchmark of the back-transformation kernels on random data:
- * variant 0 = cp.async DMMA kernel 128x128, 1 = TMA DMMA kernel 128x128, 2 = cp.async 64x64.
- * max_abs_err: against an fp64 FMA dot product on 8192 sampled entries; tflops: best of `reps`. */
-int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps, double* max_abs_err, double* tflops);
-
-/* Residual-kernel self-test / micro-benchmark on random data (n columns): one slice of rows [g0, g0+cnt) of an n-row
- * problem stored at local rows [l0, l0+cnt) with halo rows (the multi-GPU slice layout), against a plain per-column
- * loop.  variant: 0 = the default, else 10*columns-per-block + min-blocks-per-SM.  seconds (may be NULL): best of 3. */
-int cuppen_selftest_residual(int device, int n, int variant, int g0, int l0, int cnt, double* max_rel_err, double* seconds);
 
 /* ---- host-side helpers of the CLI (no GPU involved) ------------------------------------------- */
 int cuppen_scheme(int scheme, int n, double* D, double* E);

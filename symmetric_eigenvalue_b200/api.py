@@ -68,7 +68,6 @@ def _declare(lib):
         "cuppen_destroy": [H],
         "cuppen_set_tridiagonal": [H, dp, dp],
         "cuppen_solve": [H],
-        "cuppen_resolve": [H],
         "cuppen_get_eigenvalues": [H, dp],
         "cuppen_get_residuals": [H, ip, ctypes.c_int, dp],
         "cuppen_get_merge_stats": [H, ctypes.POINTER(_MergeStat), ctypes.c_int, ip],
@@ -80,10 +79,6 @@ def _declare(lib):
         "cuppen_copy_selected_eigenvectors": [H, dp, ctypes.c_long],
         "cuppen_orthogonality": [H, dp, dp],
         "cuppen_write_eigenvectors": [H, ctypes.c_char_p],
-        "cuppen_measure_fp64_peak": [ctypes.c_int, ctypes.c_int, dp, dp],
-        "cuppen_measure_fp64_mix": [ctypes.c_int, dp, dp, dp, dp],
-        "cuppen_selftest_gemm": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
-        "cuppen_selftest_residual": [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_read_mtx": [ctypes.c_char_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ip],
         "cuppen_read_ev_file": [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ip), ip],
@@ -100,10 +95,10 @@ def _declare(lib):
 
 EXPORTED_SYMBOLS = (
     "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
-    "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_resolve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
+    "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors",
     "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors", "cuppen_orthogonality", "cuppen_write_eigenvectors",
-    "cuppen_last_error", "cuppen_measure_fp64_peak", "cuppen_measure_fp64_mix", "cuppen_selftest_gemm", "cuppen_selftest_residual", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
+    "cuppen_last_error", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
 
@@ -137,35 +132,72 @@ def nccl_unique_id(lib=None):
     return buf.raw
 
 
-def measure_fp64_peak(device=0, ms=200, lib=None):
+# ---- test / bench only: lib/libcuppen_selftest.so (csrc/selftest.cu, csrc/cuppen_selftest.h) --------------------
+_SELFTEST = None
+SELFTEST_SYMBOLS = ("cuppen_measure_fp64_peak", "cuppen_measure_fp64_mix", "cuppen_selftest_gemm", "cuppen_selftest_residual",
+                    "cuppen_selftest_last_error")
+
+
+def selftest_library_path():
+    return os.path.join(_HERE, "lib", "libcuppen_selftest.so")
+
+
+def load_selftest_library():
+    """Kernel self-tests and FP64 yardsticks; not part of the product ABI."""
+    global _SELFTEST
+    if _SELFTEST is None:
+        p = selftest_library_path()
+        if not os.path.exists(p):
+            raise CuppenError(-10, "%s is missing: run `make lib`" % p)
+        lib = ctypes.CDLL(p)
+        dp = ctypes.POINTER(ctypes.c_double)
+        i = ctypes.c_int
+        for name, args in {"cuppen_measure_fp64_peak": [i, i, dp, dp], "cuppen_measure_fp64_mix": [i, dp, dp, dp, dp],
+                           "cuppen_selftest_gemm": [i, i, i, i, i, i, dp, dp],
+                           "cuppen_selftest_residual": [i, i, i, i, i, i, dp, dp]}.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        lib.cuppen_selftest_last_error.argtypes = []
+        lib.cuppen_selftest_last_error.restype = ctypes.c_char_p
+        _SELFTEST = lib
+    return _SELFTEST
+
+
+def _chk_st(lib, rc):
+    if rc != 0:
+        raise CuppenError(rc, lib.cuppen_selftest_last_error().decode("utf-8", "replace"))
+
+
+def measure_fp64_peak(device=0, ms=200):
     """(DMMA TFLOP/s, DFMA TFLOP/s) of register-resident issue loops on `device`."""
-    lib = lib or load_library()
+    lib = load_selftest_library()
     a, b = ctypes.c_double(0), ctypes.c_double(0)
-    _chk(lib, lib.cuppen_measure_fp64_peak(device, ms, ctypes.byref(a), ctypes.byref(b)))
+    _chk_st(lib, lib.cuppen_measure_fp64_peak(device, ms, ctypes.byref(a), ctypes.byref(b)))
     return a.value, b.value
 
 
-def measure_fp64_mix(device=0, lib=None):
+def measure_fp64_mix(device=0):
     """dict of TFLOP/s: DMMA / DFMA issue loops alone and sharing the SMs (do they share the FP64 units?)."""
-    lib = lib or load_library()
+    lib = load_selftest_library()
     v = [ctypes.c_double(0) for _ in range(4)]
-    _chk(lib, lib.cuppen_measure_fp64_mix(device, *[ctypes.byref(x) for x in v]))
+    _chk_st(lib, lib.cuppen_measure_fp64_mix(device, *[ctypes.byref(x) for x in v]))
     return dict(zip(("dmma_alone", "dfma_alone", "dmma_mixed", "dfma_mixed"), (x.value for x in v)))
 
 
-def selftest_gemm(variant, M, N, K, reps=3, device=0, lib=None):
+def selftest_gemm(variant, M, N, K, reps=3, device=0):
     """(max abs error on sampled entries, TFLOP/s) of one back-transformation GEMM kernel variant."""
-    lib = lib or load_library()
+    lib = load_selftest_library()
     e, t = ctypes.c_double(0), ctypes.c_double(0)
-    _chk(lib, lib.cuppen_selftest_gemm(device, variant, M, N, K, reps, ctypes.byref(e), ctypes.byref(t)))
+    _chk_st(lib, lib.cuppen_selftest_gemm(device, variant, M, N, K, reps, ctypes.byref(e), ctypes.byref(t)))
     return e.value, t.value
 
 
-def selftest_residual(n, g0, l0, cnt, variant=0, device=0, lib=None):
+def selftest_residual(n, g0, l0, cnt, variant=0, device=0):
     """(max relative error, seconds) of residual_kernel on one slice of rows (multi-GPU layout) of random data."""
-    lib = lib or load_library()
+    lib = load_selftest_library()
     e, t = ctypes.c_double(0), ctypes.c_double(0)
-    _chk(lib, lib.cuppen_selftest_residual(device, n, variant, g0, l0, cnt, ctypes.byref(e), ctypes.byref(t)))
+    _chk_st(lib, lib.cuppen_selftest_residual(device, n, variant, g0, l0, cnt, ctypes.byref(e), ctypes.byref(t)))
     return e.value, t.value
 
 

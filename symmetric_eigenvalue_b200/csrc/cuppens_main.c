@@ -19,6 +19,7 @@
 #define _GNU_SOURCE
 #include <ctype.h>
 #include <fcntl.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -148,6 +149,12 @@ int main(int argc, char** argv) {
     }
     printf("\n");
     printf("Number of MPI tasks is: %d\n", numtasks);
+    /* entries that are not finite (a literal nan / inf in the input file) cannot be decomposed */
+    for (i = 0; i < n; ++i)
+        if (!isfinite(D[i]) || (i < n - 1 && !isfinite(E[i]))) {
+            printf("Matrix contains an entry that is not finite\n");
+            return 2;
+        }
     /* the reference asserts on zero entries (main.c:196-200) */
     for (i = 0; i < n; ++i)
         if (D[i] == 0 || (i < n - 1 && E[i] == 0)) {

@@ -40,10 +40,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" :: "r"(smem_u32(bar)) : "memory");
 }
-// Pipeline watchdog: a lost arrival must fail, not hang the GPU.  g_tma_abort[0] != 0 makes every
-// wait return at once; [1..6] record who gave up first (role, stage, parity, tile, k-tile, cta).
-__device__ int g_tma_abort[8];
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int role, int stage, int tile, int kt) {
+// Pipeline watchdog: a lost arrival must fail, not hang the GPU.  ab[0] != 0 makes every wait return at
+// once; [1..6] record who gave up first (role, stage, parity, tile, k-tile, cta).  `ab` is the caller's flag block
+// (8 ints of the solver's `fail` buffer, read back with the results of the solve).
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int role, int stage, int tile, int kt, int* ab) {
     unsigned done = 0;
     unsigned spins = 0;
     while (!done) {
@@ -53,11 +53,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, unsigned parity, int ro
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
         if (!done && (++spins & 0x3ff) == 0) {
-            if (*(volatile int*)&g_tma_abort[0]) return false;
+            if (*(volatile int*)&ab[0]) return false;
             if (spins > (1u << 22)) {
-                if (atomicCAS(&g_tma_abort[0], 0, 1) == 0) {
-                    g_tma_abort[1] = role; g_tma_abort[2] = stage; g_tma_abort[3] = (int)parity;
-                    g_tma_abort[4] = tile; g_tma_abort[5] = kt; g_tma_abort[6] = blockIdx.x;
+                if (atomicCAS(&ab[0], 0, 1) == 0) {
+                    ab[1] = role; ab[2] = stage; ab[3] = (int)parity;
+                    ab[4] = tile; ab[5] = kt; ab[6] = blockIdx.x;
                 }
                 return false;
             }
@@ -72,7 +72,7 @@ __device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, unsign
 }
 
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles, const int* __restrict__ ntiles_ptr) {
+dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles, const int* __restrict__ ntiles_ptr, int* abort_flags) {
     extern __shared__ __align__(128) double tma_smem[];
     uint64_t* full = (uint64_t*)(tma_smem + TMA_STAGES * TMA_STAGE_DOUBLES);
     uint64_t* empty = full + TMA_STAGES;
@@ -104,7 +104,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
             for (int kt = 0; kt < ktiles; ++kt) {
                 int ok = 1;
                 if (lane == 0) {
-                    ok = mbar_wait(&empty[stage], phase ^ 1, 0, stage, tile, kt) ? 1 : 0;
+                    ok = mbar_wait(&empty[stage], phase ^ 1, 0, stage, tile, kt, abort_flags) ? 1 : 0;
                     if (ok) mbar_expect_tx(&full[stage], TMA_STAGE_TX_BYTES);
                 }
                 ok = __shfl_sync(0xffffffffu, ok, 0);
@@ -137,7 +137,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
         for (int kt = 0; kt < ktiles; ++kt) {
-            if (!mbar_wait(&full[stage], phase, 1, stage, tile, kt)) return;
+            if (!mbar_wait(&full[stage], phase, 1, stage, tile, kt, abort_flags)) return;
             const double* sA = tma_smem + stage * TMA_STAGE_DOUBLES + aofs;
             const double* sB = tma_smem + stage * TMA_STAGE_DOUBLES + bofs;
 #pragma unroll
@@ -176,27 +176,18 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
 
 inline size_t tma_smem_bytes() { return (size_t)TMA_STAGES * TMA_STAGE_DOUBLES * sizeof(double) + 2 * TMA_STAGES * sizeof(uint64_t); }
 
-inline void launch_gemm_tma(Stream s, const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, int grid) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
-        attr_set = true;
-    }
+// (the >48 KB dynamic shared memory opt-in is a per-device attribute: set_kernel_attributes() in solver.cu)
+inline void launch_gemm_tma(Stream s, const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, int grid, int* abort_flags) {
     if (grid < 1) return;
-    dgemm_tma_kernel<<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr);
+    dgemm_tma_kernel<<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags);
     CUDA_CHECK(cudaGetLastError());
 }
 
-// call after a synchronisation point: throws if the pipeline watchdog fired
-inline void tma_check_abort() {
-    int h[8] = {0};
-    CUDA_CHECK(cudaMemcpyFromSymbol(h, g_tma_abort, sizeof h));
-    if (h[0]) {
-        int z[8] = {0};
-        cudaMemcpyToSymbol(g_tma_abort, z, sizeof z);
+// host copy of the 8 watchdog ints: throws if the pipeline watchdog fired
+inline void tma_check_abort(const int* h) {
+    if (h[0])
         CUPPEN_THROW(-10, "TMA GEMM pipeline timeout: role=%d (0 producer, 1 consumer) stage=%d parity=%d tile=%d ktile=%d cta=%d",
                      h[1], h[2], h[3], h[4], h[5], h[6]);
-    }
 }
 
 }  // namespace cuppen

@@ -171,6 +171,7 @@ inline void build_gemm_work_host(WorkCtx w) {
     }
     w.ntiles[0] = run < w.tile_cap ? run : w.tile_cap;
     w.ntiles[1] = mis;
+    if (run > w.tile_cap) *w.fail = 1;
 }
 
 // consumes the same (problem, tile) list as the device kernels

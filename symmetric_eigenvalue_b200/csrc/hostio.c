@@ -111,6 +111,11 @@ int cuppen_read_mtx(const char* filename, double** D, double** E, int* n) {
             }
         } else (*E)[c - 1] = v;
     }
+    /* a sub-diagonal entry that the file never listed is a zero of the matrix (the reference would read
+     * uninitialised memory here): report it as the zero it is, so that the caller's `E[i] != 0` check
+     * (src/main.c:196-200) fires instead of a NaN reaching the solver */
+    for (i = 0; i < R - 1; ++i)
+        if ((*E)[i] != (*E)[i]) (*E)[i] = 0.0;
     fclose(f);
     return CUPPEN_OK;
 fail:

@@ -53,6 +53,7 @@ struct WorkCtx {
     GemmTile* tiles;
     int* ntiles;            // [0] tile count, [1] number of problems whose lines are not 16-byte aligned
     int tile_cap;
+    int* fail;              // set to 1 when the level needs more than tile_cap tiles (the solve then reports an error)
 };
 
 // Tile order of one problem: super-columns of `nsw` n-tiles whose B panel (K x nsw*BN doubles) fits
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) build_gemm_work_kernel(WorkCtx w) {
         for (int p = 0; p < np; ++p) { int c = work_off[p]; work_off[p] = run; run += c; }
         w.ntiles[0] = run < w.tile_cap ? run : w.tile_cap;
         w.ntiles[1] = misaligned;
+        if (run > w.tile_cap) *w.fail = 1;
     }
     __syncthreads();
     for (int p = threadIdx.x; p < np; p += blockDim.x) {

@@ -36,6 +36,8 @@ struct MergeDesc {
     int own_first, own_last;   // this rank holds the node's first / last global row
     double sigma;              // max |entry| of T: LAPACK's dstedc scales T to unit norm before its
                                // tolerances apply; we keep T unscaled and scale the tolerance instead
+    double dthr;               // reference rule: the absolute pole-gap threshold 1e-5 (src/eigenvalues.c:109) in the
+                               // units of the uploaded matrix (1e-5 * s when T was scaled by the power of two s)
     // ---- written by the device ----
     int nlive1;      // entries that survive z-deflation
     int k;           // live entries after the Givens sweep = number of secular roots
@@ -190,7 +192,7 @@ struct RankLive {
 
 // can the rotation step (p-1 -> p) fire, whatever chain state p-1 is in?  false = certified no.
 CUPPEN_HD bool step_may_fire(const MergeDesc& D, double dprev, double zprev, double dq, double zq) {
-    if (D.mode == MODE_REFERENCE) return fabs(dq - dprev) < 1e-5;     // src/eigenvalues.c:109
+    if (D.mode == MODE_REFERENCE) return fabs(dq - dprev) < D.dthr;    // src/eigenvalues.c:109
     double t = dq - dprev;
     double y = fabs(zq), x1 = fabs(zprev), x2 = 1.0 + 1e-9;
     double g1 = x1 * y / (x1 * x1 + y * y), g2 = x2 * y / (x2 * x2 + y * y);
@@ -230,7 +232,7 @@ struct GivensSweep {
             bool fire;
             double r = sqrt(zc * zc + zq * zq);                             // src/eigenvalues.c:113
             double cs = zq / r, sn = zc / r;
-            if (D.mode == MODE_REFERENCE) fire = fabs(dq - dc) < 1e-5;
+            if (D.mode == MODE_REFERENCE) fire = fabs(dq - dc) < D.dthr;
             else fire = fabs((dq - dc) * cs * sn) <= D.tol;
             if (fire) {
                 c.G[off + e] = eq;

@@ -80,7 +80,10 @@ inline int set_heights(Plan& p, int id) {
 
 // The divide phase on an existing tree: top-down on the already modified diagonal (main.c:339-421).  The tree
 // shape depends on (n, P, leaf_max) only, so a new matrix on the same handle needs nothing but this pass.
-inline void plan_divide(Plan& p, const double* D, const double* E) {
+// D, E may have been scaled by a power of two s (matrices of extreme norm); inv_scale = 1/s then restores the
+// reference's theta magnitudes 1000*beta / beta/1000, which are not scale equivariant (theta is dimensionless
+// everywhere else).
+inline void plan_divide(Plan& p, const double* D, const double* E, double inv_scale = 1.0) {
     const int n = p.n;
     p.D.assign(D, D + n);
     std::vector<int> order;
@@ -95,8 +98,9 @@ inline void plan_divide(Plan& p, const double* D, const double* E) {
             if ((dl > 0 && df > 0) || (dl < 0 && df < 0)) {     // main.c:370-375
                 nd.theta = ((dl * (-nd.beta)) < 0) ? -1 : 1;
             } else {                                            // main.c:376-389
-                if (fabs(nd.beta) < fabs(df)) nd.theta = 1000 * nd.beta;
-                else nd.theta = nd.beta / 1000;
+                const double borig = nd.beta * inv_scale;
+                if (fabs(nd.beta) < fabs(df)) nd.theta = 1000 * borig;
+                else nd.theta = borig / 1000;
             }
             p.D[g - 1] -= nd.theta * nd.beta;                   // main.c:392-394
             p.D[g] -= 1.0 / nd.theta * nd.beta;

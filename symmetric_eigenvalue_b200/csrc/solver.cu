@@ -30,6 +30,9 @@ static double wall_now() {
 }
 
 // ---- per-category device timers (CUDA events on the solver's stream) ---------------------------
+// fail buffer of a solve (device, read back with the results): [0] leaf QL did not converge (1 + row),
+// [1] GEMM tile list overflow, [4..11] watchdog record of the TMA GEMM pipeline
+enum { FAIL_LEAF = 0, FAIL_TILES = 1, FAIL_TMA = 4, FAIL_INTS = 16 };
 enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_APPLY, T_NCAT };
 struct PhaseTimers {
     double acc[T_NCAT] = {0};
@@ -95,7 +98,12 @@ struct Solver {
     int nloc_final = 0;           // local rows of the final V
     int slice_lo(int s, int j) const { return j >= G ? sub_n[s] : (int)(((long)j * sub_n[s] / G) & ~1L); }
 
-    std::vector<double> hD, hE;   // original matrix (host)
+    std::vector<double> hD, hE;   // matrix as uploaded (host): the caller's T times `scale`
+    // Matrices of extreme norm (max|T_ij| outside [1e-100, 1e100]) are scaled by a power of two before the divide
+    // pass, as dstedc does with dlascl (products of z^2, rho and pole gaps would leave the fp64 range otherwise);
+    // eigenvalues and residuals are scaled back on the way out.  Everything in between is exact under a power-of-
+    // two scaling, the reference rule's absolute 1e-5 gap threshold follows the scaling (MergeDesc::dthr).
+    double scale = 1.0;
     DevBuf<double> dDm, dE, dOD, dOE;
     DevBuf<double> lam, lam_sorted, frow, lrow, frow2, lrow2, fpack, lpack;
     DevBuf<double> d, z, dn, zn, gc, gs, dl, wl, zl, tau, zhat, nrm, res2, halo, halo_all;
@@ -236,8 +244,23 @@ void Solver::init_layout() {
     ldq = round_up(std::max(nlocL, nlocC), 16);
 }
 
+// Function attributes are per device: every handle opts its device in to the >48 KB dynamic shared memory of the
+// GEMM, secular and Gram kernels (a process-wide "done" flag would leave a second device without it).
+static void set_kernel_attributes() {
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<64, 64, 16, 2, 2, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DmmaCfg<64, 64, 16, 2, 2, 3>::SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<128, 128, 16, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)DmmaCfg<128, 128, 16, 2, 4, 3>::SMEM_BYTES));
+    CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
+    CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SEC_SMEM_K * sizeof(double))));
+    CUDA_CHECK(cudaFuncSetAttribute(gram_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes()));
+#endif
+}
+
 void Solver::allocate() {
     const size_t N = (size_t)n;
+    set_kernel_attributes();
     for (DevBuf<double>* b : {&dDm, &dE, &dOD, &dOE, &lam, &lam_sorted, &frow, &lrow, &frow2, &lrow2, &fpack, &lpack, &res2})
         b->alloc(N + 64);
     perm.alloc(N + 64);
@@ -255,7 +278,7 @@ void Solver::allocate() {
         for (DevBuf<double>* b : {&selX, &selY, &selXS, &selGam}) b->alloc(N * SEL_NV + 64);
         sel_dorg.alloc(N + 64);
     }
-    fail.alloc(4);
+    fail.alloc(FAIL_INTS);
     halo.alloc(2 * N * (size_t)std::max(1, G) + 64);
     halo_all.alloc(2 * N * (size_t)G * (size_t)G + 64);
     leaves.alloc(std::max<size_t>(1, plan.leaves.size()));
@@ -285,13 +308,13 @@ void Solver::allocate() {
 #if CUPPEN_CUDA
     CUDA_CHECK(cudaMallocHost((void**)&pin_lam, sizeof(double) * N));
     CUDA_CHECK(cudaMallocHost((void**)&pin_res, sizeof(double) * N));
-    CUDA_CHECK(cudaMallocHost((void**)&pin_fail, sizeof(int) * 4));
+    CUDA_CHECK(cudaMallocHost((void**)&pin_fail, sizeof(int) * FAIL_INTS));
     const char* ge = getenv("CUPPEN_GRAPH");
     if (ge && !strcmp(ge, "0")) use_graph = false;
 #else
     pin_lam = (double*)malloc(sizeof(double) * N);
     pin_res = (double*)malloc(sizeof(double) * N);
-    pin_fail = (int*)malloc(sizeof(int) * 4);
+    pin_fail = (int*)malloc(sizeof(int) * FAIL_INTS);
     use_graph = false;
 #endif
     if (G > 1) use_graph = false;
@@ -324,12 +347,30 @@ void Solver::drop_graph() {
 }
 
 void Solver::set_matrix(const double* D, const double* E) {
+    // a failed call must not leave the previous matrix's decomposition looking valid
+    have_matrix = false;
+    solved = false;
+    double amax = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!std::isfinite(D[i])) CUPPEN_THROW(CUPPEN_ERR_ARG, "D[%d] is not finite", i);
+        amax = std::max(amax, fabs(D[i]));
+    }
+    for (int i = 0; i + 1 < n; ++i) {
+        if (!std::isfinite(E[i])) CUPPEN_THROW(CUPPEN_ERR_ARG, "E[%d] is not finite", i);
+        amax = std::max(amax, fabs(E[i]));
+    }
+    scale = 1.0;
+    if (amax > 0 && (amax < 1e-100 || amax > 1e100)) scale = ldexp(1.0, -ilogb(amax));
     hD.assign(D, D + n);
     hE.assign(E, E + std::max(0, n - 1));
+    if (scale != 1.0) {
+        for (double& v : hD) v *= scale;
+        for (double& v : hE) v *= scale;
+    }
     // the tree was built in cuppen_create (its shape depends on (n, P, leaf size) only): a new matrix needs the
     // divide pass alone
     if (plan.n != n || plan.P != P || plan.nodes.empty()) CUPPEN_THROW(CUPPEN_ERR_STATE, "handle without a divide tree");
-    plan_divide(plan, hD.data(), hE.data());
+    plan_divide(plan, hD.data(), hE.data(), 1.0 / scale);
     // only the reference-rule splits need beta != 0 (assert at src/main.c:196-200, src/eigenvalues.c:68)
     for (const PlanNode& nd : plan.nodes)
         if (nd.left >= 0 && nd.mode == MODE_REFERENCE && nd.rho == 0.0)
@@ -343,7 +384,6 @@ void Solver::set_matrix(const double* D, const double* E) {
     }
     dev_sync(stream);
     have_matrix = true;
-    solved = false;
 }
 
 LevelCtx Solver::level_ctx(int li) {
@@ -370,7 +410,7 @@ MatCtx Solver::mat_ctx() {
 // ---- leaves ---------------------------------------------------------------------------------------
 void Solver::run_leaves() {
     const std::vector<LeafDesc>& hl = h_leaves;
-    dev_zero(fail.p, sizeof(int) * 4, stream);
+    dev_zero(fail.p, sizeof(int) * FAIL_INTS, stream);
     if (hl.empty()) return;
     pt.begin(T_LEAF, stream);
     // selected-eigenvector mode keeps the leaf eigenvectors compactly: (row, column c of its leaf) at row + c*n
@@ -394,11 +434,6 @@ static void launch_gemm(Stream s, const GemmProblem* probs, const GemmTile* tile
 #if CUPPEN_CUDA
     using Cfg = DmmaCfg<BM, BN, BK, WMs, WNs, STAGES>;
     auto kern = dgemm_dmma_kernel<BM, BN, BK, WMs, WNs, STAGES>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES));
-        attr_set = true;
-    }
     int grid = (int)std::max<long>(1, grid_want);
     kern<<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, s>>>(probs, tiles, ntiles_ptr);
     CUDA_CHECK(cudaGetLastError());
@@ -417,7 +452,7 @@ void Solver::update_descriptors() {
             const PlanNode& nd = plan.nodes[L.ids[t]];
             MergeDesc& D = h_desc_all[L.desc_off + t];
             if (D.off != nd.off || D.m != nd.n || D.n1 != nd.n1) CUPPEN_THROW(CUPPEN_ERR_STATE, "divide tree changed shape");
-            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = sigma; D.mode = nd.mode;
+            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = sigma; D.mode = nd.mode; D.dthr = 1e-5 * scale;
         }
     if (!h_desc_all.empty()) dev_h2d(desc_all.p, h_desc_all.data(), sizeof(MergeDesc) * h_desc_all.size(), stream);
 }
@@ -479,7 +514,7 @@ void Solver::prepare_levels() {
             MergeDesc D;
             memset(&D, 0, sizeof D);
             D.off = nd.off; D.n1 = nd.n1; D.n2 = nd.n - nd.n1; D.m = nd.n; D.mode = nd.mode;
-            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = 1.0;
+            D.rho = nd.rho; D.theta = nd.theta; D.zscale = nd.zscale; D.sigma = 1.0; D.dthr = 1e-5;
             local_rows(nd, L.coop, D.lr0, D.lsplit, D.lr1);
             D.own_first = L.coop ? (comm.rank == 0) : 1;
             D.own_last = L.coop ? (comm.rank == G - 1) : 1;
@@ -659,12 +694,6 @@ void Solver::run_level(int li) {
         {
             int kcap = std::min((int)round_up(L.maxm, 32), (int)SEC_SMEM_K);
             size_t smem = (size_t)2 * kcap * sizeof(double);
-            static bool attr_set = false;
-            if (!attr_set) {
-                CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                (int)(2 * SEC_SMEM_K * sizeof(double))));
-                attr_set = true;
-            }
             dim3 grid((unsigned)((per + SEC_WARPS - 1) / SEC_WARPS), (unsigned)nd_cnt);
             secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, nparts);
             CUDA_CHECK(cudaGetLastError());
@@ -764,6 +793,7 @@ void Solver::run_level(int li) {
         w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN;
         w.ldq = ldq; w.ldb = ldb; w.Apack = Apack.p; w.B = B.p; w.Qnext = Qcur; w.lidx = lidx.p;
         w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
+        w.fail = fail.p + FAIL_TILES;
         const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
         pt.begin(T_GEMM, stream);
 #if CUPPEN_CUDA
@@ -771,7 +801,7 @@ void Solver::run_level(int li) {
         CUDA_CHECK(cudaGetLastError());
         const int grid = (int)std::min<long>(worst, small_tiles ? num_sms * 8L : (long)num_sms);
         if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, ntiles_dev.p, grid);
-        else if (gemm_variant == 1 && L.aligned) launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid);
+        else if (gemm_variant == 1 && L.aligned) launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA);
         else launch_gemm<128, 128, 16, 2, 4, 3>(stream, probs.p, tiles.p, ntiles_dev.p, std::min<long>(worst, num_sms * 2L));
 #else
         (void)worst;
@@ -907,7 +937,7 @@ void Solver::enqueue_solve() {
     for (int li = 0; li < (int)levels.size(); ++li) run_level(li);
     if (!h_desc_all.empty()) dev_d2h(pin_desc, desc_all.p, sizeof(MergeDesc) * h_desc_all.size(), stream);
     finish();
-    dev_d2h(pin_fail, fail.p, sizeof(int), stream);
+    dev_d2h(pin_fail, fail.p, sizeof(int) * FAIL_INTS, stream);
 #if CUPPEN_CUDA
     pt.record(ev_end, stream);
 #endif
@@ -968,17 +998,20 @@ void Solver::solve() {
         h_res_sel.resize(h_sel.size());
         dev_d2h(h_res_sel.data(), res_sel.p, sizeof(double) * h_sel.size(), stream);
         dev_sync(stream);
-        for (double& r : h_res_sel) r = sqrt(r);
+        for (double& r : h_res_sel) r = sqrt(r) / scale;
     }
     solves_done++;
+    const double unscale = 1.0 / scale;
     h_lam_sorted.assign(pin_lam, pin_lam + n);
+    if (scale != 1.0) for (double& v : h_lam_sorted) v *= unscale;
     h_resid.clear();
     if (want_vectors && !(flags & CUPPEN_FLAG_NO_RESIDUALS)) {
         h_resid.assign(pin_res, pin_res + n);
-        for (double& r : h_resid) r = sqrt(r);
+        for (double& r : h_resid) r = sqrt(r) * unscale;
     }
     if (!h_desc_all.empty()) memcpy(h_desc_all.data(), pin_desc, sizeof(MergeDesc) * h_desc_all.size());
-    int hfail[4] = {pin_fail[0], 0, 0, 0};
+    int hfail[FAIL_INTS];
+    memcpy(hfail, pin_fail, sizeof hfail);
     // per-merge records and executed work, from the descriptors the device filled in
     for (size_t li = 0; li < levels.size(); ++li)
         for (size_t t = 0; t < levels[li].ids.size(); ++t) {
@@ -986,7 +1019,7 @@ void Solver::solve() {
             const PlanNode& nd = plan.nodes[levels[li].ids[t]];
             cuppen_merge_stat st;
             st.offset = D.off; st.m = D.m; st.n1 = D.n1; st.mode = D.mode; st.zdefl = D.m - D.nlive1;
-            st.givens = D.nlive1 - D.k; st.k = D.k; st.height = nd.height; st.rho = nd.beta * nd.theta;
+            st.givens = D.nlive1 - D.k; st.k = D.k; st.height = nd.height; st.rho = nd.beta * nd.theta / scale;
             stats.push_back(st);
             if (!want_vectors) continue;
             const double rows = D.lr1 - D.lr0;
@@ -1016,8 +1049,10 @@ void Solver::solve() {
 #endif
     fill_phase_timers();                               // (zeros for now when the phase events are still pending)
 #if CUPPEN_CUDA
-    if (want_vectors && gemm_variant == 1) tma_check_abort();
+    tma_check_abort(hfail + FAIL_TMA);
 #endif
+    if (hfail[FAIL_TILES] != 0)
+        CUPPEN_THROW(CUPPEN_ERR_STATE, "GEMM tile list overflow (%zu tiles allocated): the eigenvectors of this solve are incomplete", tiles.n);
     if (hfail[0] != 0) CUPPEN_THROW(CUPPEN_ERR_CONVERGENCE, "leaf QL iteration did not converge (row %d)", hfail[0] - 1);
     solved = true;
 }
@@ -1069,7 +1104,7 @@ static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int
         // the tree shape depends only on (n, P): plan with a dummy matrix to size the buffers
         std::vector<double> D0(n, 1.0), E0(std::max(1, n - 1), 1.0);
         {
-            const char* le = getenv("CUPPEN_LEAF");     // leaf size of the accurate sub-tree (8..32), default 32
+            const char* le = getenv("CUPPEN_LEAF");     // leaf size of the accurate sub-tree (4..32), default 16
             if (le && atoi(le) >= 4 && atoi(le) <= LEAF_MAX) s.leaf_max = atoi(le);
         }
         if (build_plan(s.plan, n, D0.data(), E0.data(), ref_leaves, s.leaf_max) != 0)
@@ -1154,8 +1189,6 @@ int cuppen_solve(cuppen_handle h) {
     h->s.solve();
     CUPPEN_API_END
 }
-
-int cuppen_resolve(cuppen_handle h) { return cuppen_solve(h); }
 
 int cuppen_get_eigenvalues(cuppen_handle h, double* out) {
     CUPPEN_API_BEGIN
@@ -1310,11 +1343,6 @@ int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds) 
     if (s.G > 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "the orthogonality check runs on one GPU (rows of V are distributed over %d)", s.G);
 #if CUPPEN_CUDA
     CUDA_CHECK(cudaSetDevice(s.device));
-    static bool attr_set = false;
-    if (!attr_set) {
-        CUDA_CHECK(cudaFuncSetAttribute(gram_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes()));
-        attr_set = true;
-    }
     DevBuf<unsigned long long> res;
     res.alloc(1);
     dev_zero(res.p, sizeof(unsigned long long), s.stream);
@@ -1389,234 +1417,5 @@ int cuppen_write_eigenvectors(cuppen_handle h, const char* filename) {
 }
 
 const char* cuppen_last_error(void) { return g_last_error.c_str(); }
-
-#if CUPPEN_CUDA
-namespace cuppen {
-__global__ void fill_kernel(double* p, long count, unsigned seed) {
-    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= count) return;
-    unsigned long long x = (unsigned long long)i * 6364136223846793005ull + seed * 1442695040888963407ull + 1013904223ull;
-    x ^= x >> 29; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 32;
-    p[i] = (double)(x & 0xfffff) / 524288.0 - 1.0;
-}
-__global__ void sample_check_kernel(const GemmProblem P, int samples, double* err) {
-    int sidx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (sidx >= samples) return;
-    int m = (int)(((unsigned long long)sidx * 2654435761ull) % (unsigned)P.M);
-    int nn = (int)(((unsigned long long)sidx * 40503ull + 17) % (unsigned)P.N);
-    double s = 0;
-    for (int k = 0; k < P.K; ++k) s = fma(P.A[(long)k * P.lda + m], P.B[(long)k * P.ldb + nn], s);
-    double got = P.C[(long)P.colidx[nn] * P.ldc + m];
-    atomicMax((unsigned long long*)err, (unsigned long long)__double_as_longlong(fabs(got - s)));
-}
-__global__ void iota_rev_kernel(int* p, int n) { int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = n - 1 - i; }
-// plain one-thread-per-column restatement of the residual, for cuppen_selftest_residual
-__global__ void residual_check_kernel(const double* V, long ldq, int n, int ncols, int g0, int l0, int cnt, const double* OD, const double* OE,
-                                      const double* lam, const int* perm, const double* hlo, const double* hhi, const double* got, double* err) {
-    int col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= ncols) return;
-    const double* x = V + (long)perm[col] * ldq + l0 - g0;
-    double acc = 0;
-    for (int r = g0; r < g0 + cnt; ++r) {
-        double y = OD[r] * x[r] - lam[col] * x[r];
-        if (r > 0) y += OE[r - 1] * (r > g0 ? x[r - 1] : hlo[col]);
-        if (r < n - 1) y += OE[r] * (r + 1 < g0 + cnt ? x[r + 1] : hhi[col]);
-        acc += y * y;
-    }
-    double rel = fabs(got[col] - acc) / fmax(acc, 1e-300);
-    atomicMax((unsigned long long*)err, (unsigned long long)__double_as_longlong(rel));
-}
-}  // namespace cuppen
-#endif
-
-int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps, double* max_abs_err, double* tflops) {
-    CUPPEN_API_BEGIN
-#if CUPPEN_CUDA
-    if (M < 1 || N < 1 || K < 0 || !max_abs_err || !tflops) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
-    CUDA_CHECK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    const int row0 = (variant == 1) ? 2 : 3;                 // odd row offset (cp.async kernels), even for the 16-byte bulk-copy lines
-    const long lda = round_up(M + row0 + 128, 16), ldb = round_up(N, 16) + 16, ldc = lda;
-    const long Kp = round_up(K, K_PAD);
-    DevBuf<double> A, Bm, C, err;
-    DevBuf<int> colidx;
-    DevBuf<GemmProblem> dprob;
-    DevBuf<GemmTile> dtiles;
-    A.alloc((size_t)lda * (Kp + K_PAD + 1) + 4096); Bm.alloc((size_t)ldb * (Kp + 2 * K_PAD + 2) + 4096);
-    C.alloc((size_t)ldc * (N + 1) + 4096); err.alloc(1); colidx.alloc(N);
-    Stream s = 0;
-    fill_kernel<<<(unsigned)((A.n + 255) / 256), 256>>>(A.p, (long)A.n, 1u);
-    fill_kernel<<<(unsigned)((Bm.n + 255) / 256), 256>>>(Bm.p, (long)Bm.n, 2u);
-    // zero the K tail of A (columns K..Kp) as pack_kernel does
-    if (Kp > K) CUDA_CHECK(cudaMemset(A.p + (size_t)K * lda, 0, sizeof(double) * (size_t)(Kp - K) * lda));
-    CUDA_CHECK(cudaMemset(C.p, 0, C.bytes()));
-    CUDA_CHECK(cudaMemset(err.p, 0, sizeof(double)));
-    iota_rev_kernel<<<(N + 255) / 256, 256>>>(colidx.p, N);
-    GemmProblem P;
-    P.A = A.p + row0; P.B = Bm.p; P.C = C.p + row0; P.colidx = colidx.p; P.M = M; P.N = N; P.K = K;
-    P.lda = lda; P.ldb = ldb; P.ldc = ldc; P.a_row0 = row0; P.a_col0 = 0; P.b_row0 = 0; P.b_col0 = 0;
-    std::vector<GemmTile> ht;
-    const int BM = variant == 2 ? 64 : 128, BN = BM;
-    for (int m0 = 0; m0 < M; m0 += BM)
-        for (int n0 = 0; n0 < N; n0 += BN) ht.push_back(GemmTile{0, m0, n0});
-    dprob.alloc(1); dtiles.alloc(ht.size());
-    CUDA_CHECK(cudaMemcpy(dprob.p, &P, sizeof P, cudaMemcpyHostToDevice));
-    CUDA_CHECK(cudaMemcpy(dtiles.p, ht.data(), sizeof(GemmTile) * ht.size(), cudaMemcpyHostToDevice));
-    DevBuf<int> dnt;
-    dnt.alloc(4);
-    int hnt[4] = {(int)ht.size(), 0, 0, 0};
-    CUDA_CHECK(cudaMemcpy(dnt.p, hnt, sizeof hnt, cudaMemcpyHostToDevice));
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int r = 0; r < std::max(1, reps) + 1; ++r) {
-        CUDA_CHECK(cudaEventRecord(e0, s));
-        const long nt = (long)ht.size();
-        if (variant == 1) launch_gemm_tma(s, dprob.p, dtiles.p, dnt.p, (int)std::min<long>(nt, prop.multiProcessorCount));
-        else if (variant == 2) launch_gemm<64, 64, 16, 2, 2, 3>(s, dprob.p, dtiles.p, dnt.p, std::min<long>(nt, prop.multiProcessorCount * 8L));
-        else launch_gemm<128, 128, 16, 2, 4, 3>(s, dprob.p, dtiles.p, dnt.p, std::min<long>(nt, prop.multiProcessorCount * 2L));
-        CUDA_CHECK(cudaEventRecord(e1, s));
-        CUDA_CHECK(cudaEventSynchronize(e1));
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-        if (r > 0 || reps <= 0) best = std::min(best, ms);
-    }
-    tma_check_abort();
-    const int samples = 8192;
-    sample_check_kernel<<<(samples + 127) / 128, 128>>>(P, samples, err.p);
-    CUDA_CHECK(cudaDeviceSynchronize());
-    CUDA_CHECK(cudaMemcpy(max_abs_err, err.p, sizeof(double), cudaMemcpyDeviceToHost));
-    *tflops = 2.0 * M * (double)N * K / (best * 1e-3) * 1e-12;
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-#else
-    (void)device; (void)variant; (void)M; (void)N; (void)K; (void)reps; (void)max_abs_err; (void)tflops;
-    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
-#endif
-    CUPPEN_API_END
-}
-
-int cuppen_selftest_residual(int device, int n, int variant, int g0, int l0, int cnt, double* max_rel_err, double* seconds) {
-    CUPPEN_API_BEGIN
-#if CUPPEN_CUDA
-    if (n < 1 || g0 < 0 || l0 < 0 || cnt < 1 || g0 + cnt > n || !max_rel_err) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
-    const int ncols = n;
-    CUDA_CHECK(cudaSetDevice(device));
-    long ldq = round_up(l0 + cnt, 16);
-    if (getenv("CUPPEN_LDPAD")) ldq += atoi(getenv("CUPPEN_LDPAD"));      // experiment: column stride away from a power of two
-    DevBuf<double> V, OD, OE, lam, hlo, hhi, res, err;
-    DevBuf<int> perm;
-    V.alloc((size_t)ldq * ncols + 64); OD.alloc(n + 64); OE.alloc(n + 64); lam.alloc(ncols); hlo.alloc(ncols); hhi.alloc(ncols);
-    res.alloc(ncols); err.alloc(1); perm.alloc(ncols);
-    fill_kernel<<<(unsigned)((V.n + 255) / 256), 256>>>(V.p, (long)V.n, 11u);
-    fill_kernel<<<(unsigned)((OD.n + 255) / 256), 256>>>(OD.p, (long)OD.n, 12u);
-    fill_kernel<<<(unsigned)((OE.n + 255) / 256), 256>>>(OE.p, (long)OE.n, 13u);
-    fill_kernel<<<(unsigned)((ncols + 255) / 256), 256>>>(lam.p, ncols, 14u);
-    fill_kernel<<<(unsigned)((ncols + 255) / 256), 256>>>(hlo.p, ncols, 15u);
-    fill_kernel<<<(unsigned)((ncols + 255) / 256), 256>>>(hhi.p, ncols, 16u);
-    iota_rev_kernel<<<(ncols + 255) / 256, 256>>>(perm.p, ncols);
-    CUDA_CHECK(cudaMemset(err.p, 0, sizeof(double)));
-    cudaEvent_t e0, e1;
-    CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
-    float best = 1e30f;
-    for (int rep = 0; rep < 3; ++rep) {
-        CUDA_CHECK(cudaEventRecord(e0, 0));
-        launch_residual(0, variant, V.p, ldq, n, g0, l0, cnt, OD.p, OE.p, lam.p, perm.p, hlo.p, hhi.p, res.p, 0);
-        CUDA_CHECK(cudaEventRecord(e1, 0));
-        CUDA_CHECK(cudaEventSynchronize(e1));
-        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
-        best = std::min(best, ms);
-    }
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (seconds) *seconds = best * 1e-3;
-    residual_check_kernel<<<(ncols + 127) / 128, 128>>>(V.p, ldq, n, ncols, g0, l0, cnt, OD.p, OE.p, lam.p, perm.p, hlo.p, hhi.p, res.p, err.p);
-    CUDA_CHECK(cudaDeviceSynchronize());
-    CUDA_CHECK(cudaMemcpy(max_rel_err, err.p, sizeof(double), cudaMemcpyDeviceToHost));
-#else
-    (void)device; (void)n; (void)variant; (void)g0; (void)l0; (void)cnt; (void)max_rel_err; (void)seconds;
-    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
-#endif
-    CUPPEN_API_END
-}
-
-int cuppen_measure_fp64_peak(int device, int ms, double* dmma_tflops, double* dfma_tflops) {
-    CUPPEN_API_BEGIN
-#if CUPPEN_CUDA
-    if (!dmma_tflops || !dfma_tflops) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
-    CUDA_CHECK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    const int blocks = prop.multiProcessorCount * 2, threads = 256;
-    double* out = nullptr;
-    CUDA_CHECK(cudaMalloc(&out, sizeof(double) * blocks * threads));
-    cudaEvent_t a, b;
-    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
-    for (int which = 0; which < 2; ++which) {
-        int iters = 2000;
-        double best = 0;
-        for (int rep = 0; rep < 6; ++rep) {
-            CUDA_CHECK(cudaEventRecord(a));
-            if (which == 0) dmma_peak_kernel<<<blocks, threads>>>(out, iters);
-            else dfma_peak_kernel<<<blocks, threads>>>(out, iters);
-            CUDA_CHECK(cudaEventRecord(b));
-            CUDA_CHECK(cudaEventSynchronize(b));
-            float t = 0; cudaEventElapsedTime(&t, a, b);
-            const double per_thread_iter = which == 0 ? 16.0 * 512.0 / 32.0 : 32.0 * 2.0;
-            const double fl = (double)blocks * threads * iters * per_thread_iter;
-            best = std::max(best, fl / (t * 1e-3) * 1e-12);
-            if (t < ms && rep < 3) iters = (int)std::min(2.0e8, iters * std::max(2.0, (double)ms / std::max(t, 0.01f)));
-        }
-        *(which == 0 ? dmma_tflops : dfma_tflops) = best;
-    }
-    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
-#else
-    (void)device; (void)ms; (void)dmma_tflops; (void)dfma_tflops;
-    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
-#endif
-    CUPPEN_API_END
-}
-
-// DMMA and DFMA loops sharing every SM: rates of each kind alone (half of the warps idle) and together.
-int cuppen_measure_fp64_mix(int device, double* dmma_alone, double* dfma_alone, double* dmma_mixed, double* dfma_mixed) {
-    CUPPEN_API_BEGIN
-#if CUPPEN_CUDA
-    if (!dmma_alone || !dfma_alone || !dmma_mixed || !dfma_mixed) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
-    CUDA_CHECK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    const int blocks = prop.multiProcessorCount * 2, threads = 256;
-    double* out = nullptr;
-    CUDA_CHECK(cudaMalloc(&out, sizeof(double) * blocks * threads));
-    cudaEvent_t a, b;
-    CUDA_CHECK(cudaEventCreate(&a)); CUDA_CHECK(cudaEventCreate(&b));
-    // iteration counts sized so that each kind alone runs ~20 ms: DMMA 16 x 512 flop per warp-iteration,
-    // DFMA 32 x 2 flop per thread-iteration
-    const int it_dmma = 100000, it_dfma = 400000;           // ~26 ms each when alone
-    auto run = [&](int i1, int i2) {
-        float best = 1e30f;
-        for (int rep = 0; rep < 3; ++rep) {
-            CUDA_CHECK(cudaEventRecord(a));
-            fp64_mix_kernel<<<blocks, threads>>>(out, i1, i2);
-            CUDA_CHECK(cudaEventRecord(b));
-            CUDA_CHECK(cudaEventSynchronize(b));
-            float t = 0; cudaEventElapsedTime(&t, a, b);
-            best = std::min(best, t);
-        }
-        return (double)best * 1e-3;
-    };
-    const double fl_dmma = (double)blocks * 4 * it_dmma * 16.0 * 512.0;          // 4 DMMA warps per block
-    const double fl_dfma = (double)blocks * 128 * it_dfma * 64.0;                // 128 DFMA threads per block
-    const double t1 = run(it_dmma, 0), t2 = run(0, it_dfma), t3 = run(it_dmma, it_dfma);
-    *dmma_alone = fl_dmma / t1 * 1e-12;
-    *dfma_alone = fl_dfma / t2 * 1e-12;
-    // together: both finish inside t3 (the slower kind defines it); report the rates over the common window
-    *dmma_mixed = fl_dmma / t3 * 1e-12;
-    *dfma_mixed = fl_dfma / t3 * 1e-12;
-    cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
-#else
-    (void)device; (void)dmma_alone; (void)dfma_alone; (void)dmma_mixed; (void)dfma_mixed;
-    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
-#endif
-    CUPPEN_API_END
-}
 
 }  // extern "C"

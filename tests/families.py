@@ -15,6 +15,10 @@ def family(name, n, seed=5):
         return 1e8 * rng.normal(size=n), 1e8 * rng.normal(size=n - 1)
     if name == "tiny_norm":
         return 1e-8 * rng.normal(size=n), 1e-8 * rng.normal(size=n - 1)
+    if name == "extreme_tiny":       # dstedc scales T to unit norm (dlascl); unscaled, z^2*rho products underflow
+        return 1e-160 * rng.normal(size=n), 1e-160 * rng.normal(size=n - 1)
+    if name == "extreme_huge":
+        return 1e160 * rng.normal(size=n), 1e160 * rng.normal(size=n - 1)
     if name == "tiny_offdiag":
         return rng.normal(size=n), 1e-10 * rng.normal(size=n - 1)
     if name == "const_diag":
@@ -41,7 +45,7 @@ def family(name, n, seed=5):
     raise KeyError(name)
 
 
-FAMILIES = ["normal", "graded", "graded_rev", "huge_norm", "tiny_norm", "tiny_offdiag", "const_diag", "zero_diag",
+FAMILIES = ["normal", "graded", "graded_rev", "huge_norm", "tiny_norm", "extreme_tiny", "extreme_huge", "tiny_offdiag", "const_diag", "zero_diag",
             "clustered", "wilkinson", "glued_wilkinson", "negative", "some_zero_E", "laguerre"]
 
 

@@ -150,7 +150,7 @@ def test_gemm_kernels_against_fma_reference(lib, variant, M, N, K):
     """The three back-transformation GEMM kernels (cp.async 128x128, TMA 128x128, cp.async 64x64) on random
     data with an odd row offset, ragged M/N/K and scattered output columns; fp64 tolerance: K * 4 ulp."""
     from symmetric_eigenvalue_b200 import api
-    err, _ = api.selftest_gemm(variant, M, N, K, reps=1, lib=lib)
+    err, _ = api.selftest_gemm(variant, M, N, K, reps=1)
     assert err <= max(K, 1) * 4 * 2.2e-16, (variant, M, N, K, err)
 
 
@@ -287,7 +287,7 @@ def test_residual_kernel_slices(lib, n, g0, l0, cnt):
     odd / even first rows, odd local offsets (scalar-load path), single rows, slices touching row 0 and n-1."""
     from symmetric_eigenvalue_b200 import api
     for variant in (0, 14, 83):
-        assert api.selftest_residual(n, g0, l0, cnt, variant=variant, lib=lib)[0] < 1e-13
+        assert api.selftest_residual(n, g0, l0, cnt, variant=variant)[0] < 1e-13
 
 
 @pytest.mark.parametrize("name", ["s1_n4096_p8_sel", "goe_n4096_p8_sel"])

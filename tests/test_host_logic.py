@@ -330,3 +330,57 @@ def test_hostemu_handle_reuse_with_new_matrices(hostemu, oracle):
         t = s.timers()
         assert t["kernel_launches"] > 0 and t["total_s"] > 0
     s.close()
+
+
+def test_hostemu_rejects_non_finite_input_and_failed_set_leaves_no_result(hostemu, oracle):
+    """NaN/Inf entries must be refused before they reach the sort (they corrupted the index lists), and a
+    failed cuppen_set_tridiagonal must not leave the previous matrix's decomposition looking valid."""
+    n = 200
+    D, E = oracle.goe(n)
+    s = se.CuppenSolver(n, ref_leaves=2, lib=hostemu)
+    s.set_tridiagonal(D, E)
+    s.solve()
+    lam = s.eigenvalues()
+    for bad_d, bad_e in ((5, None), (None, 17)):
+        D2, E2 = D.copy(), E.copy()
+        if bad_d is not None:
+            D2[bad_d] = np.nan
+        if bad_e is not None:
+            E2[bad_e] = np.inf
+        with pytest.raises(se.CuppenError) as ei:
+            s.set_tridiagonal(D2, E2)
+        assert ei.value.code == -1
+        with pytest.raises(se.CuppenError) as ei:          # no matrix: solve and results are refused
+            s.solve()
+        assert ei.value.code == -5
+        with pytest.raises(se.CuppenError) as ei:
+            s.eigenvalues()
+        assert ei.value.code == -5
+    E3 = E.copy(); E3[n // 2 - 1] = 0.0                      # zero at the reference split: CUPPEN_ERR_ZERO, same state rule
+    with pytest.raises(se.CuppenError) as ei:
+        s.set_tridiagonal(D, E3)
+    assert ei.value.code == -3
+    with pytest.raises(se.CuppenError):
+        s.solve()
+    s.set_tridiagonal(D, E)
+    s.solve()
+    assert np.array_equal(lam, s.eigenvalues())
+    s.close()
+
+
+@pytest.mark.parametrize("expo", [-300, -160, -120, 0, 150, 290])
+def test_hostemu_power_of_two_scaling_is_exact(hostemu, oracle, expo):
+    """Matrices of extreme norm are scaled by a power of two inside the library, as dstedc does with dlascl (ADVICE
+    r01: 1e-140*T gave max|VtV-I| = 1 unscaled).  Under the accurate rule (ref_leaves=1) scaling T by 2^e must scale
+    eigenvalues and residuals by exactly 2^e and leave the vectors and the deflation counts alone.  (The reference
+    rule is not scale invariant by construction -- absolute thresholds, theta = 1000*beta -- and is kept in the
+    caller's units: plan_divide(inv_scale), MergeDesc::dthr.)"""
+    n = 200
+    D, E = oracle.goe(n)
+    base = se.cuppens(D, E, ref_leaves=1, lib=hostemu)
+    f = 2.0 ** round(expo * np.log2(10.0))
+    out = se.cuppens(D * f, E * f, ref_leaves=1, lib=hostemu)
+    assert np.array_equal(out["lam"], base["lam"] * f)
+    assert np.array_equal(out["V"], base["V"])
+    assert np.allclose(out["resid"], base["resid"] * f, rtol=1e-12, atol=0)
+    assert [(x.m, x.offset, x.zdefl, x.givens) for x in out["stats"]] == [(x.m, x.offset, x.zdefl, x.givens) for x in base["stats"]]
