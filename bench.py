@@ -6,12 +6,17 @@ FP64 TFLOP/s of the full eigendecomposition of a synthetic symmetric tridiagonal
   python bench.py --impl reference --steps K --warmup W    the reference's own CPU implementation
                                                            (oracle/_ref/cuppens_ref, else the oracle port)
 
-A "step" is one complete decomposition (leaves, all merges, back-transformation GEMMs, residuals) of
-the workload: BASELINE configs[1] `-s 1 -n 4096 -e` with the reference tree of `mpirun -n 8`, at N>1 the same
-decomposition sharded by eigenvector row blocks (strong scaling; this small problem is latency-bound and does
-not speed up).  At N>1 the same run also measures BASELINE configs[2] -- the seeded random symmetric tridiagonal
-matrix of size 16384 sharded over the N ranks -- and reports it, with its own 1-GPU time, under "config2_sharded".
-`--size/--matrix/--ref-leaves` select the other BASELINE configurations.  One JSON line is printed by rank 0.
+A "step" is one complete decomposition (leaves, all merges, back-transformation GEMMs, residuals).  The
+headline workload is the same at every N (strong scaling): BASELINE configs[2], the seeded random symmetric
+tridiagonal matrix (GOE beta-Hermite model) of size 16384 with the reference tree of `mpirun -n 8` -- the
+configuration BASELINE assigns to 2/4/8 GPUs, which also fits one.  The other BASELINE configurations ride along
+as extra keys of the same JSON line, each with its own time, roofline and parity check: configs[1]
+(`-s 1 -n 4096`), configs[3] (Wilkinson n=16384) and, at N=8, the north-star target n=32768 and configs[4]
+n=65536.  Every run ends with a parity verdict (`check.parity`): eigenvalues and per-merge deflation counts
+against the reference's own output (tests/golden/*.npz), residuals and orthogonality recomputed outside the
+library from sampled eigenvectors; a failed check makes the process exit non-zero.  `--workload NAME` runs one
+named workload as the headline (profiling), `--size/--matrix/--ref-leaves` an ad-hoc one.
+One JSON line is printed by rank 0.
 """
 import argparse
 import json
@@ -26,6 +31,19 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+METRIC = "eigenpairs wall-time (s), full eigendecomposition (eigenvalues + eigenvectors + residuals)"
+
+# BASELINE.json configs -> named workloads.  `golden`: the reference's own output for this input
+# (tests/golden/make_golden.py); None where the reference needs hours (eigenvalues are then checked against LAPACK).
+WORKLOADS = {
+    "goe16k": dict(matrix="goe", n=16384, ref_leaves=8, golden="goe_n16384_p8", baseline="configs[2]"),
+    "s1_4k": dict(matrix="s1", n=4096, ref_leaves=8, golden="s1_n4096_p8", baseline="configs[1]"),
+    "wilk16k": dict(matrix="wilk", n=16384, ref_leaves=8, golden="wilk64_n16384_p8", baseline="configs[3]"),
+    "goe32k": dict(matrix="goe", n=32768, ref_leaves=8, golden="goe_n32768_p8", baseline="north-star target"),
+    "goe64k": dict(matrix="goe", n=65536, ref_leaves=8, golden=None, baseline="configs[4]"),
+}
+HEADLINE = "goe16k"
 
 
 def make_matrix(kind, n):
@@ -55,9 +73,18 @@ def make_matrix(kind, n):
     raise SystemExit("unknown --matrix " + kind)
 
 
-def workload_name(a):
-    flag = {"s1": "-s 1", "s2": "-s 2"}.get(a.matrix, "-i %s(seeded)" % a.matrix)
-    return "cuppens %s -n %d -e (eigenvalues+eigenvectors+residuals), reference tree mpirun -n %d" % (flag, a.n, a.ref_leaves)
+def workload_name(w):
+    flag = {"s1": "-s 1", "s2": "-s 2"}.get(w["matrix"], "-i %s(seeded)" % w["matrix"])
+    return "cuppens %s -n %d -e (eigenvalues+eigenvectors+residuals), reference tree mpirun -n %d" % (flag, w["n"], w["ref_leaves"])
+
+
+def config_of(w):
+    """Identical in both arms (the driver compares the dicts)."""
+    return {"workload": workload_name(w), "n": w["n"], "matrix": w["matrix"], "ref_leaves": w["ref_leaves"]}
+
+
+def norm_T(D, E):
+    return float(np.abs(D).max() + (2 * np.abs(E).max() if len(E) else 0.0))
 
 
 class ClockSampler(threading.Thread):
@@ -137,326 +164,416 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
 
 
+def load_golden(name):
+    p = os.path.join(ROOT, "tests", "golden", "%s.npz" % name) if name else None
+    if not p or not os.path.exists(p):
+        return None
+    z = np.load(p)
+    return dict(D=z["D"], E=z["E"], P=int(z["P"]), lam=z["lam"], merges=[tuple(int(x) for x in r) for r in z["merges"].tolist()])
+
+
 # ------------------------------------------------------------------------------------------------------
-def run_ours(a):
-    import torch
-    import torch.distributed as dist
-    import symmetric_eigenvalue_b200 as se
-    from symmetric_eigenvalue_b200 import api
+class Ctx:
+    """Process-wide plumbing: torch.distributed over NCCL (one rank per GPU), barrier, L2 flush buffer."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != a.gpus:
-        if world == 1 and a.gpus > 1:
+    def __init__(self, a):
+        import torch
+        self.torch = torch
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != a.gpus and self.world == 1 and a.gpus > 1:
             raise SystemExit("--gpus %d needs torchrun (one rank per GPU)" % a.gpus)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
-    torch.cuda.set_device(local)
-    nccl_id = None
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        idt = torch.zeros(api.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(se.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().numpy().tobytes())
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    D, E = make_matrix(a.matrix, a.n)
-    solver = se.CuppenSolver(a.n, ref_leaves=a.ref_leaves, vectors=True, device=local, rank=rank, world=world, nccl_id=nccl_id)
-    solver.set_tridiagonal(D, E)                         # inputs resident in HBM before the timed region
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    def nccl_id(self):
+        import symmetric_eigenvalue_b200 as se
+        from symmetric_eigenvalue_b200 import api
+        if self.world == 1:
+            return None
+        t = self.torch.zeros(api.NCCL_ID_BYTES, dtype=self.torch.uint8, device="cuda")
+        if self.rank == 0:
+            t.copy_(self.torch.frombuffer(bytearray(se.nccl_unique_id()), dtype=self.torch.uint8))
+        self.dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        sampler.ready.wait(10)
-    for _ in range(a.warmup):
-        solver.solve()
-    barrier()
-    if sampler:
-        sampler.active = True
-    dev_ms, wall_ms, tsum = [], [], None
-    for _ in range(a.steps):
-        flush.zero_()                                    # L2 flush between timed iterations (untimed)
-        barrier()
-        t0 = time.perf_counter()
-        solver.solve()                                   # returns after the stream is drained
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
-        t = solver.timers()
-        pair = torch.tensor([t["device_s"] * 1e3, wall], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(pair, op=dist.ReduceOp.MAX)  # max over ranks
-        dev_ms.append(float(pair[0])); wall_ms.append(float(pair[1]))
-        tsum = t if tsum is None else {k: tsum[k] + t[k] for k in t}
-    barrier()
-    if sampler:
-        sampler.active = False
-    clocks = sampler.finish() if sampler else None
-    tavg = {k: v / a.steps for k, v in tsum.items()}
-    lam = solver.eigenvalues(); res = solver.residuals()
+    def max_over_ranks(self, vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device="cuda")
+        if self.dist:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(x) for x in t]
 
-    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
-    hD = torch.from_numpy(D).pin_memory(); hE = torch.from_numpy(E).pin_memory()
-    e2e = []
-    for it in range(max(2, min(a.steps, 5)) + 1):
-        barrier()
-        t0 = time.perf_counter()
-        solver.set_tridiagonal(hD.numpy(), hE.numpy())
-        solver.solve()
-        out_l = solver.eigenvalues(); out_r = solver.residuals()
-        torch.cuda.synchronize()
-        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        if it > 0:
-            e2e.append(float(dt[0]))
-    e2e_s = float(np.mean(e2e))
+    def sum_over_ranks(self, arr):
+        t = self.torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64)).cuda()
+        if self.dist:
+            self.dist.all_reduce(t)
+        return t.cpu().numpy()
 
-    # ---- N > 1 with the default workload: BASELINE configs[2] (seeded random symmetric tridiagonal n=16384, divide tree
-    # sharded across the ranks) as an extra key next to the headline series, which keeps configs[1] at every N
-    config2 = None
-    if world > 1 and getattr(a, "secondary", False):
-        n2, kind2 = 16384, "goe"
-        idt = torch.zeros(api.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            idt.copy_(torch.frombuffer(bytearray(se.nccl_unique_id()), dtype=torch.uint8))
-        dist.broadcast(idt, 0)
-        D2, E2 = make_matrix(kind2, n2)
-        s2 = se.CuppenSolver(n2, ref_leaves=a.ref_leaves, vectors=True, device=local, rank=rank, world=world,
-                             nccl_id=bytes(idt.cpu().numpy().tobytes()))
-        s2.set_tridiagonal(D2, E2)
-        for _ in range(3):
-            s2.solve()
-        ms2, t2sum = [], None
-        for _ in range(3):
-            flush.zero_()
-            barrier()
-            s2.solve()
-            t2 = s2.timers()
-            v = torch.tensor([t2["device_s"] * 1e3], dtype=torch.float64, device="cuda")
-            dist.all_reduce(v, op=dist.ReduceOp.MAX)
-            ms2.append(float(v[0]))
-            t2sum = t2 if t2sum is None else {k: t2sum[k] + t2[k] for k in t2}
-        res2 = float(s2.residuals().max())
-        s2.close()
-        solo_s = None
-        if rank == 0:
-            solo = se.CuppenSolver(n2, ref_leaves=a.ref_leaves, vectors=True, device=local)
-            solo.set_tridiagonal(D2, E2)
-            tt = []
-            for it in range(3):
-                solo.solve()
-                if it > 0:
-                    tt.append(solo.timers()["device_s"])
-            solo.close()
-            solo_s = float(np.mean(tt))
-        barrier()
-        if rank == 0:
-            v2 = float(np.mean(ms2)) * 1e-3
-            config2 = {"workload": "cuppens -i goe(seeded) -n %d -e, reference tree mpirun -n %d, sharded over %d GPUs" % (n2, a.ref_leaves, world),
-                       "value": v2, "unit": "s", "steps": 3, "same_workload_1gpu_s": solo_s, "speedup_vs_1gpu": solo_s / v2,
-                       "gemm_tflops_executed_rank0": t2sum["gemm_flop"] / t2sum["gemm_s"] * 1e-12 if t2sum["gemm_s"] > 0 else None,
-                       "tflops_fp64_nominal_4n3_over_3": (4.0 / 3.0) * n2 ** 3 / v2 * 1e-12, "max_residual": res2}
+    def gather_objects(self, obj):
+        if not self.dist:
+            return [obj]
+        out = [None] * self.world
+        self.dist.all_gather_object(out, obj)
+        return out
 
-    if rank != 0:
-        solver.close()
-        if world > 1:
-            dist.destroy_process_group()
-        return
 
-    ms = float(np.mean(dev_ms))
-    peaks, peak_src = measured_peaks()
-    one_gpu = None
-    if world > 1 and not a.no_single_gpu_compare and a.n <= 32768:
-        # the same workload on this rank's GPU alone (strong-scaling numerator), outside the timed region
-        solo = se.CuppenSolver(a.n, ref_leaves=a.ref_leaves, vectors=True, device=local)
-        solo.set_tridiagonal(D, E)
-        tt = []
-        for it in range(3):
-            solo.solve()
-            if it > 0:
-                tt.append(solo.timers()["device_s"])
-        solo.close()
-        one_gpu = {"value": float(np.mean(tt)), "unit": "s", "speedup": float(np.mean(tt)) / (ms * 1e-3)}
-    # dominant kernel class of the step, by CUDA-event time inside the library
+def parity_check(ctx, solver, w, D, E, lapack=None, accurate=False):
+    """Parity verdict of one decomposition (all ranks take part, the dict is complete on rank 0).
+      * eigenvalues within 1e-12*||T|| of the reference's own output where a golden exists, identical
+        (m, offset, zdefl, givens) per reference merge (the union over the ranks: a rank sees the merges that touch
+        its rows); without a golden: against LAPACK (dsterf) within the accuracy the reference rule allows
+        (its 1e-6 / 1e-5 absolute deflation thresholds: 2e-6*||T||), or 5e-14*||T|| under the accurate rule;
+      * residuals: the library's ||T x - lambda x|| column recomputed with numpy from sampled eigenvectors whose rows
+        are gathered from all ranks, and bounded by 1e-5*||T|| (reference rule; golden residual columns at these sizes do
+        not exist: the reference's -e is O(n^4)), 5e-14*||T|| under the accurate rule;
+      * orthogonality: max|V_S^T V_S - I| over the sampled columns S, Gram matrix summed over the ranks' row slices
+        (on one GPU additionally the full on-GPU Gram check)."""
+    n = w["n"]
+    nT = norm_T(D, E)
+    lam = solver.eigenvalues()
+    res = solver.residuals()
+    stats = sorted(set(s for part in ctx.gather_objects([(x.m, x.offset, x.zdefl, x.givens) for x in solver.merge_stats() if x.mode == 1])
+                       for s in part))
+    out = {"max_residual": float(res.max()), "lambda_min": float(lam[0]), "lambda_max": float(lam[-1]), "norm_T": nT}
+    ok = True
+    g = None if accurate else load_golden(w.get("golden"))
+    if g is not None and len(g["lam"]) == n and np.array_equal(g["D"], D):
+        out["lambda_max_abs_diff_vs_reference"] = float(np.abs(lam - g["lam"]).max())
+        out["lambda_tol"] = 1e-12 * nT
+        out["merge_stats_identical"] = (stats == sorted(g["merges"]))
+        out["reference_merges"] = len(g["merges"])
+        out["against"] = "reference output tests/golden/%s.npz" % w["golden"]
+        ok = ok and out["lambda_max_abs_diff_vs_reference"] <= out["lambda_tol"] and out["merge_stats_identical"]
+    else:
+        if lapack is None:
+            from scipy.linalg import eigvalsh_tridiagonal
+            lapack = eigvalsh_tridiagonal(D, E)
+        out["lambda_max_abs_diff_vs_lapack"] = float(np.abs(lam - lapack).max())
+        out["lambda_tol"] = (5e-14 if accurate else 2e-6) * nT
+        out["against"] = "LAPACK dsterf (scipy), %s" % ("accurate rule" if accurate else "reference-rule accuracy: no golden at this size")
+        ok = ok and out["lambda_max_abs_diff_vs_lapack"] <= out["lambda_tol"]
+    ok = ok and bool((np.diff(lam) >= 0).all())
+    # sampled eigenvectors: evenly spaced ranks plus their upper neighbours (close pairs are the hard ones)
+    base = np.unique(np.linspace(0, n - 2, 24).astype(np.int32))
+    sel = np.unique(np.concatenate([base, base + 1]))
+    Vloc = solver.eigenvector_columns(sel)
+    rowmap = solver.local_row_map()
+    gram = ctx.sum_over_ranks(Vloc.T @ Vloc)
+    out["orthogonality_sampled_max_abs"] = float(np.abs(gram - np.eye(len(sel))).max())
+    parts = ctx.gather_objects((rowmap, Vloc))
+    if ctx.rank == 0:
+        V = np.empty((n, len(sel)))
+        seen = np.zeros(n, dtype=np.int64)
+        for rm, vl in parts:
+            V[rm] = vl
+            seen[rm] += 1
+        TV = D[:, None] * V
+        TV[1:] += E[:, None] * V[:-1]
+        TV[:-1] += E[:, None] * V[1:]
+        r2 = np.linalg.norm(TV - V * lam[sel][None, :], axis=0)
+        out["rows_partitioned"] = bool((seen == 1).all())
+        out["residual_recomputed_max_rel_diff"] = float((np.abs(r2 - res[sel]) / np.maximum(res[sel], 1e-13 * nT)).max())
+        ok = ok and out["rows_partitioned"] and out["residual_recomputed_max_rel_diff"] < 1e-3
+    res_tol = (5e-14 if accurate else 1e-5) * nT
+    out["residual_tol"] = res_tol
+    ok = ok and out["max_residual"] <= res_tol and out["orthogonality_sampled_max_abs"] < 1e-11
+    if ctx.world == 1:
+        dev, sec = solver.orthogonality()              # on-GPU max|V^T V - I| of the whole matrix (gram_check_kernel)
+        out["orthogonality_max_abs"] = dev
+        out["orthogonality_check_s"] = sec
+        out["orthogonality_check_tflops"] = (n ** 3 + n ** 2 * 128.0) / sec * 1e-12 if sec > 0 else None
+        ok = ok and dev < 1e-11
+    out["parity"] = bool(ok)
+    return out
+
+
+def roofline_entry(tavg, w, world, ms, fp64, peaks, peak_src):
+    """Roofline of the dominant kernel class of the step (by CUDA-event time inside the library)."""
+    n = w["n"]
     cats = {"gemm": tavg["gemm_s"], "pack": tavg["pack_s"], "ugen": tavg["backtransform_ev_s"], "secular": tavg["root_finding_s"],
             "deflation": tavg["deflation_s"], "leaf": tavg["leaf_s"], "residual": tavg["residual_s"]}
     dom = max(cats, key=cats.get)
-    dmma_tf, dfma_tf = se.api.measure_fp64_peak(local, 200)
-    dgemm_tf = None
-    try:
-        A = torch.randn(8192, 8192, dtype=torch.float64, device="cuda"); B = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
-        best = 1e9
-        for _ in range(4):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); torch.matmul(A, B); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
-        dgemm_tf = 2 * 8192.0 ** 3 / (best * 1e-3) * 1e-12
-        del A, B
-    except Exception:
-        pass
-    fp64_peak = max(x for x in (dmma_tf, dgemm_tf) if x)
     gemm_tflops = tavg["gemm_flop"] / tavg["gemm_s"] * 1e-12 if tavg["gemm_s"] > 0 else 0.0
+    fp64_peak = fp64["peak"]
     if dom in ("gemm", "secular", "deflation", "leaf"):
-        roof = {"kernel": "dgemm_tma_kernel + dgemm_dmma_kernel (DMMA.8x8x4 back-transformation GEMMs)", "bound": "tensor", "achieved": gemm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": gemm_tflops / fp64_peak if fp64_peak else None, "traffic": None,
-                "peak_source": "measured in this run: DMMA.8x8x4 issue loop %.1f TF/s, cuBLAS Dgemm 8192^3 %s TF/s (no FP64 entry in MEASURED_PEAKS.json)"
-                               % (dmma_tf, "%.1f" % dgemm_tf if dgemm_tf else "n/a"),
-                "dominant_by_time": dom}
+        roof = {"kernel": "dgemm_tma_kernel + dgemm_dmma_kernel (DMMA.8x8x4 back-transformation GEMMs)", "bound": "tensor",
+                "achieved": gemm_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": gemm_tflops / fp64_peak if fp64_peak else None,
+                "traffic": None, "peak_source": fp64["source"], "dominant_by_time": dom,
+                "share_of_step": tavg["gemm_s"] / (ms * 1e-3)}
     else:
-        nbytes = tavg["pack_bytes"] if dom == "pack" else tavg["ugen_bytes"] if dom == "ugen" else 8.0 * a.n * a.n
-        sec = cats[dom]
-        ach = nbytes / sec * 1e-9
+        nbytes = tavg["pack_bytes"] if dom == "pack" else tavg["ugen_bytes"] if dom == "ugen" else 8.0 * n * n / world
+        ach = nbytes / cats[dom] * 1e-9
         roof = {"kernel": {"pack": "pack_kernel", "ugen": "ugen_kernel", "residual": "residual_kernel"}[dom], "bound": "hbm",
                 "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
-                "peak_source": peak_src, "dominant_by_time": dom,
-                "gemm": {"achieved_tflops": gemm_tflops, "fp64_peak_tflops": fp64_peak,
-                         "frac": gemm_tflops / fp64_peak if fp64_peak else None}}
-    # DRAM traffic of the roofline kernel from a committed `ncu --set full` capture of the same command, when there is one
+                "peak_source": peak_src, "dominant_by_time": dom, "share_of_step": cats[dom] / (ms * 1e-3),
+                "gemm": {"achieved_tflops": gemm_tflops, "fp64_peak_tflops": fp64_peak, "frac": gemm_tflops / fp64_peak if fp64_peak else None}}
+    # DRAM traffic of the roofline kernel from a committed `ncu --set full` capture of the same workload, when there is one
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get("%s|%d" % (workload_name(a), world))
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("%s|%d" % (workload_name(w), world))
         if tr and tr["kernel"].split()[0] in roof["kernel"]:
             roof["traffic"] = tr["dram_bytes_per_launch"]
             roof["traffic_source"] = tr["source"]
     except Exception:
         pass
     if dom not in ("gemm", "pack", "ugen", "residual"):
-        roof["note"] = ("latency-bound configuration: %d launches per step, the largest phase (%s) is %.0f %% of it; the roofline "
-                        "is quoted for the only tensor-bound kernel" % (int(tsum["kernel_launches"]) // a.steps, dom, 100 * cats[dom] / (ms * 1e-3)))
-    line = {
-        "metric": "eigenpairs wall-time (s), full eigendecomposition (eigenvalues + eigenvectors + residuals)",
-        "value": ms * 1e-3, "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms,
-        "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "n": a.n, "matrix": a.matrix, "ref_leaves": a.ref_leaves,
-                   "l2": "256 MiB buffer zeroed between timed steps (untimed); Q working set 2x%.0f MB (in place + packed live columns)" % (8e-6 * a.n * a.n / world),
-                   "sharding": "eigenvector row blocks, %d rank(s)" % world},
-        "wall_ms_per_step": float(np.mean(wall_ms)),
-        "eigenpairs_per_s": a.n / (ms * 1e-3),
-        "tflops_fp64_nominal_4n3_over_3": (4.0 / 3.0) * a.n ** 3 / (ms * 1e-3) * 1e-12,
-        "gemm_tflops_executed": gemm_tflops,
-        "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(8 * (4 * a.n - 2)), "d2h_bytes_per_step": int(8 * 2 * a.n)},
-        "gpu_launches": int(tsum["kernel_launches"]),
-        "same_workload_1gpu": one_gpu,
-        "phase_ms": {k: v * 1e3 for k, v in cats.items()},
-        "roofline": roof,
-        "fp64_yardsticks_tflops": {"dmma_issue_loop": dmma_tf, "dfma_issue_loop": dfma_tf, "cublas_dgemm_8192": dgemm_tf},
-        "clocks": clocks,
-        "config2_sharded": config2,
-        "check": {"max_residual": float(res.max()), "lambda_min": float(lam[0]), "lambda_max": float(lam[-1])},
-    }
-    if world == 1:
-        dev, sec = solver.orthogonality()              # on-GPU max|V^T V - I| of the last decomposition (gram_check_kernel)
-        line["check"]["orthogonality_max_abs"] = dev
-        line["check"]["orthogonality_check_s"] = sec
-        line["check"]["orthogonality_check_tflops"] = (a.n ** 3 + a.n ** 2 * 128.0) / sec * 1e-12 if sec > 0 else None
-    if world == 1 and a.select > 0:
-        line["selected_mode"] = selected_mode(a, D, E, local, res)
-    if world == 1 and not a.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference(a, bounded_s=25.0)
-    print(json.dumps(line), flush=True)
+        roof["note"] = ("latency-bound configuration: the largest phase (%s) is %.0f %% of the step; the roofline is quoted for the "
+                        "only tensor-bound kernel" % (dom, 100 * cats[dom] / (ms * 1e-3)))
+    return roof, cats, gemm_tflops
+
+
+def run_workload(ctx, w, steps, warmup, e2e_iters, fp64, lapack=None, want_solo=True, accurate=False):
+    """Times `steps` decompositions of workload w on all ranks of ctx (CUDA events inside the library, max over ranks,
+    L2 flushed between steps), checks parity, and -- on several GPUs -- times the same workload on rank 0's GPU alone."""
+    import symmetric_eigenvalue_b200 as se
+    torch = ctx.torch
+    n, P = w["n"], (1 if accurate else w["ref_leaves"])
+    D, E = make_matrix(w["matrix"], n)
+    solver = se.CuppenSolver(n, ref_leaves=P, vectors=True, device=ctx.local, rank=ctx.rank, world=ctx.world, nccl_id=ctx.nccl_id())
+    solver.set_tridiagonal(D, E)                         # inputs resident in HBM before the timed region
+    for _ in range(warmup):
+        solver.solve()
+    ctx.barrier()
+    dev_ms, wall_ms, tsum = [], [], None
+    for _ in range(steps):
+        ctx.flush.zero_()                                # L2 flush between timed iterations (untimed)
+        ctx.barrier()
+        t0 = time.perf_counter()
+        solver.solve()                                   # returns after the stream is drained
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        t = solver.timers()
+        d, wl = ctx.max_over_ranks([t["device_s"] * 1e3, wall])
+        dev_ms.append(d); wall_ms.append(wl)
+        tsum = t if tsum is None else {k: tsum[k] + t[k] for k in t}
+    ctx.barrier()
+    tavg = {k: v / steps for k, v in tsum.items()}
+    ms = float(np.mean(dev_ms))
+    out = {"workload": workload_name(w), "baseline_config": w.get("baseline"), "value": ms * 1e-3, "unit": "s", "steps": steps, "warmup": warmup,
+           "ms_per_step": ms, "ms_per_step_min": float(np.min(dev_ms)), "wall_ms_per_step": float(np.mean(wall_ms)),
+           "gpu_launches": int(tsum["kernel_launches"]), "launches_per_step": int(tsum["kernel_launches"]) // steps}
+    # ---- end to end through the public API with HOST buffers (pinned), H2D + D2H inside the timed region
+    if e2e_iters > 0:
+        hD = torch.from_numpy(D).pin_memory(); hE = torch.from_numpy(E).pin_memory()
+        e2e = []
+        for it in range(e2e_iters + 1):
+            ctx.barrier()
+            t0 = time.perf_counter()
+            solver.set_tridiagonal(hD.numpy(), hE.numpy())
+            solver.solve()
+            solver.eigenvalues(); solver.residuals()
+            torch.cuda.synchronize()
+            dt, = ctx.max_over_ranks([time.perf_counter() - t0])
+            if it > 0:
+                e2e.append(dt)
+        out["e2e"] = {"value": float(np.mean(e2e)), "unit": "s", "h2d_bytes_per_step": int(8 * (4 * n - 2)), "d2h_bytes_per_step": int(8 * 2 * n)}
+    out["check"] = parity_check(ctx, solver, w, D, E, lapack=lapack, accurate=accurate)
+    lam_sharded = solver.eigenvalues()
     solver.close()
-    if world > 1:
-        dist.destroy_process_group()
+    peaks, peak_src = measured_peaks()
+    roof, cats, gemm_tflops = roofline_entry(tavg, w, ctx.world, ms, fp64, peaks, peak_src)
+    out["phase_ms"] = {k: v * 1e3 for k, v in cats.items()}
+    out["phase_ms"]["outside_phase_timers"] = ms - sum(out["phase_ms"].values())
+    out["roofline"] = roof
+    out["gemm_tflops_executed_rank0"] = gemm_tflops
+    out["fp64_tflops_nominal"] = {"value": (4.0 / 3.0) * n ** 3 / (ms * 1e-3) * 1e-12,
+                                  "note": "NOMINAL (4/3)n^3 flop of an undeflated binary tree / time, all GPUs; deflation removes work, "
+                                          "so this can exceed the FP64 peak -- not an achieved rate (that is roofline.achieved)"}
+    # ---- the same workload on this rank's GPU alone (strong-scaling numerator), outside the timed region
+    if ctx.world > 1 and want_solo:
+        solo_s = None
+        if ctx.rank == 0:
+            solo = se.CuppenSolver(n, ref_leaves=P, vectors=True, device=ctx.local)
+            solo.set_tridiagonal(D, E)
+            tt = []
+            for it in range(3):
+                solo.solve()
+                if it > 0:
+                    tt.append(solo.timers()["device_s"])
+            lam1 = solo.eigenvalues()
+            solo.close()
+            solo_s = float(np.mean(tt))
+            diff = float(np.abs(lam1 - lam_sharded).max())
+            out["same_workload_1gpu"] = {"value": solo_s, "unit": "s", "speedup": solo_s / (ms * 1e-3),
+                                         "lambda_max_abs_diff_vs_sharded": diff}
+            # the sharded run must reproduce the one-GPU eigenvalues (same algorithm, different reduction orders)
+            out["check"]["parity"] = bool(out["check"]["parity"] and diff <= 1e-13 * norm_T(D, E))
+        ctx.barrier()
+    return out, (D, E)
 
 
-def selected_mode(a, D, E, device, full_resid):
+def run_ours(a):
+    import symmetric_eigenvalue_b200 as se
+    ctx = Ctx(a)
+    rank, world, local = ctx.rank, ctx.world, ctx.local
+    head = a.workload_dict
+    # FP64 yardsticks first (no FP64 entry in MEASURED_PEAKS.json): register-resident DMMA issue loop + cuBLAS Dgemm
+    fp64 = None
+    if rank == 0:
+        torch = ctx.torch
+        dmma_tf, dfma_tf = se.api.measure_fp64_peak(local, 200)
+        dgemm_tf = None
+        try:
+            A = torch.randn(8192, 8192, dtype=torch.float64, device="cuda"); B = torch.randn(8192, 8192, dtype=torch.float64, device="cuda")
+            best = 1e9
+            for _ in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); torch.matmul(A, B); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1))
+            dgemm_tf = 2 * 8192.0 ** 3 / (best * 1e-3) * 1e-12
+            del A, B
+        except Exception:
+            pass
+        fp64 = {"peak": max(x for x in (dmma_tf, dgemm_tf) if x), "dmma_issue_loop": dmma_tf, "dfma_issue_loop": dfma_tf, "cublas_dgemm_8192": dgemm_tf,
+                "source": "measured in this run: DMMA.8x8x4 issue loop %.1f TF/s, cuBLAS Dgemm 8192^3 %s TF/s (no FP64 entry in MEASURED_PEAKS.json)"
+                          % (dmma_tf, "%.1f" % dgemm_tf if dgemm_tf else "n/a")}
+    fp64 = ctx.gather_objects(fp64)[0]
+    ctx.barrier()
+
+    # LAPACK eigenvalues (dsterf, ~1 min at n = 65536) for the extra workloads that have no reference golden: computed
+    # on rank 0's host cores while the GPUs work
+    lapack_threads, lapack_box = {}, {}
+    if rank == 0 and a.extras and (world == 8 or a.big):
+        for k in ("goe32k", "goe64k"):
+            if load_golden(WORKLOADS[k].get("golden")) is None:
+                def _lap(k=k):
+                    from scipy.linalg import eigvalsh_tridiagonal
+                    d, e = make_matrix(WORKLOADS[k]["matrix"], WORKLOADS[k]["n"])
+                    lapack_box[k] = eigvalsh_tridiagonal(d, e)
+                lapack_threads[k] = threading.Thread(target=_lap, daemon=True)
+                lapack_threads[k].start()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        sampler.ready.wait(10)
+        sampler.active = True
+    res, (D, E) = run_workload(ctx, head, a.steps, a.warmup, max(2, min(a.steps, 5)), fp64)
+    if sampler:
+        sampler.active = False
+    clocks = sampler.finish() if sampler else None
+
+    extras = {}
+    if a.extras:
+        names = [k for k in ("s1_4k", "wilk16k") if WORKLOADS[k] is not head]
+        if world == 8 or a.big:
+            names += ["goe32k", "goe64k"]
+        for k in names:
+            w = WORKLOADS[k]
+            n = w["n"]
+            if rank == 0 and k in lapack_threads:
+                lapack_threads[k].join()
+            lap = ctx.gather_objects(lapack_box.get(k))[0]
+            steps = 10 if n <= 4096 else 5 if n <= 16384 else 3 if n <= 32768 else 2
+            r, _ = run_workload(ctx, w, steps, 3, 0, fp64, lapack=lap, want_solo=(n <= 32768))
+            if k == "goe64k":
+                # configs[4] once more under the accurate rule (ref_leaves = 1: LAPACK-grade tolerances on every level),
+                # where eigenvalues, residuals and orthogonality can be held to working precision against LAPACK
+                r2, _ = run_workload(ctx, w, 1, 1, 0, fp64, lapack=lap, want_solo=False, accurate=True)
+                r["accurate_rule"] = {"value": r2["value"], "unit": "s", "check": r2["check"]}
+            extras[k] = r
+
+    if rank != 0:
+        ok = res["check"]["parity"] and all(x["check"]["parity"] for x in extras.values())
+        if ctx.dist:
+            ctx.dist.destroy_process_group()
+        sys.exit(0 if ok else 3)
+
+    line = {
+        "metric": METRIC, "value": res["value"], "unit": "s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": res["ms_per_step"], "higher_is_better": False, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_of(head),
+        "timing": {"l2": "256 MiB buffer zeroed between timed steps (untimed); Q working set 2x%.0f MB per GPU (in place + packed live columns)"
+                         % (8e-6 * head["n"] ** 2 / world),
+                   "sharding": "eigenvector row blocks, %d rank(s)" % world, "clock": "CUDA events inside the library, max over ranks",
+                   "ms_per_step_min": res["ms_per_step_min"], "wall_ms_per_step": res["wall_ms_per_step"]},
+        "eigenpairs_per_s": head["n"] / res["value"],
+        "fp64_tflops_nominal": res["fp64_tflops_nominal"],
+        "gemm_tflops_executed": res["gemm_tflops_executed_rank0"],
+        "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "launches_per_step": res["launches_per_step"],
+        "same_workload_1gpu": res.get("same_workload_1gpu"),
+        "phase_ms": res["phase_ms"], "roofline": res["roofline"],
+        "fp64_yardsticks_tflops": {k: fp64[k] for k in ("dmma_issue_loop", "dfma_issue_loop", "cublas_dgemm_8192")},
+        "clocks": clocks, "check": res["check"], "other_configs": extras,
+    }
+    if world == 1 and a.select > 0:
+        line["selected_mode"] = selected_mode(a, head, D, E, local)
+    if world == 1:
+        line["eigenvalues_only"] = eigenvalues_only(head, D, E, local, a)
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference(head, vectors=False)
+        if line["cpu_baseline"].get("eigenvalue_phase_s") and line.get("eigenvalues_only"):
+            line["eigenvalues_only"]["reference_cpu_s"] = line["cpu_baseline"]["eigenvalue_phase_s"]
+    ok = line["check"]["parity"] and all(x["check"]["parity"] and x.get("accurate_rule", {"check": {"parity": True}})["check"]["parity"]
+                                         for x in extras.values())
+    line["check"]["parity_all_configs"] = bool(ok)
+    print(json.dumps(line), flush=True)
+    if ctx.dist:
+        ctx.dist.destroy_process_group()
+    if not ok:
+        sys.stderr.write("bench.py: PARITY CHECK FAILED (see check / other_configs[*].check)\n")
+        sys.exit(3)
+
+
+def eigenvalues_only(w, D, E, device, a):
+    """Eigenvalue-only decomposition (the reference without -e): boundary-row propagation instead of GEMMs.  The
+    fully measured counterpart of the reference arm's eigenvalue phase (no extrapolation on either side)."""
+    import symmetric_eigenvalue_b200 as se
+    s = se.CuppenSolver(w["n"], ref_leaves=w["ref_leaves"], vectors=False, device=device)
+    s.set_tridiagonal(D, E)
+    dev = []
+    for it in range(3 + max(3, min(a.steps, 10))):
+        s.solve()
+        if it >= 3:
+            dev.append(s.timers()["device_s"])
+    lam = s.eigenvalues()
+    s.close()
+    g = load_golden(w.get("golden"))
+    out = {"value": float(np.mean(dev)), "unit": "s"}
+    if g is not None and len(g["lam"]) == w["n"]:
+        out["lambda_max_abs_diff_vs_reference"] = float(np.abs(lam - g["lam"]).max())
+    return out
+
+
+def selected_mode(a, w, D, E, device):
     """The reference's -eFILE use case (extra key, not the headline metric): `--select K` evenly spaced
     eigenvectors through the selected-eigenvector mode (no n x n matrix; select_stages.h).  Time per solve =
     eigenvalue-only decomposition + back-application, CUDA events inside the library."""
     import symmetric_eigenvalue_b200 as se
-    sel = np.unique(np.linspace(0, a.n - 1, a.select).astype(np.int32))
-    s = se.CuppenSolver(a.n, ref_leaves=a.ref_leaves, device=device, select=True)
+    n = w["n"]
+    sel = np.unique(np.linspace(0, n - 1, a.select).astype(np.int32))
+    s = se.CuppenSolver(n, ref_leaves=w["ref_leaves"], device=device, select=True)
     s.set_tridiagonal(D, E)
     s.select(sel)
     dev, app = [], []
-    for it in range(a.warmup + max(3, min(a.steps, 10))):
+    for it in range(3 + max(3, min(a.steps, 10))):
         s.solve()
-        if it >= a.warmup:
+        if it >= 3:
             t = s.timers()
             dev.append(t["device_s"]); app.append(t["apply_s"])
     r = s.residuals(sel)
     s.close()
-    # algorithmic work of the apply phase: pole/root pairs = sum over merges of k^2 (one fp64 reciprocal + 8 fma each)
     return {"k": int(sel.size), "device_s_per_solve": float(np.mean(dev)), "apply_s": float(np.mean(app)),
-            "max_residual": float(r.max()), "max_residual_full_mode_same_columns": float(full_resid[sel].max()),
+            "max_residual": float(r.max()),
             "note": "eigenvalue-only solve + implicit back-application of the K selected columns; "
-                    "the reference's -eFILE costs cpu_baseline.backtransform_s_per_eigenvector per column"}
+                    "the reference's -eFILE costs backtransform_s_per_eigenvector (--impl reference line) per column"}
 
 
 # ------------------------------------------------------------------------------------------------------
-_BT_CACHE = {}
-
-
-def cpu_reference(a, bounded_s=25.0):
-    """The reference's own CPU path on this box's host cores, on a bounded sample of the workload:
-    the complete eigenvalue phase (`cuppens -s .. -n ..`, mpirun -n P x OMP threads) plus the
-    back-transformation of `nvec` sampled eigenvectors (-eFILE), extrapolated to all n vectors
-    (the reference's back-transformation is O(n^3)..O(n^4), SURVEY.md finding 5)."""
-    import oracle
-    cores = os.cpu_count() or 1
-    P = a.ref_leaves
-    T = max(1, cores // P)
-    D, E = make_matrix(a.matrix, a.n)
-    have_ref = os.path.exists(oracle.ref_binary())
-    if not have_ref:
-        t0 = time.perf_counter()
-        oracle.solve(D, E, P, vectors=False, residuals=False)
-        dt = time.perf_counter() - t0
-        return {"value": None, "unit": "s", "cores": cores, "kind": "port", "eigenvalues_only_s": dt,
-                "sample": "oracle port (oracle/cuppen_oracle.c), eigenvalue phase only, OpenMP %d threads" % cores}
-    with tempfile.TemporaryDirectory() as td:
-        mtx = os.path.join(td, "in.mtx")
-        if a.matrix in ("s1", "s2"):
-            args = ["-s", a.matrix[1], "-n", str(a.n)]
-        else:
-            oracle.write_mtx(mtx, D, E)
-            args = ["-i", mtx]
-        out = os.path.join(td, "out.txt")
-        t0 = time.perf_counter()
-        r = oracle.run_reference(args + [out], P=P, threads=T, timeout=3600, stats=False)
-        t_eval_wall = time.perf_counter() - t0
-        txt = r["stdout"]
-        t_eval = _grab(txt, "Required time to compute all eigenvalues:")
-        # sampled eigenvectors: time one, then as many as fit the budget (measured once per process:
-        # later steps of the same run re-time the eigenvalue phase and reuse the per-vector cost)
-        nvec, per_vec, t_bt = 0, None, None
-        budget = max(0.0, bounded_s - t_eval_wall)
-        ev = os.path.join(td, "ev.txt")
-        trial = 1
-        key = (a.matrix, a.n, P)
-        if key in _BT_CACHE:
-            nvec, per_vec = _BT_CACHE[key]
-        while key not in _BT_CACHE:
-            idx = np.unique(np.linspace(1, a.n, trial).astype(int))
-            open(ev, "w").write("".join("%d\n" % i for i in idx))
-            t0 = time.perf_counter()
-            r2 = oracle.run_reference(args + ["-e" + ev, out], P=P, threads=T, timeout=3600, stats=False)
-            dt = time.perf_counter() - t0
-            bt = _grab(r2["stdout"], "Required time for backtransformation:")
-            if bt is not None:
-                nvec, per_vec, t_bt = len(idx), bt / len(idx), bt
-            budget -= dt
-            if per_vec is None or budget < 2 * dt or trial >= 64:
-                if per_vec is not None:
-                    _BT_CACHE[key] = (nvec, per_vec)
-                break
-            trial = min(64, max(trial + 1, int(trial * min(4.0, budget / max(dt, 1e-3) / 2))))
-    value = None if (t_eval is None or per_vec is None) else t_eval + per_vec * a.n
-    return {"value": value, "unit": "s", "cores": P * T, "kind": "reference",
-            "eigenvalue_phase_s": t_eval, "backtransform_s_per_eigenvector": per_vec, "sampled_eigenvectors": nvec,
-            "sample": "unmodified reference (oracle/_ref/cuppens_ref, MPI shim ranks P=%d x OMP_NUM_THREADS=%d): full eigenvalue "
-                      "phase + back-transformation of %d sampled eigenvectors (-eFILE), extrapolated x n=%d" % (P, T, nvec, a.n)}
-
-
 def _grab(txt, key):
     for line in txt.splitlines():
         if key in line:
@@ -467,24 +584,82 @@ def _grab(txt, key):
     return None
 
 
+def cpu_reference(w, vectors, vec_timeout=1500.0):
+    """The reference's own CPU path on this box's host cores (unmodified reference, oracle/_ref/cuppens_ref, MPI shim
+    ranks P x OpenMP threads = all cores): the complete eigenvalue phase, and -- `vectors` -- the back-transformation
+    of ONE eigenvector (-eFILE), which the reference repeats for each of the n eigenvectors (O(n^3) per vector for
+    P >= 4, SURVEY.md finding 5); the full-decomposition figure is therefore eigenvalue phase + n x that, marked
+    `extrapolated`.  Each part is timed once."""
+    import oracle
+    cores = os.cpu_count() or 1
+    P = w["ref_leaves"]
+    T = max(1, cores // P)
+    D, E = make_matrix(w["matrix"], w["n"])
+    n = w["n"]
+    if not os.path.exists(oracle.ref_binary()):
+        t0 = time.perf_counter()
+        oracle.solve(D, E, P, vectors=False, residuals=False)
+        dt = time.perf_counter() - t0
+        return {"value": dt, "unit": "s", "cores": 1, "kind": "port", "eigenvalue_phase_s": dt, "metric_covered": "eigenvalues only",
+                "sample": "oracle port (oracle/cuppen_oracle.c), eigenvalue phase only, single thread"}
+    with tempfile.TemporaryDirectory() as td:
+        if w["matrix"] in ("s1", "s2"):
+            args = ["-s", w["matrix"][1], "-n", str(n)]
+        else:
+            mtx = os.path.join(td, "in.mtx")
+            oracle.write_mtx(mtx, D, E)
+            args = ["-i", mtx]
+        out = os.path.join(td, "out.txt")
+        t0 = time.perf_counter()
+        r = oracle.run_reference(args + [out], P=P, threads=T, timeout=3600, stats=False)
+        wall_eval = time.perf_counter() - t0
+        t_eval = _grab(r["stdout"], "Required time to compute all eigenvalues:")
+        info = {"unit": "s", "cores": P * T, "kind": "reference", "eigenvalue_phase_s": t_eval, "eigenvalue_run_wall_s": wall_eval,
+                "root_finding_s": _grab(r["stdout"], "Required time for root finding:")}
+        who = "unmodified reference (oracle/_ref/cuppens_ref, MPI shim ranks P=%d x OMP_NUM_THREADS=%d)" % (P, T)
+        if not vectors:
+            info.update(value=t_eval, metric_covered="eigenvalues only",
+                        sample=who + ": the complete eigenvalue phase of the headline workload, measured once; its -e back-transformation "
+                                     "is timed by the --impl reference arm (one eigenvector at this size takes minutes)")
+            return info
+        ev = os.path.join(td, "ev.txt")
+        open(ev, "w").write("%d\n" % (n // 2))
+        per_vec, how = None, None
+        try:
+            r2 = oracle.run_reference(args + ["-e" + ev, out], P=P, threads=T, timeout=vec_timeout, stats=False)
+            per_vec = _grab(r2["stdout"], "Required time for backtransformation:")
+            how = "back-transformation of 1 eigenvector (-eFILE, rank n/2) at full size, measured once"
+        except subprocess.TimeoutExpired:
+            per_vec = None
+        if per_vec is None and n > 4096:
+            # the single eigenvector did not finish inside the budget: time it on the leading 4096 x 4096 block and scale
+            # by (n/4096)^3 (O(n^3) per vector: n rows x sum over inner stages of pn*n_ts)
+            mtx2 = os.path.join(td, "in4k.mtx")
+            oracle.write_mtx(mtx2, D[:4096], E[:4095])
+            open(ev, "w").write("2048\n")
+            r3 = oracle.run_reference(["-i", mtx2, "-e" + ev, out], P=P, threads=T, timeout=vec_timeout, stats=False)
+            b4 = _grab(r3["stdout"], "Required time for backtransformation:")
+            per_vec = None if b4 is None else b4 * (n / 4096.0) ** 3
+            how = "1 eigenvector did not finish in %.0f s at full size; timed on the leading 4096-block and scaled by (n/4096)^3" % vec_timeout
+    value = None if (t_eval is None or per_vec is None) else t_eval + per_vec * n
+    info.update(value=value, backtransform_s_per_eigenvector=per_vec, sampled_eigenvectors=1, extrapolated=True,
+                sample=who + ": full eigenvalue phase (measured) + %s, extrapolated x n=%d" % (how, n))
+    return info
+
+
 def run_reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vals, info = [], None
-    for it in range(a.warmup + a.steps):
-        info = cpu_reference(a, bounded_s=a.ref_budget)
-        if it >= a.warmup and info["value"] is not None:
-            vals.append(info["value"])
-    v = float(np.mean(vals)) if vals else None
-    info["value"] = v
-    line = {"impl": "reference",
-            "metric": "eigenpairs wall-time (s), full eigendecomposition (eigenvalues + eigenvectors + residuals)",
-            "value": v, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+    w = a.workload_dict
+    info = cpu_reference(w, vectors=True, vec_timeout=a.ref_vec_timeout)      # each part timed once per process
+    v = info["value"]
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": None if v is None else v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a), "n": a.n, "matrix": a.matrix, "ref_leaves": a.ref_leaves},
+            "dtype": "f64", "data": "synthetic", "config": config_of(w), "extrapolated": True,
             "cpu_baseline": info,
+            "eigenvalues_only": {"value": info.get("eigenvalue_phase_s"), "unit": "s",
+                                 "note": "fully measured (no extrapolation): the reference without -e; our arm reports the same under eigenvalues_only"},
             "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -495,22 +670,26 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS), help="named BASELINE workload as the headline (default %s)" % HEADLINE)
     ap.add_argument("--size", dest="n", type=int, default=None)
     ap.add_argument("--matrix", default=None, choices=["s1", "s2", "goe", "randu", "wilk"])
     ap.add_argument("--ref-leaves", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", dest="extras", action="store_false", help="headline workload only")
+    ap.add_argument("--big", action="store_true", help="also run n=32768 / n=65536 as extra keys below 8 GPUs")
     ap.add_argument("--select", type=int, default=16, help="also time the selected-eigenvector mode on K vectors (0: skip)")
-    ap.add_argument("--no-single-gpu-compare", action="store_true")
-    ap.add_argument("--ref-budget", type=float, default=25.0, help="seconds of CPU work per reference step")
+    ap.add_argument("--ref-vec-timeout", type=float, default=1500.0, help="reference arm: seconds allowed for the one full-size eigenvector")
     a = ap.parse_args()
-    # default workload: BASELINE configs[1] (`-s 1 -n 4096`) at every N, so that the per-N values form one strong-scaling
-    # series; at N>1 BASELINE configs[2] (seeded random symmetric tridiagonal n=16384, divide tree sharded across
-    # 2/4/8 B200) is measured in the same run and reported under "config2_sharded"
-    a.secondary = (a.n is None and a.matrix is None and a.gpus > 1 and a.impl == "ours")
-    if a.n is None:
-        a.n = 4096
-    if a.matrix is None:
-        a.matrix = "s1"
+    if a.n is not None or a.matrix is not None:
+        a.workload_dict = dict(matrix=a.matrix or "goe", n=a.n or 16384, ref_leaves=a.ref_leaves, golden=None, baseline="ad hoc")
+        for w in WORKLOADS.values():
+            if (w["matrix"], w["n"], w["ref_leaves"]) == (a.workload_dict["matrix"], a.workload_dict["n"], a.ref_leaves):
+                a.workload_dict = w
+        a.extras = False
+    else:
+        a.workload_dict = WORKLOADS[a.workload or HEADLINE]
+        if a.workload is not None:
+            a.extras = False
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference_arm(a)

@@ -145,6 +145,9 @@ int cuppen_local_rows(cuppen_handle h, int* row0, int* rows);
  * holds one slice of every subtree of the divide tree's top levels, not one contiguous range */
 int cuppen_local_row_map(cuppen_handle h, int* global_rows);
 int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld);
+/* the listed columns only (idx[i] = 0-based rank in ascending-lambda order): local rows x cnt, column-major, ld >= rows.
+ * What the reference's -eFILE hands to its residual loop one vector at a time (src/filehandling.c:339-345,508). */
+int cuppen_copy_eigenvector_columns(cuppen_handle h, const int* idx, int cnt, double* V, long ld);
 /* Selected-eigenvector mode (handle created with CUPPEN_FLAG_SELECT): replaces determineEigenvectorsToCompute's
  * EVToCompute list (src/filehandling.h:10-24,69) and the per-index loop of writeResults (src/filehandling.c:339-345).
  * idx[i] = 0-based rank in ascending-lambda order; takes effect at the next cuppen_solve.  Afterwards

@@ -75,6 +75,7 @@ def _declare(lib):
         "cuppen_local_rows": [H, ip, ip],
         "cuppen_local_row_map": [H, ip],
         "cuppen_copy_eigenvectors": [H, dp, ctypes.c_long],
+        "cuppen_copy_eigenvector_columns": [H, ip, ctypes.c_int, dp, ctypes.c_long],
         "cuppen_select_eigenvectors": [H, ip, ctypes.c_int],
         "cuppen_copy_selected_eigenvectors": [H, dp, ctypes.c_long],
         "cuppen_orthogonality": [H, dp, dp],
@@ -96,7 +97,7 @@ def _declare(lib):
 EXPORTED_SYMBOLS = (
     "cuppen_create", "cuppen_nccl_unique_id", "cuppen_create_nccl", "cuppen_create_callbacks", "cuppen_destroy",
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
-    "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors",
+    "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors", "cuppen_copy_eigenvector_columns",
     "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors", "cuppen_orthogonality", "cuppen_write_eigenvectors",
     "cuppen_last_error", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
@@ -319,6 +320,15 @@ class CuppenSolver:
         out = np.zeros(max(rows, 1), dtype=np.int32)
         _chk(self.lib, self.lib.cuppen_local_row_map(self._h, out.ctypes.data_as(ctypes.POINTER(ctypes.c_int))))
         return out[:rows]
+
+    def eigenvector_columns(self, indices):
+        """Local rows of the eigenvectors with the given 0-based ranks (ascending lambda): rows x len(indices)."""
+        idx = np.ascontiguousarray(indices, dtype=np.int32).ravel()
+        _, rows = self.local_rows()
+        V = np.empty((max(rows, 1), idx.size), order="F")
+        _chk(self.lib, self.lib.cuppen_copy_eigenvector_columns(self._h, idx.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), idx.size,
+                                                                _dp(V), max(rows, 1)))
+        return V[:rows]
 
     def eigenvectors(self):
         """Rows of V owned by this rank (all rows when world == 1), columns in ascending-lambda order."""

@@ -883,6 +883,15 @@ __global__ void __launch_bounds__(256) gather_cols_kernel(const double* __restri
     double* d = dst + (long)cidx * ldq;
     for (int r = blockIdx.y * 256 + threadIdx.x; r < rows; r += gridDim.y * 256) d[r] = s[r];
 }
+// the listed columns only (ascending-lambda ranks idx[]; perm == nullptr: the storage order is the rank order)
+__global__ void __launch_bounds__(256) gather_sel_cols_kernel(const double* __restrict__ src, double* __restrict__ dst, long ldq, int rows,
+                                                              const int* __restrict__ perm, const int* __restrict__ idx) {
+    const int c = blockIdx.x;
+    const int col = perm ? perm[idx[c]] : idx[c];
+    const double* s = src + (long)col * ldq;
+    double* d = dst + (long)c * ldq;
+    for (int r = blockIdx.y * 256 + threadIdx.x; r < rows; r += gridDim.y * 256) d[r] = s[r];
+}
 #endif  // CUPPEN_CUDA
 
 }  // namespace cuppen

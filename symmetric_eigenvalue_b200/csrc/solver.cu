@@ -1294,6 +1294,44 @@ int cuppen_copy_eigenvectors(cuppen_handle h, double* V, long ld) {
     CUPPEN_API_END
 }
 
+// selected columns of V (ascending-lambda ranks idx[0..cnt)), local rows only: rows x cnt, column-major
+int cuppen_copy_eigenvector_columns(cuppen_handle h, const int* idx, int cnt, double* V, long ld) {
+    CUPPEN_API_BEGIN
+    if (!h || cnt < 0 || (cnt > 0 && (!idx || !V))) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
+    Solver& s = h->s;
+    if (!s.solved || !s.want_vectors) CUPPEN_THROW(CUPPEN_ERR_STATE, "no eigenvectors (solve with CUPPEN_FLAG_VECTORS)");
+    if (ld < s.nloc_final) CUPPEN_THROW(CUPPEN_ERR_ARG, "ld too small");
+    for (int i = 0; i < cnt; ++i)
+        if (idx[i] < 0 || idx[i] >= s.n) CUPPEN_THROW(CUPPEN_ERR_ARG, "eigenvector index %d out of range", idx[i]);
+    if (cnt == 0) return CUPPEN_OK;
+#if CUPPEN_CUDA
+    CUDA_CHECK(cudaSetDevice(s.device));
+#endif
+    DevBuf<int> didx;
+    DevBuf<double> tmp;
+    didx.alloc((size_t)cnt);
+    tmp.alloc((size_t)cnt * s.ldq);
+    dev_h2d(didx.p, idx, sizeof(int) * cnt, s.stream);
+    const int* perm = s.sorted_materialised ? nullptr : s.perm.p;      // after the sorted gather the storage order IS the rank order
+#if CUPPEN_CUDA
+    {
+        dim3 grid((unsigned)cnt, (unsigned)std::max(1, std::min(64, (s.nloc_final + 255) / 256)));
+        gather_sel_cols_kernel<<<grid, 256, 0, s.stream>>>(s.Qcur, tmp.p, s.ldq, s.nloc_final, perm, didx.p);
+        CUDA_CHECK(cudaGetLastError());
+        g_launches.launches++;
+        CUDA_CHECK(cudaMemcpy2DAsync(V, sizeof(double) * ld, tmp.p, sizeof(double) * s.ldq, sizeof(double) * s.nloc_final, cnt,
+                                     cudaMemcpyDeviceToHost, s.stream));
+    }
+    dev_sync(s.stream);
+#else
+    for (int c = 0; c < cnt; ++c) {
+        const int col = perm ? perm[idx[c]] : idx[c];
+        memcpy(V + (long)c * ld, s.Qcur + (long)col * s.ldq, sizeof(double) * s.nloc_final);
+    }
+#endif
+    CUPPEN_API_END
+}
+
 int cuppen_select_eigenvectors(cuppen_handle h, const int* idx, int cnt) {
     CUPPEN_API_BEGIN
     if (!h || cnt < 0 || (cnt > 0 && !idx)) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
