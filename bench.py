@@ -584,7 +584,7 @@ def _grab(txt, key):
     return None
 
 
-def cpu_reference(w, vectors, vec_timeout=1500.0):
+def cpu_reference(w, vectors, vec_timeout=1500.0, full_vector=False):
     """The reference's own CPU path on this box's host cores (unmodified reference, oracle/_ref/cuppens_ref, MPI shim
     ranks P x OpenMP threads = all cores): the complete eigenvalue phase, and -- `vectors` -- the back-transformation
     of ONE eigenvector (-eFILE), which the reference repeats for each of the n eigenvectors (O(n^3) per vector for
@@ -623,26 +623,40 @@ def cpu_reference(w, vectors, vec_timeout=1500.0):
                                      "is timed by the --impl reference arm (one eigenvector at this size takes minutes)")
             return info
         ev = os.path.join(td, "ev.txt")
-        open(ev, "w").write("%d\n" % (n // 2))
-        per_vec, how = None, None
-        try:
-            r2 = oracle.run_reference(args + ["-e" + ev, out], P=P, threads=T, timeout=vec_timeout, stats=False)
-            per_vec = _grab(r2["stdout"], "Required time for backtransformation:")
-            how = "back-transformation of 1 eigenvector (-eFILE, rank n/2) at full size, measured once"
-        except subprocess.TimeoutExpired:
-            per_vec = None
-        if per_vec is None and n > 4096:
-            # the single eigenvector did not finish inside the budget: time it on the leading 4096 x 4096 block and scale
-            # by (n/4096)^3 (O(n^3) per vector: n rows x sum over inner stages of pn*n_ts)
-            mtx2 = os.path.join(td, "in4k.mtx")
-            oracle.write_mtx(mtx2, D[:4096], E[:4095])
-            open(ev, "w").write("2048\n")
-            r3 = oracle.run_reference(["-i", mtx2, "-e" + ev, out], P=P, threads=T, timeout=vec_timeout, stats=False)
-            b4 = _grab(r3["stdout"], "Required time for backtransformation:")
-            per_vec = None if b4 is None else b4 * (n / 4096.0) ** 3
-            how = "1 eigenvector did not finish in %.0f s at full size; timed on the leading 4096-block and scaled by (n/4096)^3" % vec_timeout
+        per_vec, how, blocks = None, None, {}
+
+        def one_vector(m):
+            """back-transformation time of ONE eigenvector (rank m/2) of the leading m x m block"""
+            if m == n:
+                a2 = args
+            else:
+                mtx2 = os.path.join(td, "in_%d.mtx" % m)
+                oracle.write_mtx(mtx2, D[:m], E[:m - 1])
+                a2 = ["-i", mtx2]
+            open(ev, "w").write("%d\n" % (m // 2))
+            rr = oracle.run_reference(a2 + ["-e" + ev, out], P=P, threads=T, timeout=vec_timeout, stats=False)
+            return _grab(rr["stdout"], "Required time for backtransformation:")
+
+        if n <= 8192 or full_vector:
+            try:
+                per_vec = one_vector(n)
+                how = "back-transformation of 1 eigenvector (-eFILE, rank n/2) at full size, measured once"
+            except subprocess.TimeoutExpired:
+                per_vec = None
+        if per_vec is None and n >= 4096:
+            # One eigenvector at n = 16384 takes the reference ~20 min (measured in the build container: 1285 s, 8 vCPU,
+            # profiles/r02_reference_scaling.txt), so the arm times it on the leading n/4 and n/2 blocks and continues the
+            # measured growth one more doubling: t(n) = t(n/2) * (t(n/2) / t(n/4)).  The same procedure predicted 979 s
+            # for the 1285 s measured there, i.e. it under-states the reference's cost.
+            blocks[n // 4] = one_vector(n // 4)
+            blocks[n // 2] = one_vector(n // 2)
+            if blocks[n // 4] and blocks[n // 2]:
+                per_vec = blocks[n // 2] * (blocks[n // 2] / blocks[n // 4])
+                how = ("back-transformation of 1 eigenvector (-eFILE) measured on the leading n/4 and n/2 blocks (%.2f s, %.2f s), "
+                       "continued one doubling at the measured growth factor %.2f" % (blocks[n // 4], blocks[n // 2], blocks[n // 2] / blocks[n // 4]))
     value = None if (t_eval is None or per_vec is None) else t_eval + per_vec * n
     info.update(value=value, backtransform_s_per_eigenvector=per_vec, sampled_eigenvectors=1, extrapolated=True,
+                backtransform_s_one_eigenvector_of_leading_blocks={str(k): v for k, v in blocks.items()},
                 sample=who + ": full eigenvalue phase (measured) + %s, extrapolated x n=%d" % (how, n))
     return info
 
@@ -652,7 +666,7 @@ def run_reference_arm(a):
     if rank != 0:
         return
     w = a.workload_dict
-    info = cpu_reference(w, vectors=True, vec_timeout=a.ref_vec_timeout)      # each part timed once per process
+    info = cpu_reference(w, vectors=True, vec_timeout=a.ref_vec_timeout, full_vector=a.ref_full_vector)      # each part timed once per process
     v = info["value"]
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "s", "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": None if v is None else v * 1e3, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
@@ -678,7 +692,8 @@ def main():
     ap.add_argument("--no-extras", dest="extras", action="store_false", help="headline workload only")
     ap.add_argument("--big", action="store_true", help="also run n=32768 / n=65536 as extra keys below 8 GPUs")
     ap.add_argument("--select", type=int, default=16, help="also time the selected-eigenvector mode on K vectors (0: skip)")
-    ap.add_argument("--ref-vec-timeout", type=float, default=1500.0, help="reference arm: seconds allowed for the one full-size eigenvector")
+    ap.add_argument("--ref-vec-timeout", type=float, default=1500.0, help="reference arm: seconds allowed for one eigenvector run")
+    ap.add_argument("--ref-full-vector", action="store_true", help="reference arm: time the one eigenvector at full size even above n=8192 (~20 min at 16384)")
     a = ap.parse_args()
     if a.n is not None or a.matrix is not None:
         a.workload_dict = dict(matrix=a.matrix or "goe", n=a.n or 16384, ref_leaves=a.ref_leaves, golden=None, baseline="ad hoc")

@@ -95,6 +95,8 @@ typedef struct {
     double secular_root_iters; /* reserved */
     long   kernel_launches;
     double apply_s;          /* CUPPEN_FLAG_SELECT: device time of the back-application of the selected columns */
+    double comm_s;           /* several GPUs, peer-memory back end: device time of the row redistribution and the barriers */
+    long   comm_mode;        /* 0 one GPU, 1 NCCL collectives / callbacks between the kernels, 2 peer memory (NVLink loads/stores in our kernels) */
 } cuppen_timers;
 
 /* Communication callbacks for world > 1 when NCCL is not used (tests drive these with gloo).

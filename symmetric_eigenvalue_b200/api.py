@@ -30,7 +30,8 @@ class _Timers(ctypes.Structure):
     _fields_ = [(k, ctypes.c_double) for k in (
         "total_s", "root_finding_s", "ev_extract_s", "backtransform_s", "backtransform_ev_s", "gemm_s",
         "gemm_flop", "leaf_s", "deflation_s", "pack_s", "residual_s", "device_s", "pack_bytes", "ugen_bytes",
-        "secular_root_iters")] + [("kernel_launches", ctypes.c_long), ("apply_s", ctypes.c_double)]
+        "secular_root_iters")] + [("kernel_launches", ctypes.c_long), ("apply_s", ctypes.c_double), ("comm_s", ctypes.c_double),
+                                       ("comm_mode", ctypes.c_long)]
 
 
 _BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,

@@ -117,7 +117,7 @@ int main(int argc, char** argv) {
         case 'c': checkOrth = 1; break;
         case 'g':
             gpus = atoi(optarg);
-            if (gpus < 1 || (gpus & (gpus - 1))) { fprintf(stderr, "Invalid argument for option -g. See help.\n"); return 1; }
+            if (gpus < 1 || gpus > 16) { fprintf(stderr, "Invalid argument for option -g. See help.\n"); return 1; }
             break;
         case '?':
             if (isprint(optopt)) fprintf(stderr, "Unknown option `-%c'.\n", optopt);

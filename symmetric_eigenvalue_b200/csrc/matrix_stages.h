@@ -16,6 +16,7 @@
 #include "merge_stages.h"
 #include "secular_core.h"
 #include "gemm_dmma.h"
+#include "p2p.h"
 #if CUPPEN_CUDA
 #include <cooperative_groups.h>
 #endif
@@ -292,7 +293,16 @@ struct SecularStagedEval {
     }
 };
 
-__global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int kcap, int part, int nparts) {
+// several GPUs, peer-memory back end: the root is stored into every peer's (origin, tau) arrays as well (H.G > 0)
+__device__ __forceinline__ void secular_store(const LevelCtx& c, const SymHeap& H, long g, const SecularRoot& r) {
+    c.org[g] = r.origin; c.tau[g] = r.tau;
+    for (int p = 0; p < H.G; ++p) {
+        if (p == H.me) continue;
+        H.at(p, c.org)[g] = r.origin; H.at(p, c.tau)[g] = r.tau;
+    }
+}
+
+__global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int kcap, int part, int nparts, SymHeap H) {
     extern __shared__ double sec_smem[];
     const int id = blockIdx.y;
     const MergeDesc& D = c.desc[id];
@@ -310,13 +320,13 @@ __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int
         __syncthreads();
         if (i >= i1) return;
         SecularRoot r = secular_solve(L, k, sec_smem, sec_smem + kcap, fabs(D.rho), D.sumw, i);
-        if (L.lane() == 0) { c.org[D.off + i] = r.origin; c.tau[D.off + i] = r.tau; }
+        if (L.lane() == 0) secular_store(c, H, D.off + i, r);
         return;
     }
     const SecularStagedEval ev{dl, wl, k, kcap, sec_smem};
     if (i < i1) {
         SecularRoot r = secular_solve_ev(ev, k, dl, wl, fabs(D.rho), D.sumw, i);
-        if (L.lane() == 0) { c.org[D.off + i] = r.origin; c.tau[D.off + i] = r.tau; }
+        if (L.lane() == 0) secular_store(c, H, D.off + i, r);
     }
     ev.drain();
 }

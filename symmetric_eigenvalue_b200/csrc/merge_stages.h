@@ -17,6 +17,7 @@
 
 #include <math.h>
 #include "platform.h"
+#include "p2p.h"
 
 namespace cuppen {
 
@@ -468,13 +469,22 @@ struct ExtractRows {
     long ldq;
     double* frow;
     double* lrow;
+    SymHeap H;             // peer-memory back end: the owner of a boundary row stores it into every rank's copy
     CUPPEN_HD void operator()(long g) const {
         int id = c.node_of[g];
         if (id < 0) return;
         const MergeDesc& D = c.desc[id];
         if (D.lr1 <= D.lr0) return;
-        if (D.own_first) frow[g] = Q[(long)D.lr0 + g * ldq];
-        if (D.own_last) lrow[g] = Q[(long)(D.lr1 - 1) + g * ldq];
+        if (D.own_first) {
+            const double v = Q[(long)D.lr0 + g * ldq];
+            frow[g] = v;
+            for (int p = 0; p < H.G; ++p) if (p != H.me) H.at(p, frow)[g] = v;
+        }
+        if (D.own_last) {
+            const double v = Q[(long)(D.lr1 - 1) + g * ldq];
+            lrow[g] = v;
+            for (int p = 0; p < H.G; ++p) if (p != H.me) H.at(p, lrow)[g] = v;
+        }
     }
 };
 

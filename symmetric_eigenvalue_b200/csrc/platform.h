@@ -123,15 +123,21 @@ template <class T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    bool owned = true;       // false: a view into memory owned by somebody else (the symmetric heap of p2p.h)
     DevBuf() {}
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    ~DevBuf() { dev_free(p); }
+    ~DevBuf() { if (owned) dev_free(p); }
     void alloc(size_t count) {
-        dev_free(p);
+        if (owned) dev_free(p);
         p = nullptr;
         n = count;
+        owned = true;
         p = static_cast<T*>(dev_alloc_bytes(count * sizeof(T)));
+    }
+    void attach(T* ptr, size_t count) {
+        if (owned) dev_free(p);
+        p = ptr; n = count; owned = false;
     }
     size_t bytes() const { return n * sizeof(T); }
 };

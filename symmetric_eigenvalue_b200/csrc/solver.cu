@@ -19,6 +19,7 @@
 #include "gemm_tma.h"
 #include "host_twins.h"
 #include "comm.h"
+#include "p2p.h"
 
 namespace cuppen {
 
@@ -31,9 +32,9 @@ static double wall_now() {
 
 // ---- per-category device timers (CUDA events on the solver's stream) ---------------------------
 // fail buffer of a solve (device, read back with the results): [0] leaf QL did not converge (1 + row),
-// [1] GEMM tile list overflow, [4..11] watchdog record of the TMA GEMM pipeline
-enum { FAIL_LEAF = 0, FAIL_TILES = 1, FAIL_TMA = 4, FAIL_INTS = 16 };
-enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_APPLY, T_NCAT };
+// [1] GEMM tile list overflow, [2] peer barrier timed out (1 + peer rank), [4..11] watchdog record of the TMA GEMM pipeline
+enum { FAIL_LEAF = 0, FAIL_TILES = 1, FAIL_COMM = 2, FAIL_TMA = 4, FAIL_INTS = 16 };
+enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_APPLY, T_COMM, T_NCAT };
 struct PhaseTimers {
     double acc[T_NCAT] = {0};
     bool capturing = false;     // stream capture in progress: record events as external graph nodes
@@ -85,18 +86,26 @@ struct Solver {
     Stream stream = 0;
 
     // ---- row ownership ---------------------------------------------------------------------------
-    // G ranks; subtree s = s-th node at depth log2(G) of the divide tree, global rows
-    // [sub_off[s], sub_off[s]+sub_n[s]).
-    //  layout L (local phase): rank g holds all rows of subtree g, local row = r - R0.
-    //  layout C (cooperative phase, the top log2(G) levels): rank g holds slice g of EVERY subtree,
+    // G ranks (any count), S subtrees = the nodes at depth ceil(log2 G) of the divide tree, global rows
+    // [sub_off[s], sub_off[s]+sub_n[s]); rank g owns the contiguous subtrees [first_sub(g), first_sub(g+1)).
+    //  layout L (local phase): rank g holds all rows of its subtrees, local row = r - R0.
+    //  layout C (cooperative phase, the levels above the subtrees): rank g holds slice g of EVERY subtree,
     //    rows [sub_off[s]+slice_lo(s,g), sub_off[s]+slice_lo(s,g+1)) at local rows crow0[s]... ;
     //    every cooperative merge is then split evenly over all ranks whatever its halves deflate to.
-    int G = 1, glog = 0;
+    int G = 1, glog = 0, S = 1;
+    int first_sub(int r) const { return (int)((long)S * r / G); }
+    int owner_of_sub(int sub) const { int r = 0; while (r + 1 < G && first_sub(r + 1) <= sub) ++r; return r; }
+    int rank_row0(int r) const { return r >= G ? n : sub_off[first_sub(r)]; }
     std::vector<int> sub_off, sub_n, sub_root;
     int R0 = 0, R1 = 0, nlocL = 0, nlocC = 0;
     std::vector<int> crow0;
     int nloc_final = 0;           // local rows of the final V
     int slice_lo(int s, int j) const { return j >= G ? sub_n[s] : (int)(((long)j * sub_n[s] / G) & ~1L); }
+    long ldq_of(int r) const {    // leading dimension of rank r's Q buffers (every rank can work out every rank's layout)
+        long c = 0;
+        for (int s = 0; s < S; ++s) c += slice_lo(s, r + 1) - slice_lo(s, r);
+        return round_up(std::max<long>(rank_row0(r + 1) - rank_row0(r), c), 16);
+    }
 
     std::vector<double> hD, hE;   // matrix as uploaded (host): the caller's T times `scale`
     // Matrices of extreme norm (max|T_ij| outside [1e-100, 1e100]) are scaled by a power of two before the divide
@@ -125,6 +134,33 @@ struct Solver {
     DevBuf<GemmProblem> probs;
     DevBuf<GemmTile> tiles;
     double* Qcur = nullptr;       // block-diagonal eigenvector matrix: children before a level, parents after it, V at the end
+    double* Awork = nullptr;      // the other of the two n x n buffers: packed live columns of the level in flight.  Qcur / Awork
+                                  // start every solve as Qa / Apack and trade places at the peer-memory row redistribution
+    double* Qfinal = nullptr;     // where a (replayed) solve leaves V and its pack buffer
+    double* Afinal = nullptr;
+    // ---- peer-memory back end (p2p.h): symmetric heap + IPC mappings of the peers' heaps and Q buffers -------------
+    struct P2PState {
+        bool on = false;
+        SymHeap H;
+        char* heap = nullptr;
+        size_t heap_bytes = 0, used = 0;
+        const double* peerQ[P2P_MAX] = {nullptr};
+        void* opened[2 * P2P_MAX] = {nullptr};
+        int nopened = 0;
+        unsigned* flags = nullptr;     // heap
+        unsigned* epoch = nullptr;     // heap (local use)
+        double *halo_lo = nullptr, *halo_hi = nullptr, *res_part = nullptr;
+        template <class T>
+        T* carve(size_t count) {
+            used = (used + 255) & ~(size_t)255;
+            T* p = (T*)(heap + used);
+            used += count * sizeof(T);
+            if (used > heap_bytes) CUPPEN_THROW(CUPPEN_ERR_STATE, "symmetric heap overflow (%zu of %zu bytes)", used, heap_bytes);
+            return p;
+        }
+    } p2p;
+    void setup_p2p();
+    void p2p_barrier();
     bool sorted_materialised = false;    // Qcur (= Apack's storage) holds the columns in ascending-lambda order
     void materialise_sorted();
     // one-GPU solves are captured into a CUDA graph on the second call and replayed afterwards
@@ -163,6 +199,8 @@ struct Solver {
         timers.deflation_s = pt.acc[T_DEFL];
         timers.pack_s = pt.acc[T_PACK];
         timers.residual_s = pt.acc[T_RESID];
+        timers.comm_s = pt.acc[T_COMM];
+        timers.comm_mode = G <= 1 ? 0 : (p2p.on ? 2 : 1);
         if (select_mode && !h_sel.empty()) timers.backtransform_s = timers.apply_s;
     }
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
@@ -200,12 +238,13 @@ struct Solver {
     void run_leaves();
     void run_level(int li);
     void enter_cooperative();
+    void enter_cooperative_p2p();
     void finish();
     LevelCtx level_ctx(int li);
     MatCtx mat_ctx();
     int subtree_at(int off) const {
-        for (int s = 0; s < G; ++s) if (sub_off[s] == off) return s;
-        if (off == n) return G;
+        for (int s = 0; s < S; ++s) if (sub_off[s] == off) return s;
+        if (off == n) return S;
         CUPPEN_THROW(CUPPEN_ERR_STATE, "offset %d is not a subtree boundary", off);
     }
 };
@@ -215,33 +254,35 @@ void Solver::init_layout() {
     G = comm.world;
     glog = 0;
     while ((1 << glog) < G) ++glog;
-    if ((1 << glog) != G) CUPPEN_THROW(CUPPEN_ERR_ARG, "world size %d is not a power of two", G);
     std::vector<std::pair<int, int>> roots;      // (offset, node id) of the nodes at depth log2 G
     for (size_t id = 0; id < plan.nodes.size(); ++id)
         if (plan.nodes[id].depth == glog) roots.push_back({plan.nodes[id].off, (int)id});
     std::sort(roots.begin(), roots.end());
     long covered = 0;
     for (auto& r : roots) covered += plan.nodes[r.second].n;
-    if ((int)roots.size() != G || covered != n)
-        CUPPEN_THROW(CUPPEN_ERR_ARG, "the divide tree of n=%d (reference leaves %d) has no level with %d subtrees", n, P, G);
-    sub_off.resize(G); sub_n.resize(G); sub_root.resize(G);
-    for (int s = 0; s < G; ++s) { sub_off[s] = roots[s].first; sub_root[s] = roots[s].second; sub_n[s] = plan.nodes[roots[s].second].n; }
+    S = (int)roots.size();
+    if (S < G || covered != n || S > P2P_MAX * 2)
+        CUPPEN_THROW(CUPPEN_ERR_ARG, "n=%d is too small to distribute over %d GPUs: the divide tree (reference leaves %d) has %d "
+                     "subtrees at depth %d", n, G, P, S, glog);
+    sub_off.resize(S); sub_n.resize(S); sub_root.resize(S);
+    for (int s = 0; s < S; ++s) { sub_off[s] = roots[s].first; sub_root[s] = roots[s].second; sub_n[s] = plan.nodes[roots[s].second].n; }
     parent_of.assign(plan.nodes.size(), -1);
     for (size_t id = 0; id < plan.nodes.size(); ++id)
         if (plan.nodes[id].left >= 0) { parent_of[plan.nodes[id].left] = (int)id; parent_of[plan.nodes[id].right] = (int)id; }
-    R0 = sub_off[comm.rank];
-    R1 = R0 + sub_n[comm.rank];
+    R0 = rank_row0(comm.rank);
+    R1 = rank_row0(comm.rank + 1);
     nlocL = R1 - R0;
-    crow0.assign(G + 1, 0);
-    for (int s = 0; s < G; ++s) {
+    crow0.assign(S + 1, 0);
+    for (int s = 0; s < S; ++s) {
         const int len = slice_lo(s, comm.rank + 1) - slice_lo(s, comm.rank);
         if (G > 1 && want_vectors && len <= 0)
             CUPPEN_THROW(CUPPEN_ERR_ARG, "n=%d is too small to distribute over %d GPUs", n, G);
         crow0[s + 1] = crow0[s] + len;
     }
-    nlocC = crow0[G];
+    nlocC = crow0[S];
     nloc_final = (G > 1) ? nlocC : nlocL;
     ldq = round_up(std::max(nlocL, nlocC), 16);
+    if (ldq != ldq_of(comm.rank)) CUPPEN_THROW(CUPPEN_ERR_STATE, "inconsistent leading dimension");
 }
 
 // Function attributes are per device: every handle opts its device in to the >48 KB dynamic shared memory of the
@@ -261,16 +302,40 @@ static void set_kernel_attributes() {
 void Solver::allocate() {
     const size_t N = (size_t)n;
     set_kernel_attributes();
+    // several GPUs over NCCL: the exchanged vectors live in a symmetric heap that the peers map (p2p.h); env
+    // CUPPEN_P2P=0 keeps them private and exchanges them with NCCL collectives instead
+    bool want_p2p = false;
+#if CUPPEN_CUDA
+    {
+        const char* pe = getenv("CUPPEN_P2P");
+        want_p2p = G > 1 && G <= P2P_MAX && S <= P2P_MAX && comm.nccl != nullptr && !(pe && !strcmp(pe, "0"));
+    }
+    if (want_p2p) {
+        p2p.heap_bytes = (size_t)(5 + 2 * S + G) * (N + 64) * sizeof(double) + 64 * 256;
+        CUDA_CHECK(cudaMalloc((void**)&p2p.heap, p2p.heap_bytes));
+        CUDA_CHECK(cudaMemsetAsync(p2p.heap, 0, p2p.heap_bytes, stream));
+        lam.attach(p2p.carve<double>(N + 64), N + 64);
+        frow.attach(p2p.carve<double>(N + 64), N + 64);
+        lrow.attach(p2p.carve<double>(N + 64), N + 64);
+        tau.attach(p2p.carve<double>(N + 64), N + 64);
+        org.attach(p2p.carve<int>(N + 64), N + 64);
+        p2p.halo_lo = p2p.carve<double>((size_t)S * N);
+        p2p.halo_hi = p2p.carve<double>((size_t)S * N);
+        p2p.res_part = p2p.carve<double>((size_t)G * N);
+        p2p.flags = p2p.carve<unsigned>(64);
+        p2p.epoch = p2p.carve<unsigned>(64);
+    }
+#endif
     for (DevBuf<double>* b : {&dDm, &dE, &dOD, &dOE, &lam, &lam_sorted, &frow, &lrow, &frow2, &lrow2, &fpack, &lpack, &res2})
-        b->alloc(N + 64);
+        if (b->p == nullptr) b->alloc(N + 64);
     perm.alloc(N + 64);
     // scratch vectors of a level: shared by all levels, or one slice per level in selected-eigenvector mode
     lvl_stride = N + 64;
     lvl_cap = select_mode ? (int)plan.by_height.size() + 1 : 1;
     for (DevBuf<double>* b : {&d, &z, &dn, &zn, &gc, &gs, &dl, &wl, &zl, &tau, &zhat, &nrm})
-        b->alloc(lvl_stride * lvl_cap);
+        if (b->p == nullptr) b->alloc(lvl_stride * lvl_cap);
     for (DevBuf<int>* b : {&G_, &lsort, &head, &sup, &prev, &tpos, &bpos, &lidx, &org, &toplist, &botlist})
-        b->alloc(lvl_stride * lvl_cap);
+        if (b->p == nullptr) b->alloc(lvl_stride * lvl_cap);
     if (select_mode) {
         Qleaf.alloc(N * LEAF_MAX + 64);
         leaf_off_dev.alloc(N + 64);
@@ -279,8 +344,11 @@ void Solver::allocate() {
         sel_dorg.alloc(N + 64);
     }
     fail.alloc(FAIL_INTS);
-    halo.alloc(2 * N * (size_t)std::max(1, G) + 64);
-    halo_all.alloc(2 * N * (size_t)G * (size_t)G + 64);
+    if (want_p2p) { halo.alloc(64); halo_all.alloc(64); }          // the halo rows go straight into the peers' heaps
+    else {
+        halo.alloc(2 * N * (size_t)std::max(1, S) + 64);
+        halo_all.alloc(2 * N * (size_t)S * (size_t)G + 64);
+    }
     leaves.alloc(std::max<size_t>(1, plan.leaves.size()));
     if (want_vectors) {
         const size_t qelems = (size_t)ldq * (N + K_PAD + 2) + 4096;
@@ -317,13 +385,85 @@ void Solver::allocate() {
     pin_fail = (int*)malloc(sizeof(int) * FAIL_INTS);
     use_graph = false;
 #endif
-    if (G > 1) use_graph = false;
     dev_sync(stream);
+    if (want_p2p) setup_p2p();
+    if (G > 1 && !p2p.on) use_graph = false;         // NCCL collectives / callbacks between the kernels: launched eagerly
+}
+
+// Exchange the CUDA IPC handles of the symmetric heap and of the Q buffer (NCCL all-gather: the bootstrap) and map the
+// peers' copies.  All ranks agree on the outcome (a rank that cannot map a peer makes everybody fall back to the
+// collective back end).
+void Solver::setup_p2p() {
+#if CUPPEN_CUDA
+    struct Handles { cudaIpcMemHandle_t heap, q; int has_q; int pad[15]; };
+    static_assert(sizeof(Handles) == 2 * sizeof(cudaIpcMemHandle_t) + 64, "handle record");
+    Handles mine;
+    memset(&mine, 0, sizeof mine);
+    int ok = 1;
+    if (cudaIpcGetMemHandle(&mine.heap, p2p.heap) != cudaSuccess) ok = 0;
+    mine.has_q = want_vectors ? 1 : 0;
+    if (ok && want_vectors && cudaIpcGetMemHandle(&mine.q, Qa.p) != cudaSuccess) ok = 0;
+    cudaGetLastError();
+    DevBuf<unsigned char> sbuf, rbuf;
+    sbuf.alloc(sizeof mine); rbuf.alloc(sizeof mine * G);
+    dev_h2d(sbuf.p, &mine, sizeof mine, stream);
+    comm.allgather(sbuf.p, rbuf.p, sizeof mine, stream);
+    std::vector<Handles> all(G);
+    dev_d2h(all.data(), rbuf.p, sizeof mine * G, stream);
+    dev_sync(stream);
+    p2p.H.me = comm.rank; p2p.H.G = G;
+    for (int r = 0; r < P2P_MAX; ++r) p2p.H.base[r] = nullptr;
+    p2p.H.base[comm.rank] = p2p.heap;
+    p2p.peerQ[comm.rank] = Qa.p;
+    for (int r = 0; r < G && ok; ++r) {
+        if (r == comm.rank) continue;
+        void* ptr = nullptr;
+        if (cudaIpcOpenMemHandle(&ptr, all[r].heap, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+        p2p.opened[p2p.nopened++] = ptr;
+        p2p.H.base[r] = (char*)ptr;
+        if (want_vectors) {
+            if (cudaIpcOpenMemHandle(&ptr, all[r].q, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; break; }
+            p2p.opened[p2p.nopened++] = ptr;
+            p2p.peerQ[r] = (const double*)ptr;
+        }
+    }
+    cudaGetLastError();
+    // agreement: sum of the failure counts over the ranks
+    DevBuf<double> agree;
+    agree.alloc(8);
+    double bad = ok ? 0.0 : 1.0;
+    dev_h2d(agree.p, &bad, sizeof bad, stream);
+    comm.allreduce_sum(agree.p, 1, stream);
+    dev_d2h(&bad, agree.p, sizeof bad, stream);
+    dev_sync(stream);
+    p2p.on = (bad == 0.0);
+    if (!p2p.on) {
+        const char* strict = getenv("CUPPEN_P2P");
+        if (strict && !strcmp(strict, "require"))
+            CUPPEN_THROW(CUPPEN_ERR_COMM, "peer memory (CUDA IPC) is not available between the %d GPUs", G);
+        p2p.H.G = 0;
+        // the collective back end needs its staging buffers after all
+        halo.alloc(2 * (size_t)n * (size_t)S + 64);
+        halo_all.alloc(2 * (size_t)n * (size_t)S * (size_t)G + 64);
+        dev_zero(halo.p, halo.bytes(), stream);
+        dev_sync(stream);
+    }
+#endif
+}
+
+void Solver::p2p_barrier() {
+#if CUPPEN_CUDA
+    p2p_barrier_kernel<<<1, 32, 0, stream>>>(p2p.H, p2p.flags, p2p.epoch, fail.p + FAIL_COMM);
+    CUDA_CHECK(cudaGetLastError());
+    g_launches.launches++;
+#endif
 }
 
 Solver::~Solver() {
     drop_graph();
 #if CUPPEN_CUDA
+    for (int i = 0; i < p2p.nopened; ++i) cudaIpcCloseMemHandle(p2p.opened[i]);
+    if (p2p.heap) cudaFree(p2p.heap);
     if (pin_lam) cudaFreeHost(pin_lam);
     if (pin_res) cudaFreeHost(pin_res);
     if (pin_fail) cudaFreeHost(pin_fail);
@@ -403,7 +543,7 @@ LevelCtx Solver::level_ctx(int li) {
 
 MatCtx Solver::mat_ctx() {
     MatCtx M;
-    M.n = n; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qcur; M.Apack = Apack.p; M.B = B.p; M.ldb = ldb;       // in place
+    M.n = n; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qcur; M.Apack = Awork; M.B = B.p; M.ldb = ldb;       // in place
     return M;
 }
 
@@ -563,8 +703,43 @@ void Solver::prepare_levels() {
 }
 
 // ---- transition to the cooperative phase: replicate the subtree vectors, redistribute the rows ------
+// Peer-memory version: push the subtree vectors, then PULL the rows of the slice layout straight out of the peers' Q
+// blocks into the other n x n buffer (no staging copies, no collective); the two buffers trade places.
+void Solver::enter_cooperative_p2p() {
+#if CUPPEN_CUDA
+    pt.begin(T_COMM, stream);
+    p2p_barrier();                                   // nobody is still reading the heap vectors of the previous solve
+    launch_items(stream, R1 - R0, PushSubtreeVectors{p2p.H, lam.p, frow.p, lrow.p, R0});
+    p2p_barrier();                                   // every subtree is finished: vectors replicated, Q blocks final
+    if (want_vectors) {
+        PullCtx pc;
+        memset(&pc, 0, sizeof pc);
+        pc.dst = Awork; pc.ldq = ldq; pc.S = S;
+        int maxlen = 1;
+        for (int s = 0; s < S; ++s) {
+            const int o = owner_of_sub(s);           // layout L of the owner: local row = global row - its first row
+            pc.src[s] = p2p.peerQ[o];
+            pc.src_ld[s] = ldq_of(o);
+            pc.sub_off[s] = sub_off[s];
+            pc.slo[s] = sub_off[s] - rank_row0(o) + slice_lo(s, comm.rank);
+            pc.crow0[s] = crow0[s];
+            maxlen = std::max(maxlen, crow0[s + 1] - crow0[s]);
+        }
+        pc.sub_off[S] = n; pc.crow0[S] = crow0[S];
+        dim3 grid((unsigned)n, (unsigned)std::max(1, std::min(16, (maxlen + 255) / 256)));
+        p2p_pull_rows_kernel<<<grid, 256, 0, stream>>>(pc);
+        CUDA_CHECK(cudaGetLastError());
+        g_launches.launches++;
+        p2p_barrier();                               // every rank has taken its slices: the source buffers may be reused
+        std::swap(Qcur, Awork);
+    }
+    pt.end(stream);
+#endif
+}
+
 void Solver::enter_cooperative() {
     if (G <= 1) return;
+    if (p2p.on) { enter_cooperative_p2p(); return; }
     // every rank has lam / first row / last row of its own subtree: zero the rest and sum
     for (DevBuf<double>* b : {&lam, &frow, &lrow}) {
         if (R0 > 0) dev_zero(b->p, sizeof(double) * R0, stream);
@@ -572,62 +747,55 @@ void Solver::enter_cooperative() {
         comm.allreduce_sum(b->p, n, stream);
     }
     if (!want_vectors) return;
-    // rows: my subtree block (nlocL x nlocL at columns [R0,R1)) is cut into G slices; slice j goes to rank j.
-    // staging inside Apack: first the send blocks (one contiguous len x nlocL block per destination), then the
-    // receive blocks; Apack holds ldq*n >= 2 (n/G)^2 doubles for G >= 2
+    // rows: each of my subtree blocks is cut into G slices; slice j goes to rank j.  Staging inside Apack: first the
+    // send blocks (per destination: one contiguous len x sub_n[s] block per subtree of mine), then the receive blocks
+    // (per source rank: one block per subtree it owns)
     const int me = comm.rank;
+    auto copy_block = [&](double* dst, long dpitch, const double* src, long spitch, int rows, int cols) {
+        if (rows <= 0 || cols <= 0) return;
+#if CUPPEN_CUDA
+        CUDA_CHECK(cudaMemcpy2DAsync(dst, sizeof(double) * dpitch, src, sizeof(double) * spitch, sizeof(double) * rows, cols,
+                                     cudaMemcpyDeviceToDevice, stream));
+#else
+        for (int col = 0; col < cols; ++col) memcpy(dst + (size_t)col * dpitch, src + (size_t)col * spitch, sizeof(double) * rows);
+#endif
+    };
     std::vector<const void*> sp(G, nullptr);
     std::vector<void*> rp(G, nullptr);
     std::vector<size_t> sb(G, 0), rb(G, 0);
     size_t sofs = 0, rofs = 0;
-    std::vector<size_t> rofs_of(G, 0);
+    std::vector<size_t> rofs_of(S, 0);
     for (int j = 0; j < G; ++j) {
-        const int lo = slice_lo(me, j), len = slice_lo(me, j + 1) - lo;
-        sp[j] = Apack.p + sofs; sb[j] = sizeof(double) * (size_t)len * nlocL;
-        if (j != me && len > 0) {
-#if CUPPEN_CUDA
-            CUDA_CHECK(cudaMemcpy2DAsync(Apack.p + sofs, sizeof(double) * len, Qcur + (long)R0 * ldq + lo, sizeof(double) * ldq,
-                                         sizeof(double) * len, nlocL, cudaMemcpyDeviceToDevice, stream));
-#else
-            for (int col = 0; col < nlocL; ++col)
-                memcpy(Apack.p + sofs + (size_t)col * len, Qcur + (long)(R0 + col) * ldq + lo, sizeof(double) * len);
-#endif
+        sp[j] = Apack.p + sofs;
+        if (j == me) continue;
+        for (int t = first_sub(me); t < first_sub(me + 1); ++t) {
+            const int lo = slice_lo(t, j), len = slice_lo(t, j + 1) - lo;
+            copy_block(Apack.p + sofs, len, Qcur + (long)sub_off[t] * ldq + (sub_off[t] - R0) + lo, ldq, len, sub_n[t]);
+            sofs += (size_t)len * sub_n[t];
         }
-        sofs += (size_t)len * nlocL;
+        sb[j] = sizeof(double) * (size_t)((Apack.p + sofs) - (const double*)sp[j]);
     }
     double* const rstage = Apack.p + round_up((long)sofs, 32);
-    for (int s = 0; s < G; ++s) {
-        const int len = crow0[s + 1] - crow0[s];
-        rofs_of[s] = rofs;
-        rp[s] = rstage + rofs; rb[s] = sizeof(double) * (size_t)len * sub_n[s];
-        rofs += (size_t)len * sub_n[s];
+    for (int o = 0; o < G; ++o) {
+        rp[o] = rstage + rofs;
+        for (int t = first_sub(o); t < first_sub(o + 1); ++t) {
+            const int len = crow0[t + 1] - crow0[t];
+            rofs_of[t] = rofs;
+            rofs += (size_t)len * sub_n[t];
+        }
+        rb[o] = sizeof(double) * (size_t)((rstage + rofs) - (double*)rp[o]);
     }
     if ((size_t)round_up((long)sofs, 32) + rofs > Apack.n)
         CUPPEN_THROW(CUPPEN_ERR_STATE, "row redistribution needs %zu doubles of staging, Apack has %zu", (size_t)round_up((long)sofs, 32) + rofs, Apack.n);
-    // my own slice moves inside the buffer: stage it like a received block
-    {
-        const int lo = slice_lo(me, me), len = slice_lo(me, me + 1) - lo;
-#if CUPPEN_CUDA
-        CUDA_CHECK(cudaMemcpy2DAsync(rstage + rofs_of[me], sizeof(double) * len, Qcur + (long)R0 * ldq + lo, sizeof(double) * ldq,
-                                     sizeof(double) * len, nlocL, cudaMemcpyDeviceToDevice, stream));
-#else
-        for (int col = 0; col < nlocL; ++col)
-            memcpy(rstage + rofs_of[me] + (size_t)col * len, Qcur + (long)(R0 + col) * ldq + lo, sizeof(double) * len);
-#endif
+    // my own slices move inside the buffer: stage them like received blocks
+    for (int t = first_sub(me); t < first_sub(me + 1); ++t) {
+        const int lo = slice_lo(t, me), len = slice_lo(t, me + 1) - lo;
+        copy_block(rstage + rofs_of[t], len, Qcur + (long)sub_off[t] * ldq + (sub_off[t] - R0) + lo, ldq, len, sub_n[t]);
     }
     comm.alltoallv(sp, sb, rp, rb, stream);
-    // unpack into Qcur in layout C: slice of subtree s at local rows crow0[s], columns of subtree s
-    for (int s = 0; s < G; ++s) {
-        const int len = crow0[s + 1] - crow0[s];
-        if (len <= 0) continue;
-#if CUPPEN_CUDA
-        CUDA_CHECK(cudaMemcpy2DAsync(Qcur + (long)sub_off[s] * ldq + crow0[s], sizeof(double) * ldq, rstage + rofs_of[s],
-                                     sizeof(double) * len, sizeof(double) * len, sub_n[s], cudaMemcpyDeviceToDevice, stream));
-#else
-        for (int col = 0; col < sub_n[s]; ++col)
-            memcpy(Qcur + (long)(sub_off[s] + col) * ldq + crow0[s], rstage + rofs_of[s] + (size_t)col * len, sizeof(double) * len);
-#endif
-    }
+    // unpack into Qcur in layout C: slice of subtree t at local rows crow0[t], columns of subtree t
+    for (int t = 0; t < S; ++t)
+        copy_block(Qcur + (long)sub_off[t] * ldq + crow0[t], ldq, rstage + rofs_of[t], crow0[t + 1] - crow0[t], crow0[t + 1] - crow0[t], sub_n[t]);
 }
 
 void Solver::run_level(int li) {
@@ -685,7 +853,7 @@ void Solver::run_level(int li) {
         // (tau, origin) arrays are zeroed first so that a sum over ranks assembles them.
         pt.begin(T_ROOT, stream);
         const int part = coop ? comm.rank : 0, nparts = coop ? G : 1;
-        if (coop) {
+        if (coop && !p2p.on) {
             dev_zero(tau.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), stream);
             dev_zero(org.p + lo_idx, sizeof(int) * (hi_idx - lo_idx), stream);
         }
@@ -695,7 +863,7 @@ void Solver::run_level(int li) {
             int kcap = std::min((int)round_up(L.maxm, 32), (int)SEC_SMEM_K);
             size_t smem = (size_t)2 * kcap * sizeof(double);
             dim3 grid((unsigned)((per + SEC_WARPS - 1) / SEC_WARPS), (unsigned)nd_cnt);
-            secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, nparts);
+            secular_kernel<<<grid, SEC_WARPS * 32, smem, stream>>>(c, kcap, part, nparts, (coop && p2p.on) ? p2p.H : SymHeap());
             CUDA_CHECK(cudaGetLastError());
         }
 #else
@@ -703,7 +871,11 @@ void Solver::run_level(int li) {
 #endif
         g_launches.launches++;
         pt.end(stream);
-        if (coop) {
+        if (coop && p2p.on) {
+            pt.begin(T_COMM, stream);
+            p2p_barrier();                           // every rank's root slice has landed in every heap (secular_kernel pushes)
+            pt.end(stream);
+        } else if (coop) {
             comm.allreduce_sum(tau.p + lo_idx, hi_idx - lo_idx, stream);
             comm.allreduce_sum_i32(org.p + lo_idx, hi_idx - lo_idx, stream);
         }
@@ -791,7 +963,7 @@ void Solver::run_level(int li) {
 
         WorkCtx w;
         w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN;
-        w.ldq = ldq; w.ldb = ldb; w.Apack = Apack.p; w.B = B.p; w.Qnext = Qcur; w.lidx = lidx.p;
+        w.ldq = ldq; w.ldb = ldb; w.Apack = Awork; w.B = B.p; w.Qnext = Qcur; w.lidx = lidx.p;
         w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
         w.fail = fail.p + FAIL_TILES;
         const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
@@ -812,8 +984,11 @@ void Solver::run_level(int li) {
         pt.end(stream);
     }
 
-    if (c.Qz == nullptr) launch_items(stream, n, ExtractRows{c, Qcur, ldq, frow.p, lrow.p});
-    if (coop && li + 1 < (int)levels.size()) {
+    if (c.Qz == nullptr) launch_items(stream, n, ExtractRows{c, Qcur, ldq, frow.p, lrow.p, (coop && p2p.on) ? p2p.H : SymHeap()});
+    if (coop && p2p.on) {
+        // (first rows were pushed by rank 0, last rows by rank G-1, straight from the GEMM output)
+        if (li + 1 < (int)levels.size()) { pt.begin(T_COMM, stream); p2p_barrier(); pt.end(stream); }
+    } else if (coop && li + 1 < (int)levels.size()) {
         // first rows live on rank 0, last rows on rank G-1 (slice layout): replicate them for the next level
         comm.group_bcast(frow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), 0, 0, G, stream);
         comm.group_bcast(lrow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), G - 1, 0, G, stream);
@@ -836,20 +1011,30 @@ void Solver::finish() {
             struct Slice { int g0, l0, cnt; const double* lo; const double* hi; };
             std::vector<Slice> sl;
             if (G == 1) sl.push_back(Slice{0, 0, n, halo.p, halo.p});
-            else {
+            else if (p2p.on) {
+                // halo rows: stored straight into the heap of the rank that needs them, one barrier
+                HaloCtx hc;
+                hc.H = p2p.H; hc.Q = Qcur; hc.ldq = ldq; hc.perm = perm.p; hc.halo_lo = p2p.halo_lo; hc.halo_hi = p2p.halo_hi; hc.n = n; hc.S = S;
+                for (int s = 0; s <= S; ++s) hc.crow0[s] = crow0[s];
+                launch_items(stream, (long)S * n, PushHaloRows{hc});
+                p2p_barrier();
+                for (int s = 0; s < S; ++s)
+                    sl.push_back(Slice{sub_off[s] + slice_lo(s, comm.rank), crow0[s], crow0[s + 1] - crow0[s],
+                                       p2p.halo_lo + (size_t)s * n, p2p.halo_hi + (size_t)s * n});
+            } else {
                 // halo rows: first and last local row of every slice of every rank
-                for (int s = 0; s < G; ++s) {
+                for (int s = 0; s < S; ++s) {
                     launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s], perm.p, halo.p + (size_t)(2 * s) * n});
                     launch_items(stream, n, ExtractRowVec{Qcur, ldq, (long)crow0[s + 1] - 1, perm.p, halo.p + (size_t)(2 * s + 1) * n});
                 }
-                comm.allgather(halo.p, halo_all.p, sizeof(double) * 2 * n * G, stream);
-                auto row_of = [&](int rank, int s, int which) { return halo_all.p + ((size_t)rank * 2 * G + 2 * s + which) * n; };
+                comm.allgather(halo.p, halo_all.p, sizeof(double) * 2 * n * S, stream);
+                auto row_of = [&](int rank, int s, int which) { return halo_all.p + ((size_t)rank * 2 * S + 2 * s + which) * n; };
                 const int me = comm.rank;
-                for (int s = 0; s < G; ++s) {
+                for (int s = 0; s < S; ++s) {
                     Slice x;
                     x.g0 = sub_off[s] + slice_lo(s, me); x.l0 = crow0[s]; x.cnt = crow0[s + 1] - crow0[s];
                     x.lo = (me > 0) ? row_of(me - 1, s, 1) : (s > 0 ? row_of(G - 1, s - 1, 1) : halo.p);
-                    x.hi = (me < G - 1) ? row_of(me + 1, s, 0) : (s < G - 1 ? row_of(0, s + 1, 0) : halo.p);
+                    x.hi = (me < G - 1) ? row_of(me + 1, s, 0) : (s < S - 1 ? row_of(0, s + 1, 0) : halo.p);
                     sl.push_back(x);
                 }
             }
@@ -862,7 +1047,11 @@ void Solver::finish() {
 #endif
                 g_launches.launches++;
             }
-            comm.allreduce_sum(res2.p, n, stream);
+            if (p2p.on) {
+                launch_items(stream, n, PushResidualPartials{p2p.H, res2.p, p2p.res_part, n});
+                p2p_barrier();
+                launch_items(stream, n, SumResidualPartials{p2p.res_part, res2.p, n, G});
+            } else comm.allreduce_sum(res2.p, n, stream);
             dev_d2h(pin_res, res2.p, sizeof(double) * n, stream);
         }
         pt.end(stream);
@@ -875,14 +1064,14 @@ void Solver::materialise_sorted() {
 #if CUPPEN_CUDA
     {
         dim3 grid((unsigned)n, (unsigned)std::max(1, std::min(64, (nloc_final + 255) / 256)));
-        gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Apack.p, ldq, nloc_final, perm.p);
+        gather_cols_kernel<<<grid, 256, 0, stream>>>(Qcur, Awork, ldq, nloc_final, perm.p);
         CUDA_CHECK(cudaGetLastError());
     }
 #else
-    gather_cols_host(Qcur, Apack.p, ldq, nloc_final, perm.p, n);
+    gather_cols_host(Qcur, Awork, ldq, nloc_final, perm.p, n);
 #endif
     g_launches.launches++;
-    Qcur = Apack.p;                  // until the next solve, which starts from Qa again
+    std::swap(Qcur, Awork);          // until the next solve, which starts from Qa / Apack again
     dev_sync(stream);
     sorted_materialised = true;
 }
@@ -933,11 +1122,14 @@ void Solver::enqueue_solve() {
     pt.record(ev_begin, stream);
 #endif
     Qcur = Qa.p;
+    Awork = Apack.p;
     run_leaves();
     for (int li = 0; li < (int)levels.size(); ++li) run_level(li);
     if (!h_desc_all.empty()) dev_d2h(pin_desc, desc_all.p, sizeof(MergeDesc) * h_desc_all.size(), stream);
     finish();
     dev_d2h(pin_fail, fail.p, sizeof(int) * FAIL_INTS, stream);
+    Qfinal = Qcur;
+    Afinal = Awork;
 #if CUPPEN_CUDA
     pt.record(ev_end, stream);
 #endif
@@ -959,7 +1151,8 @@ void Solver::solve() {
 #if CUPPEN_CUDA
     if (use_graph && !graph_failed && graph_exec) {
         CUDA_CHECK(cudaGraphLaunch(graph_exec, stream));
-        Qcur = Qa.p;
+        Qcur = Qfinal;
+        Awork = Afinal;
         g_launches.launches += graph_launches;
         replayed = true;
     } else if (use_graph && !graph_failed && solves_done >= 1) {
@@ -1053,6 +1246,8 @@ void Solver::solve() {
 #endif
     if (hfail[FAIL_TILES] != 0)
         CUPPEN_THROW(CUPPEN_ERR_STATE, "GEMM tile list overflow (%zu tiles allocated): the eigenvectors of this solve are incomplete", tiles.n);
+    if (hfail[FAIL_COMM] != 0)
+        CUPPEN_THROW(CUPPEN_ERR_COMM, "peer barrier timed out waiting for rank %d (a peer fell out of the solve)", hfail[FAIL_COMM] - 1);
     if (hfail[0] != 0) CUPPEN_THROW(CUPPEN_ERR_CONVERGENCE, "leaf QL iteration did not converge (row %d)", hfail[0] - 1);
     solved = true;
 }
@@ -1268,7 +1463,7 @@ int cuppen_local_row_map(cuppen_handle h, int* global_rows) {
     Solver& s = h->s;
     if (s.G == 1) { for (int r = 0; r < s.n; ++r) global_rows[r] = r; }
     else
-        for (int sub = 0; sub < s.G; ++sub)
+        for (int sub = 0; sub < s.S; ++sub)
             for (int l = s.crow0[sub]; l < s.crow0[sub + 1]; ++l)
                 global_rows[l] = s.sub_off[sub] + s.slice_lo(sub, s.comm.rank) + (l - s.crow0[sub]);
     CUPPEN_API_END

@@ -41,6 +41,9 @@ CASES = [
     ("goe_n4096_p8", ("goe", 4096), 8, False),
     ("wilk64_n16384_p8", ("wilk", 16384), 8, False),
     ("randu_n16384_p8", ("randu", 16384), 8, False),
+    # BASELINE configs[2] as bench.py runs it (the headline workload) and the north-star target size
+    ("goe_n16384_p8", ("goe", 16384), 8, False),
+    ("goe_n32768_p8", ("goe", 32768), 8, False),
     # -eFILE at BASELINE configs[1] / a GEMM-heavy input: the reference back-transforms only the listed (1-based)
     # indices (src/filehandling.c:165-239,339-345; ~4 s per vector here) -- pins the selected-eigenvector mode
     ("s1_n4096_p8_sel", ("scheme", 1, 4096), 8, [1, 1000, 2048, 4096]),

@@ -49,6 +49,12 @@ def _run(world, gen, n, P, vectors, hostemu):
     (2, "goe", 333, 1, True),      # odd sizes: slices start at odd rows
     (4, "s2", 1000, 8, True),      # reference leaves of 125 rows, Givens-heavy
     (8, "goe", 640, 8, True),      # one rank per reference leaf, three cooperative levels
+    (3, "goe", 400, 4, True),      # any rank count: 4 subtrees over 3 ranks (1 / 1 / 2)
+    (3, "s1", 333, 3, True),       # reference tree of 3 leaves on 3 ranks
+    (5, "goe", 777, 8, True),      # 8 subtrees over 5 ranks
+    (6, "s2", 600, 1, True),       # accurate tree, 8 subtrees over 6 ranks
+    (7, "rand_u", 900, 2, False),  # eigenvalue-only mode on 7 ranks
+    (2, "goe", 301, 3, True),      # `-g 2 -p 3`: unequal subtrees (2 reference leaves | 1)
 ])
 def test_sharded_solve_over_gloo(hostemu, oracle, world, gen, n, P, vectors):
     _run(world, gen, n, P, vectors, hostemu)
