@@ -387,6 +387,9 @@ def run_workload(ctx, w, steps, warmup, e2e_iters, fp64, lapack=None, want_solo=
     peaks, peak_src = measured_peaks()
     roof, cats, gemm_tflops = roofline_entry(tavg, w, ctx.world, ms, fp64, peaks, peak_src)
     out["phase_ms"] = {k: v * 1e3 for k, v in cats.items()}
+    if ctx.world > 1:
+        out["phase_ms"]["comm"] = tavg["comm_s"] * 1e3
+        out["comm_backend"] = {0: "none", 1: "NCCL collectives between the kernels", 2: "peer memory (NVLink loads/stores in our kernels, flag barriers)"}.get(int(round(tavg["comm_mode"])), "?")
     out["phase_ms"]["outside_phase_timers"] = ms - sum(out["phase_ms"].values())
     out["roofline"] = roof
     out["gemm_tflops_executed_rank0"] = gemm_tflops
@@ -506,7 +509,7 @@ def run_ours(a):
         "gemm_tflops_executed": res["gemm_tflops_executed_rank0"],
         "e2e": res["e2e"], "gpu_launches": res["gpu_launches"], "launches_per_step": res["launches_per_step"],
         "same_workload_1gpu": res.get("same_workload_1gpu"),
-        "phase_ms": res["phase_ms"], "roofline": res["roofline"],
+        "phase_ms": res["phase_ms"], "comm_backend": res.get("comm_backend"), "roofline": res["roofline"],
         "fp64_yardsticks_tflops": {k: fp64[k] for k in ("dmma_issue_loop", "dfma_issue_loop", "cublas_dgemm_8192")},
         "clocks": clocks, "check": res["check"], "other_configs": extras,
     }

@@ -64,7 +64,9 @@ enum {
     CUPPEN_FLAG_NO_RESIDUALS = 2,
     CUPPEN_FLAG_SELECT = 4      /* eigenvectors of selected eigenvalues only (the reference's -eFILE): no n x n matrix
                                    is formed, the selected columns are pushed through the implicit U factors of
-                                   the tree; see cuppen_select_eigenvectors */
+                                   the tree; see cuppen_select_eigenvectors.  Several ranks: the (cheap) eigenvalue-only
+                                   decomposition is replicated, the selected vectors are dealt to the ranks and
+                                   gathered, so every rank returns all of them */
 };
 
 /* One record per merge of the tree. */
@@ -162,7 +164,8 @@ int cuppen_copy_selected_eigenvectors(cuppen_handle h, double* V, long ld);
  * One GPU, CUPPEN_FLAG_VECTORS.  seconds (may be NULL): device time of the check. */
 int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds);
 /* Eigenvector file (binary): "CUPPENV1" | int64 n | int64 ncols | int64 rank[ncols] | double lambda[ncols] |
- * double V[ncols][n].  All n vectors (CUPPEN_FLAG_VECTORS, ascending lambda) or the selected ones (CUPPEN_FLAG_SELECT). */
+ * double V[ncols][n].  All n vectors (CUPPEN_FLAG_VECTORS, ascending lambda) or the selected ones (CUPPEN_FLAG_SELECT).
+ * Several ranks: every rank calls (the row slices are gathered panel by panel), rank 0 writes; filename may be NULL elsewhere. */
 int cuppen_write_eigenvectors(cuppen_handle h, const char* filename);
 const char* cuppen_last_error(void);
 

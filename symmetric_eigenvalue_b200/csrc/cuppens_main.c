@@ -9,11 +9,12 @@
  * Additions that do not collide with the reference's options:
  *   -p P     number of reference MPI tasks whose divide tree is reproduced (what `mpirun -n P`
  *            was; default 1 or $CUPPENS_NUMTASKS)
- *   -g G     number of B200s (one process per GPU is forked, vectors travel over NCCL)
+ *   -g G     number of B200s, any count up to 8 (one process per GPU is forked; the O(n) vectors and the row
+ *            redistribution travel through peer memory over NVLink, NCCL ships the IPC handles)
  *   -v FILE  write the computed eigenvectors (all with -e, the selected ones with -eFILE) to FILE
  *            (binary CUPPENV1 layout, include/cuppen_b200.h) -- the reference cannot emit V
  *   -c       print max|V^T V - I| of the computed eigenvectors (evaluated on the GPU; needs -e, one GPU)
- * With -eFILE and few requested indices (count <= n/16, one GPU) the library's selected-eigenvector
+ * With -eFILE and few requested indices (count <= n/16) the library's selected-eigenvector
  * mode is used: no n x n matrix is formed (filehandling.c:339-345 computes one vector at a time too).
  */
 #define _GNU_SOURCE
@@ -63,9 +64,9 @@ static void showHelp(void) {
     printf("    Number of tasks of the original MPI program whose divide tree and deflation\n");
     printf("    rules are reproduced (default 1: accurate tolerances on all levels).\n");
     printf(" -g NUM\n");
-    printf("    Number of GPUs (power of two; one process per GPU).\n");
+    printf("    Number of GPUs (any count up to 8; one process per GPU).\n");
     printf(" -v FILENAME\n");
-    printf("    Write the computed eigenvectors to this file (binary; needs -e and one GPU).\n");
+    printf("    Write the computed eigenvectors to this file (binary; needs -e).\n");
     printf(" -c\n");
     printf("    Check the orthogonality of the computed eigenvectors (needs -e, one GPU).\n");
     printf("\n");
@@ -126,8 +127,8 @@ int main(int argc, char** argv) {
         default: return 1;
     }
     if (argc - optind > 1) { fprintf(stderr, "Invalid number of positional arguments. See help.\n"); return 1; }
-    if (gpus > 1 && (vecFile != NULL || checkOrth)) {
-        fprintf(stderr, "Options -v and -c need a single GPU (the rows of V are distributed over the GPUs). See help.\n");
+    if (gpus > 1 && checkOrth) {
+        fprintf(stderr, "Option -c needs a single GPU (the rows of V are distributed over the GPUs). See help.\n");
         return 1;
     }
     outputfile = argv[optind];
@@ -192,7 +193,7 @@ int main(int argc, char** argv) {
      * reference parses it, filehandling.c:339) to decide between the full and the selected-eigenvector mode */
     int selectMode = 0, selCount = 0;
     int* selIdx = NULL;
-    if (vectors && evFile != NULL && gpus == 1) {
+    if (vectors && evFile != NULL) {
         fflush(stdout);
         int keep = dup(1), nul = open("/dev/null", O_WRONLY);
         if (keep >= 0 && nul >= 0) {
@@ -229,7 +230,12 @@ int main(int argc, char** argv) {
     if (rc != 0) { fprintf(stderr, "cuppens: %s\n", cuppen_last_error()); return 5; }
     double toc = now_s();
 
-    if (rank != 0) { cuppen_destroy(h); _exit(0); }
+    if (rank != 0) {
+        /* the eigenvector file is written by rank 0 from row slices that every rank contributes */
+        if (vectors && vecFile != NULL) cuppen_write_eigenvectors(h, NULL);
+        cuppen_destroy(h);
+        _exit(0);
+    }
 
     cuppen_timers tm;
     cuppen_get_timers(h, &tm);

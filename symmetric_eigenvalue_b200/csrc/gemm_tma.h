@@ -21,6 +21,7 @@
 #include "gemm_dmma.h"
 
 #if CUPPEN_CUDA
+#include <cuda.h>
 
 namespace cuppen {
 
@@ -70,9 +71,24 @@ __device__ __forceinline__ void tma_bulk_load(void* dst, const void* src, unsign
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
                  :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// TMA tensor copy of one {TMA_LD x TMA_BK} box (UTMALDG): c_in = element index along the contiguous dimension
+// (must be EVEN for fp64 maps -- a 16-byte aligned start; odd coordinates raise "illegal instruction" on this pool,
+// tests/probe/tma_probe.cu, profiles/r02_tma_probe.txt), c_out = line index
+__device__ __forceinline__ void tma_tensor_load(void* dst, const CUtensorMap* map, int c_in, int c_out, uint64_t* bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(c_in), "r"(c_out), "r"(smem_u32(bar)) : "memory");
+}
 
+// Operand tiles whose first row is odd (odd reference leaf sizes, odd slice offsets): a TMA copy needs a 16-byte
+// aligned source, so the A lines are fetched from one row earlier (`ashift` = 1: 130 doubles per line instead of 128;
+// the 4 pad doubles of the shared-memory line absorb them) and the consumers read their fragments one element further.
+// TENSOR = false: 32 bulk-copy lines per stage issued by the 32 lanes of the producer warp (UBLKCP);
+// TENSOR = true:  two tensor copies per stage issued by one lane (UTMALDG), box {TMA_LD, TMA_BK}: the box is as wide
+//                 as the padded shared-memory line, so the tile lands in the same conflict-free layout.
+template <bool TENSOR>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
-dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles, const int* __restrict__ ntiles_ptr, int* abort_flags) {
+dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles, const int* __restrict__ ntiles_ptr, int* abort_flags,
+                 const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
     extern __shared__ __align__(128) double tma_smem[];
     uint64_t* full = (uint64_t*)(tma_smem + TMA_STAGES * TMA_STAGE_DOUBLES);
     uint64_t* empty = full + TMA_STAGES;
@@ -86,7 +102,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
     __syncthreads();
 
     if (warp >= TMA_CONSUMER_WARPS) {
-        // ===== producer warpgroup: its first warp issues the bulk copies, one line per lane =====
+        // ===== producer warpgroup: its first warp issues the copies =====
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" :: "n"((int)TMA_REGS_PRODUCER));
         if (warp != TMA_CONSUMER_WARPS) return;
         int stage = 0;
@@ -97,19 +113,34 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
             const GemmTile T = tiles[tile];
             const GemmProblem& P = probs[T.prob];
             const int ktiles = (P.K + TMA_BK - 1) / TMA_BK;
+            const int ashift = P.a_row0 & 1;
+            if (TENSOR) {
+                if (lane != 0) continue;
+                const int ain = P.a_row0 + T.m0 - ashift, bin = P.b_col0 + T.n0;
+                for (int kt = 0; kt < ktiles; ++kt) {
+                    if (!mbar_wait(&empty[stage], phase ^ 1, 0, stage, tile, kt, abort_flags)) return;
+                    mbar_expect_tx(&full[stage], 2 * TMA_TILE_DOUBLES * 8);
+                    double* st = tma_smem + stage * TMA_STAGE_DOUBLES;
+                    tma_tensor_load(st, &mapA, ain, P.a_col0 + kt * TMA_BK, &full[stage]);
+                    tma_tensor_load(st + TMA_TILE_DOUBLES, &mapB, bin, P.b_row0 + kt * TMA_BK, &full[stage]);
+                    if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
+                }
+                continue;
+            }
             // lane < 16: line kk of the A tile; lane >= 16: line kk of the B tile
-            const double* src = isA ? P.A + (long)kk * P.lda + T.m0 : P.B + (long)kk * P.ldb + T.n0;
+            const double* src = isA ? P.A + (long)kk * P.lda + T.m0 - ashift : P.B + (long)kk * P.ldb + T.n0;
             const long step = (long)TMA_BK * (isA ? P.lda : P.ldb);
             const int dofs = (isA ? 0 : TMA_TILE_DOUBLES) + kk * TMA_LD;
+            const unsigned bytes = TMA_LINE_BYTES + ((isA && ashift) ? 16u : 0u);
             for (int kt = 0; kt < ktiles; ++kt) {
                 int ok = 1;
                 if (lane == 0) {
                     ok = mbar_wait(&empty[stage], phase ^ 1, 0, stage, tile, kt, abort_flags) ? 1 : 0;
-                    if (ok) mbar_expect_tx(&full[stage], TMA_STAGE_TX_BYTES);
+                    if (ok) mbar_expect_tx(&full[stage], TMA_STAGE_TX_BYTES + (ashift ? 16u * TMA_BK : 0u));
                 }
                 ok = __shfl_sync(0xffffffffu, ok, 0);
                 if (!ok) return;
-                tma_bulk_load(tma_smem + stage * TMA_STAGE_DOUBLES + dofs, src, TMA_LINE_BYTES, &full[stage]);
+                tma_bulk_load(tma_smem + stage * TMA_STAGE_DOUBLES + dofs, src, bytes, &full[stage]);
                 src += step;
                 if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
             }
@@ -121,7 +152,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" :: "n"((int)TMA_REGS_CONSUMER));
     const int wm = warp & 1, wn = warp >> 1;
     const int lr = lane >> 2, lk = lane & 3;
-    const int aofs = lk * TMA_LD + wm * 64 + lr;
+    const int aofs0 = lk * TMA_LD + wm * 64 + lr;
     const int bofs = TMA_TILE_DOUBLES + lk * TMA_LD + wn * 32 + lr;
 
     int stage = 0;
@@ -130,6 +161,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
         const GemmTile T = tiles[tile];
         const GemmProblem P = probs[T.prob];
         const int ktiles = (P.K + TMA_BK - 1) / TMA_BK;
+        const int aofs = aofs0 + (P.a_row0 & 1);
         double acc[8][4][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -176,10 +208,37 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
 
 inline size_t tma_smem_bytes() { return (size_t)TMA_STAGES * TMA_STAGE_DOUBLES * sizeof(double) + 2 * TMA_STAGES * sizeof(uint64_t); }
 
+// Tensor map of a whole operand buffer (fp64, 2-D, box {TMA_LD, TMA_BK}, no swizzle): `inner` contiguous elements per
+// line, `lines` lines `ld` elements apart.  The driver entry point is resolved through the runtime (no -lcuda).
+inline bool tma_encode_map(CUtensorMap* map, const double* base, long inner, long lines, long ld) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn enc = nullptr;
+    if (!enc) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) { cudaGetLastError(); return false; }
+        enc = (EncodeFn)fn;
+    }
+    memset(map, 0, sizeof *map);
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)lines};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 8};
+    cuuint32_t box[2] = {TMA_LD, TMA_BK}, es[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // (the >48 KB dynamic shared memory opt-in is a per-device attribute: set_kernel_attributes() in solver.cu)
-inline void launch_gemm_tma(Stream s, const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, int grid, int* abort_flags) {
+// mapA / mapB == nullptr: bulk-copy lines; else one tensor copy per operand and stage through the two maps
+inline void launch_gemm_tma(Stream s, const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, int grid, int* abort_flags,
+                            const CUtensorMap* mapA = nullptr, const CUtensorMap* mapB = nullptr) {
     if (grid < 1) return;
-    dgemm_tma_kernel<<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags);
+    if (mapA && mapB) dgemm_tma_kernel<true><<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags, *mapA, *mapB);
+    else {
+        static const CUtensorMap none = {};
+        dgemm_tma_kernel<false><<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags, none, none);
+    }
     CUDA_CHECK(cudaGetLastError());
 }
 

@@ -251,5 +251,21 @@ inline void cauchy_apply_host(LevelCtx c, SelCtx s, int ndesc) {
 }
 #endif
 
+// several ranks: gathered layout [rank][slot][n] (vector t of the caller's list sits at rank t % world, slot t / world)
+// -> the caller's order
+struct SelReorder {
+    const double* Vgath;
+    double* Vsel;
+    const double* rgath;
+    double* rsel;
+    int n, world, per;
+    CUPPEN_HD void operator()(long i) const {
+        const long t = i / n, r = i - t * n;
+        const long src = (t % world) * per + t / world;
+        Vsel[i] = Vgath[src * n + r];
+        if (r == 0) rsel[t] = rgath[src];
+    }
+};
+
 }  // namespace cuppen
 #endif

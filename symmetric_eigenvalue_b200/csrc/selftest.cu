@@ -84,7 +84,10 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    const int row0 = (variant == 1) ? 2 : 3;                 // odd row offset (cp.async kernels), even for the 16-byte bulk-copy lines
+    // row offset of the operand inside its buffer: odd for the cp.async kernels and for variants 3 / 5 (the TMA kernels
+    // fetch such tiles from one row earlier), even for variants 1 / 4
+    const int row0 = (variant == 1 || variant == 4) ? 2 : 3;
+    const bool tma = (variant == 1 || variant == 3 || variant == 4 || variant == 5), tensor = (variant == 4 || variant == 5);
     const long lda = round_up(M + row0 + 128, 16), ldb = round_up(N, 16) + 16, ldc = lda;
     const long Kp = round_up(K, K_PAD);
     DevBuf<double> A, Bm, C, err;
@@ -106,6 +109,9 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     P.lda = lda; P.ldb = ldb; P.ldc = ldc; P.a_row0 = row0; P.a_col0 = 0; P.b_row0 = 0; P.b_col0 = 0;
     std::vector<GemmTile> ht;
     const int BM = variant == 2 ? 64 : 128, BN = BM;
+    CUtensorMap mA, mB;
+    if (tensor && (!tma_encode_map(&mA, A.p, lda, (long)(A.n / lda), lda) || !tma_encode_map(&mB, Bm.p, ldb, (long)(Bm.n / ldb), ldb)))
+        CUPPEN_THROW(CUPPEN_ERR_CUDA, "cuTensorMapEncodeTiled failed");
     for (int m0 = 0; m0 < M; m0 += BM)
         for (int n0 = 0; n0 < N; n0 += BN) ht.push_back(GemmTile{0, m0, n0});
     dprob.alloc(1); dtiles.alloc(ht.size());
@@ -122,8 +128,11 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     for (int r = 0; r < std::max(1, reps) + 1; ++r) {
         CUDA_CHECK(cudaEventRecord(e0, s));
         const long nt = (long)ht.size();
-        if (variant == 1) { CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
-            launch_gemm_tma(s, dprob.p, dtiles.p, dnt.p, (int)std::min<long>(nt, prop.multiProcessorCount), dabort.p); }
+        if (tma) {
+            CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
+            CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
+            launch_gemm_tma(s, dprob.p, dtiles.p, dnt.p, (int)std::min<long>(nt, prop.multiProcessorCount), dabort.p, tensor ? &mA : nullptr, tensor ? &mB : nullptr);
+        }
         else if (variant == 2) launch_gemm<64, 64, 16, 2, 2, 3>(s, dprob.p, dtiles.p, dnt.p, std::min<long>(nt, prop.multiProcessorCount * 8L));
         else launch_gemm<128, 128, 16, 2, 4, 3>(s, dprob.p, dtiles.p, dnt.p, std::min<long>(nt, prop.multiProcessorCount * 2L));
         CUDA_CHECK(cudaEventRecord(e1, s));

@@ -101,10 +101,10 @@ struct Solver {
     std::vector<int> crow0;
     int nloc_final = 0;           // local rows of the final V
     int slice_lo(int s, int j) const { return j >= G ? sub_n[s] : (int)(((long)j * sub_n[s] / G) & ~1L); }
-    long ldq_of(int r) const {    // leading dimension of rank r's Q buffers (every rank can work out every rank's layout)
+    long rows_of(int r) const {   // rows rank r needs in either layout (every rank can work out every rank's layout)
         long c = 0;
         for (int s = 0; s < S; ++s) c += slice_lo(s, r + 1) - slice_lo(s, r);
-        return round_up(std::max<long>(rank_row0(r + 1) - rank_row0(r), c), 16);
+        return std::max<long>(rank_row0(r + 1) - rank_row0(r), c);
     }
 
     std::vector<double> hD, hE;   // matrix as uploaded (host): the caller's T times `scale`
@@ -122,6 +122,14 @@ struct Solver {
     size_t lvl_stride = 0;
     int lvl_cap = 1;
     std::vector<int> h_sel;                  // requested ranks (ascending-lambda order), caller's order
+    // several ranks: the eigenvalue-only decomposition is replicated (61 ms at n = 65536 -- cheaper than exchanging its
+    // per-level vectors), the selected vectors are dealt round-robin to the ranks (vector t goes to rank t % world) and
+    // gathered at the end, so every rank returns all of them (src/filehandling.c:339-348 serves -eFILE at any rank count)
+    Comm sel_comm;
+    int sel_rank = 0, sel_world = 1;
+    std::vector<int> h_sel_local;
+    DevBuf<double> Vgath, res_gath;
+    int sel_per() const { return ((int)h_sel.size() + sel_world - 1) / sel_world; }
     DevBuf<int> sel_dev, leaf_off_dev, leaf_n_dev;
     DevBuf<double> Qleaf, selX, selY, selXS, selGam, sel_dorg, Vsel, res_sel;
     std::vector<double> h_res_sel;
@@ -205,7 +213,10 @@ struct Solver {
     }
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
     int resid_variant = 0;        // residual_kernel variant (0: default); env CUPPEN_RESID
-    int gemm_variant = 1;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA kernel (gemm_tma.h); env CUPPEN_GEMM
+    int gemm_variant = 1;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA bulk-copy lines, 2: TMA tensor maps (gemm_tma.h); env CUPPEN_GEMM
+#if CUPPEN_CUDA
+    CUtensorMap map_qa, map_apack, map_b;      // tensor maps of the two n x n buffers (either can be the pack buffer) and of the U arena
+#endif
     int num_sms = 148;
 #if CUPPEN_CUDA
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
@@ -281,8 +292,11 @@ void Solver::init_layout() {
     }
     nlocC = crow0[S];
     nloc_final = (G > 1) ? nlocC : nlocL;
-    ldq = round_up(std::max(nlocL, nlocC), 16);
-    if (ldq != ldq_of(comm.rank)) CUPPEN_THROW(CUPPEN_ERR_STATE, "inconsistent leading dimension");
+    // one leading dimension for all ranks (the largest row count): peers address each other's buffers with it
+    long rows = 0;
+    for (int r = 0; r < G; ++r) rows = std::max(rows, rows_of(r));
+    if (rows < std::max(nlocL, nlocC)) CUPPEN_THROW(CUPPEN_ERR_STATE, "inconsistent row layout");
+    ldq = round_up(rows, 16);
 }
 
 // Function attributes are per device: every handle opts its device in to the >48 KB dynamic shared memory of the
@@ -293,7 +307,8 @@ static void set_kernel_attributes() {
                                     (int)DmmaCfg<64, 64, 16, 2, 2, 3>::SMEM_BYTES));
     CUDA_CHECK(cudaFuncSetAttribute(dgemm_dmma_kernel<128, 128, 16, 2, 4, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)DmmaCfg<128, 128, 16, 2, 4, 3>::SMEM_BYTES));
-    CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
+    CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
+    CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
     CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SEC_SMEM_K * sizeof(double))));
     CUDA_CHECK(cudaFuncSetAttribute(gram_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes()));
 #endif
@@ -367,6 +382,13 @@ void Solver::allocate() {
         if (rv && atoi(rv) > 0) resid_variant = atoi(rv);
         const char* gv = getenv("CUPPEN_GEMM");
         if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
+        if (gv && !strcmp(gv, "tensor")) gemm_variant = 2;
+        if (gemm_variant == 2) {
+            const long cols = (long)(qelems / (size_t)ldq), brows = (long)(B.n / (size_t)ldb);
+            if (!tma_encode_map(&map_qa, Qa.p, ldq, cols, ldq) || !tma_encode_map(&map_apack, Apack.p, ldq, cols, ldq) ||
+                !tma_encode_map(&map_b, B.p, ldb, brows, ldb))
+                CUPPEN_THROW(CUPPEN_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUPPEN_GEMM=tensor)");
+        }
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
         num_sms = prop.multiProcessorCount;
@@ -719,7 +741,7 @@ void Solver::enter_cooperative_p2p() {
         for (int s = 0; s < S; ++s) {
             const int o = owner_of_sub(s);           // layout L of the owner: local row = global row - its first row
             pc.src[s] = p2p.peerQ[o];
-            pc.src_ld[s] = ldq_of(o);
+            pc.src_ld[s] = ldq;
             pc.sub_off[s] = sub_off[s];
             pc.slo[s] = sub_off[s] - rank_row0(o) + slice_lo(s, comm.rank);
             pc.crow0[s] = crow0[s];
@@ -973,7 +995,9 @@ void Solver::run_level(int li) {
         CUDA_CHECK(cudaGetLastError());
         const int grid = (int)std::min<long>(worst, small_tiles ? num_sms * 8L : (long)num_sms);
         if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, ntiles_dev.p, grid);
-        else if (gemm_variant == 1 && L.aligned) launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA);
+        else if (gemm_variant == 2)
+            launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA, Awork == Apack.p ? &map_apack : &map_qa, &map_b);
+        else if (gemm_variant == 1) launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA);
         else launch_gemm<128, 128, 16, 2, 4, 3>(stream, probs.p, tiles.p, ntiles_dev.p, std::min<long>(worst, num_sms * 2L));
 #else
         (void)worst;
@@ -1079,8 +1103,11 @@ void Solver::materialise_sorted() {
 // selected-eigenvector mode: push the unit vectors of the requested columns of the root down the tree
 // (select_stages.h).  Runs after the (possibly graph-replayed) eigenvalue solve on the same stream.
 void Solver::enqueue_apply() {
-    const int cnt = (int)h_sel.size();
-    if (!select_mode || cnt == 0) return;
+    if (!select_mode || h_sel.empty()) return;
+    const int cnt = (int)h_sel_local.size();           // vectors of this rank (all of them on one rank)
+    const int per = sel_per();
+    double* Vloc = sel_world > 1 ? Vgath.p + (size_t)sel_rank * per * n : Vsel.p;
+    double* rloc = sel_world > 1 ? res_gath.p + (size_t)sel_rank * per : res_sel.p;
 #if CUPPEN_CUDA
     if (!ev_ap0) { CUDA_CHECK(cudaEventCreate(&ev_ap0)); CUDA_CHECK(cudaEventCreate(&ev_ap1)); }
     CUDA_CHECK(cudaEventRecord(ev_ap0, stream));
@@ -1108,9 +1135,15 @@ void Solver::enqueue_apply() {
             launch_items(stream, n, ApplyChains{c, s});
             std::swap(s.X, s.Y);
         }
-        launch_items(stream, n, LeafApply{s, leaf_off_dev.p, leaf_n_dev.p, Qleaf.p, Vsel.p + (size_t)v0 * n});
+        launch_items(stream, n, LeafApply{s, leaf_off_dev.p, leaf_n_dev.p, Qleaf.p, Vloc + (size_t)v0 * n});
     }
-    launch_warps(stream, cnt, SelResidual{n, Vsel.p, dOD.p, dOE.p, lam_sorted.p, sel_dev.p, res_sel.p});
+    if (cnt > 0) launch_warps(stream, cnt, SelResidual{n, Vloc, dOD.p, dOE.p, lam_sorted.p, sel_dev.p, rloc});
+    if (sel_world > 1) {
+        // every rank ends up with all vectors, in the caller's order
+        sel_comm.allgather(Vloc, Vgath.p, sizeof(double) * (size_t)per * n, stream);
+        sel_comm.allgather(rloc, res_gath.p, sizeof(double) * (size_t)per, stream);
+        launch_items(stream, (long)h_sel.size() * n, SelReorder{Vgath.p, Vsel.p, res_gath.p, res_sel.p, n, sel_world, per});
+    }
 #if CUPPEN_CUDA
     CUDA_CHECK(cudaEventRecord(ev_ap1, stream));
 #endif
@@ -1277,8 +1310,6 @@ static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int
     if (n / ref_leaves == 0) CUPPEN_THROW(CUPPEN_ERR_LEAF, "Leaf Size is too small! Reduce number of tasks.");
     if ((flags & CUPPEN_FLAG_SELECT) && (flags & CUPPEN_FLAG_VECTORS))
         CUPPEN_THROW(CUPPEN_ERR_ARG, "CUPPEN_FLAG_SELECT and CUPPEN_FLAG_VECTORS are exclusive");
-    if ((flags & CUPPEN_FLAG_SELECT) && comm.world > 1)
-        CUPPEN_THROW(CUPPEN_ERR_ARG, "selected-eigenvector mode runs on one GPU (it needs O(n) memory per vector)");
 #if CUPPEN_CUDA
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1292,6 +1323,12 @@ static int create_common(cuppen_handle* h, int n, int ref_leaves, int flags, int
     s.n = n; s.P = ref_leaves; s.flags = flags; s.device = device; s.want_vectors = (flags & CUPPEN_FLAG_VECTORS) != 0;
     s.select_mode = (flags & CUPPEN_FLAG_SELECT) != 0;
     s.comm = comm;
+    if (s.select_mode && comm.world > 1) {
+        // replicated eigenvalue-only decomposition, the selected vectors dealt to the ranks: the communicator is only
+        // used to gather them
+        s.sel_comm = comm; s.sel_rank = comm.rank; s.sel_world = comm.world;
+        s.comm = Comm();
+    }
     try {
 #if CUPPEN_CUDA
         CUDA_CHECK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -1357,6 +1394,7 @@ int cuppen_destroy(cuppen_handle h) {
     CUPPEN_API_BEGIN
     if (h) {
         h->s.comm.destroy();
+        h->s.sel_comm.destroy();
 #if CUPPEN_CUDA
         if (h->s.stream) cudaStreamDestroy(h->s.stream);
 #endif
@@ -1538,11 +1576,18 @@ int cuppen_select_eigenvectors(cuppen_handle h, const int* idx, int cnt) {
     CUDA_CHECK(cudaSetDevice(s.device));
 #endif
     s.h_sel.assign(idx, idx + cnt);
+    s.h_sel_local.clear();
+    for (int t = s.sel_rank; t < cnt; t += s.sel_world) s.h_sel_local.push_back(idx[t]);
     s.h_res_sel.clear();
     if (cnt > 0) {
         if (s.sel_dev.n < (size_t)cnt + SEL_NV) { s.sel_dev.alloc((size_t)cnt + SEL_NV); s.res_sel.alloc((size_t)cnt + SEL_NV); }
         if (s.Vsel.n < (size_t)cnt * s.n) s.Vsel.alloc((size_t)cnt * s.n);
-        dev_h2d(s.sel_dev.p, s.h_sel.data(), sizeof(int) * cnt, s.stream);
+        if (s.sel_world > 1) {
+            const size_t slots = (size_t)s.sel_per() * s.sel_world;
+            if (s.Vgath.n < slots * s.n) s.Vgath.alloc(slots * s.n);
+            if (s.res_gath.n < slots + SEL_NV) s.res_gath.alloc(slots + SEL_NV);
+        }
+        if (!s.h_sel_local.empty()) dev_h2d(s.sel_dev.p, s.h_sel_local.data(), sizeof(int) * s.h_sel_local.size(), s.stream);
         dev_sync(s.stream);
     }
     s.solved = false;
@@ -1609,10 +1654,12 @@ int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds) 
 //   double lambda[ncols] | double V[ncols][n] (one eigenvector after the other)
 int cuppen_write_eigenvectors(cuppen_handle h, const char* filename) {
     CUPPEN_API_BEGIN
-    if (!h || !filename) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
+    if (!h) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
     Solver& s = h->s;
     if (!s.solved || !(s.want_vectors || s.select_mode)) CUPPEN_THROW(CUPPEN_ERR_STATE, "no eigenvectors to write");
-    if (s.G > 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "eigenvector output runs on one GPU");
+    // several ranks: every rank calls; rank 0 writes (selected mode: every rank holds all selected vectors)
+    const bool writer = s.select_mode ? (s.sel_rank == 0) : (s.comm.rank == 0);
+    if (writer && !filename) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
 #if CUPPEN_CUDA
     CUDA_CHECK(cudaSetDevice(s.device));
 #endif
@@ -1623,29 +1670,77 @@ int cuppen_write_eigenvectors(cuppen_handle h, const char* filename) {
     const long long ncols = (long long)ranks.size();
     std::vector<double> lam(ncols);
     for (long long t = 0; t < ncols; ++t) lam[t] = s.h_lam_sorted[ranks[t]];
-    FILE* f = fopen(filename, "wb");
-    if (!f) { fprintf(stderr, "Could not open file\n"); CUPPEN_THROW(CUPPEN_ERR_IO, "cannot open %s", filename); }
-    bool ok = fwrite("CUPPENV1", 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1 && fwrite(&ncols, 8, 1, f) == 1;
-    ok = ok && (ncols == 0 || (fwrite(ranks.data(), 8, ncols, f) == (size_t)ncols && fwrite(lam.data(), 8, ncols, f) == (size_t)ncols));
-    const double* src = nullptr;
-    long ld = 0;
-    if (s.select_mode) { src = s.Vsel.p; ld = s.n; }
-    else { s.materialise_sorted(); src = s.Qcur; ld = s.ldq; }
-    const long long panel = std::max<long long>(1, (64LL << 20) / (8 * n));        // <= 64 MB of host staging
-    std::vector<double> buf((size_t)std::min(panel, std::max<long long>(ncols, 1)) * n);
-    for (long long c0 = 0; ok && c0 < ncols; c0 += panel) {
-        const long long w = std::min(panel, ncols - c0);
-#if CUPPEN_CUDA
-        CUDA_CHECK(cudaMemcpy2DAsync(buf.data(), sizeof(double) * n, src + c0 * ld, sizeof(double) * ld, sizeof(double) * n, w,
-                                     cudaMemcpyDeviceToHost, s.stream));
-        dev_sync(s.stream);
-#else
-        for (long long c = 0; c < w; ++c) memcpy(buf.data() + c * n, src + (c0 + c) * ld, sizeof(double) * n);
-#endif
-        ok = fwrite(buf.data(), 8, (size_t)(w * n), f) == (size_t)(w * n);
+    FILE* f = nullptr;
+    bool ok = true;
+    if (writer) {
+        f = fopen(filename, "wb");
+        if (!f) fprintf(stderr, "Could not open file\n");
+        ok = f != nullptr;
+        ok = ok && fwrite("CUPPENV1", 1, 8, f) == 8 && fwrite(&n, 8, 1, f) == 1 && fwrite(&ncols, 8, 1, f) == 1;
+        ok = ok && (ncols == 0 || (fwrite(ranks.data(), 8, ncols, f) == (size_t)ncols && fwrite(lam.data(), 8, ncols, f) == (size_t)ncols));
     }
-    ok = (fclose(f) == 0) && ok;
-    if (!ok) CUPPEN_THROW(CUPPEN_ERR_IO, "write error on %s", filename);
+    const bool distributed = !s.select_mode && s.G > 1;
+    if (distributed) {
+        // all ranks must agree before the collective part starts
+        DevBuf<double> flag;
+        flag.alloc(8);
+        double bad = ok ? 0.0 : 1.0;
+        dev_h2d(flag.p, &bad, sizeof bad, s.stream);
+        s.comm.allreduce_sum(flag.p, 1, s.stream);
+        dev_d2h(&bad, flag.p, sizeof bad, s.stream);
+        dev_sync(s.stream);
+        if (bad != 0.0) { if (f) fclose(f); CUPPEN_THROW(CUPPEN_ERR_IO, "cannot open %s", filename ? filename : "(rank 0's file)"); }
+        s.materialise_sorted();
+        // panels of sorted columns: all-gather the ranks' row slices (ldq x w doubles each), rank 0 puts the rows in place
+        const int G = s.G;
+        const long long w = std::max<long long>(1, std::min<long long>(n, (256LL << 20) / (8LL * G * s.ldq)));
+        DevBuf<double> gath;
+        gath.alloc((size_t)G * s.ldq * w);
+        std::vector<double> hg, buf;
+        std::vector<std::vector<int>> rowmap(G);
+        if (writer) {
+            hg.resize((size_t)G * s.ldq * w);
+            buf.resize((size_t)w * n);
+            for (int r = 0; r < G; ++r)
+                for (int sub = 0; sub < s.S; ++sub)
+                    for (int i = s.slice_lo(sub, r); i < s.slice_lo(sub, r + 1); ++i) rowmap[r].push_back(s.sub_off[sub] + i);
+        }
+        for (long long c0 = 0; c0 < n; c0 += w) {
+            const long long wc = std::min(w, n - c0);
+            s.comm.allgather(s.Qcur + c0 * s.ldq, gath.p, sizeof(double) * (size_t)s.ldq * wc, s.stream);
+            if (!writer) continue;
+            dev_d2h(hg.data(), gath.p, sizeof(double) * (size_t)G * s.ldq * wc, s.stream);
+            dev_sync(s.stream);
+            for (int r = 0; r < G; ++r)
+                for (long long c = 0; c < wc; ++c) {
+                    const double* src = hg.data() + ((size_t)r * wc + c) * s.ldq;
+                    double* dst = buf.data() + c * n;
+                    for (size_t l = 0; l < rowmap[r].size(); ++l) dst[rowmap[r][l]] = src[l];
+                }
+            ok = ok && fwrite(buf.data(), 8, (size_t)(wc * n), f) == (size_t)(wc * n);
+        }
+        dev_sync(s.stream);
+    } else if (writer) {
+        const double* src = nullptr;
+        long ld = 0;
+        if (s.select_mode) { src = s.Vsel.p; ld = s.n; }
+        else { s.materialise_sorted(); src = s.Qcur; ld = s.ldq; }
+        const long long panel = std::max<long long>(1, (64LL << 20) / (8 * n));        // <= 64 MB of host staging
+        std::vector<double> buf((size_t)std::min(panel, std::max<long long>(ncols, 1)) * n);
+        for (long long c0 = 0; ok && c0 < ncols; c0 += panel) {
+            const long long w = std::min(panel, ncols - c0);
+#if CUPPEN_CUDA
+            CUDA_CHECK(cudaMemcpy2DAsync(buf.data(), sizeof(double) * n, src + c0 * ld, sizeof(double) * ld, sizeof(double) * n, w,
+                                         cudaMemcpyDeviceToHost, s.stream));
+            dev_sync(s.stream);
+#else
+            for (long long c = 0; c < w; ++c) memcpy(buf.data() + c * n, src + (c0 + c) * ld, sizeof(double) * n);
+#endif
+            ok = fwrite(buf.data(), 8, (size_t)(w * n), f) == (size_t)(w * n);
+        }
+    }
+    if (f) ok = (fclose(f) == 0) && ok;
+    if (!ok) CUPPEN_THROW(CUPPEN_ERR_IO, "write error on %s", filename ? filename : "(null)");
     CUPPEN_API_END
 }
 

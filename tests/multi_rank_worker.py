@@ -86,11 +86,33 @@ def make_callbacks(rank, world):
 def main():
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     gen, n, P, vectors = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4] == "1"
+    select_mode = sys.argv[4] == "sel"
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lib = api._declare(ctypes.CDLL(os.path.join(ROOT, "tests", "host", "_build", "libcuppen_hostemu.so")))
     D, E = {"goe": oracle.goe, "s1": lambda k: oracle.scheme(1, k), "s2": lambda k: oracle.scheme(2, k),
             "rand_u": oracle.rand_u}[gen](n)
     cb = make_callbacks(rank, world)
+    if select_mode:
+        # -eFILE on several ranks: replicated eigenvalue-only solve, the selected vectors dealt to the ranks and gathered
+        rng = np.random.default_rng(n)
+        sel = [0, n - 1] + rng.integers(0, n, size=11).tolist()       # 13 vectors: uneven over 2 / 3 / 4 ranks, duplicates allowed
+        s = se.CuppenSolver(n, ref_leaves=P, rank=rank, world=world, callbacks=cb, lib=lib, select=True)
+        s.set_tridiagonal(D, E)
+        s.select(sel)
+        s.solve()
+        one = se.cuppens(D, E, ref_leaves=P, lib=lib, select=sel)      # the same on one rank
+        assert np.array_equal(s.eigenvalues(), one["lam"])
+        assert np.array_equal(s.selected_eigenvectors(), one["V"]), "gathered vectors differ from the one-rank run"
+        assert np.array_equal(s.residuals(sel), one["resid"])
+        s.select(sel[:1])                                              # fewer vectors than ranks
+        s.solve()
+        assert np.array_equal(s.selected_eigenvectors(), one["V"][:, :1])
+        s.close()
+        dist.barrier()
+        if rank == 0:
+            print("MULTI_RANK_OK", flush=True)
+        dist.destroy_process_group()
+        return
     s = se.CuppenSolver(n, ref_leaves=P, vectors=vectors, rank=rank, world=world, callbacks=cb, lib=lib)
     s.set_tridiagonal(D, E)
     s.solve()

@@ -144,11 +144,13 @@ def test_resolve_is_repeatable(lib, oracle):
     s.close()
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 16), (1, 1, 1), (300, 200, 70), (77, 129, 0), (1000, 1203, 513), (130, 4000, 33), (2048, 1024, 2048)])
 def test_gemm_kernels_against_fma_reference(lib, variant, M, N, K):
-    """The three back-transformation GEMM kernels (cp.async 128x128, TMA 128x128, cp.async 64x64) on random
-    data with an odd row offset, ragged M/N/K and scattered output columns; fp64 tolerance: K * 4 ulp."""
+    """The back-transformation GEMM kernels on full-mantissa random data with ragged M/N/K and scattered output columns:
+    0 cp.async 128x128 (odd row offset), 1 TMA bulk-copy lines (even offset), 2 cp.async 64x64, 3 TMA bulk-copy lines with
+    an ODD row offset (lines fetched from one row earlier), 4 / 5 TMA tensor maps with an even / odd offset.
+    fp64 tolerance: K * 4 ulp."""
     from symmetric_eigenvalue_b200 import api
     err, _ = api.selftest_gemm(variant, M, N, K, reps=1)
     assert err <= max(K, 1) * 4 * 2.2e-16, (variant, M, N, K, err)

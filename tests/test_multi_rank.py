@@ -25,7 +25,7 @@ def _run(world, gen, n, P, vectors, hostemu):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                    OMP_NUM_THREADS="1")
         procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "multi_rank_worker.py"), gen, str(n), str(P),
-                                       "1" if vectors else "0"], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+                                       vectors if isinstance(vectors, str) else ("1" if vectors else "0")], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
     outs = []
     for p in procs:
         try:
@@ -55,6 +55,9 @@ def _run(world, gen, n, P, vectors, hostemu):
     (6, "s2", 600, 1, True),       # accurate tree, 8 subtrees over 6 ranks
     (7, "rand_u", 900, 2, False),  # eigenvalue-only mode on 7 ranks
     (2, "goe", 301, 3, True),      # `-g 2 -p 3`: unequal subtrees (2 reference leaves | 1)
+    (2, "goe", 300, 4, "sel"),     # -eFILE (selected-eigenvector mode) on several ranks
+    (3, "s1", 500, 8, "sel"),
+    (4, "s2", 256, 1, "sel"),
 ])
 def test_sharded_solve_over_gloo(hostemu, oracle, world, gen, n, P, vectors):
     _run(world, gen, n, P, vectors, hostemu)
