@@ -66,16 +66,22 @@ CUPPEN_HD int work_supercol(const WorkCtx& w, const GemmProblem& Pb) {
     if (nsw < 1) nsw = 1;
     return nsw < ntn ? (int)nsw : ntn;
 }
+// the q-th tile of problem p in that order (closed form, so that the tiles of a problem can be written in parallel)
+CUPPEN_HD GemmTile work_tile_at(const WorkCtx& w, const GemmProblem& Pb, int p, int q) {
+    const int ntm = (Pb.M + w.BM - 1) / w.BM, ntn = (Pb.N + w.BN - 1) / w.BN;
+    const int nsw = work_supercol(w, Pb);
+    const int full = ntm * nsw;                      // tiles of a full super-column (only the last one can be narrower)
+    const int sc = q / full, rem = q - sc * full;
+    const int ns = sc * nsw;
+    const int wd = (ntn - ns) < nsw ? (ntn - ns) : nsw;
+    const int mt = rem / wd, nt = ns + (rem - mt * wd);
+    return GemmTile{p, mt * w.BM, nt * w.BN};
+}
 template <class Emit>
 CUPPEN_HD void work_emit_tiles(const WorkCtx& w, const GemmProblem& Pb, int p, int t, Emit emit) {
     const int ntm = (Pb.M + w.BM - 1) / w.BM, ntn = (Pb.N + w.BN - 1) / w.BN;
-    const int nsw = work_supercol(w, Pb);
-    for (int ns = 0; ns < ntn; ns += nsw)
-        for (int mt = 0; mt < ntm; ++mt)
-            for (int nt = ns; nt < ns + nsw && nt < ntn; ++nt) {
-                if (t < w.tile_cap) emit(t, GemmTile{p, mt * w.BM, nt * w.BN});
-                ++t;
-            }
+    for (int q = 0; q < ntm * ntn; ++q, ++t)
+        if (t < w.tile_cap) emit(t, work_tile_at(w, Pb, p, q));
 }
 
 CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
@@ -99,7 +105,7 @@ CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
 
 #if CUPPEN_CUDA
 // one block; shared memory: 2*nd ints (tile offsets)
-__global__ void __launch_bounds__(256) build_gemm_work_kernel(WorkCtx w) {
+__global__ void __launch_bounds__(1024) build_gemm_work_kernel(WorkCtx w) {
     extern __shared__ int work_off[];
     __shared__ int misaligned;
     const int np = 2 * w.nd;
@@ -120,11 +126,14 @@ __global__ void __launch_bounds__(256) build_gemm_work_kernel(WorkCtx w) {
         if (run > w.tile_cap) *w.fail = 1;
     }
     __syncthreads();
-    for (int p = threadIdx.x; p < np; p += blockDim.x) {
+    // all threads write the tiles of one problem after the other (thousands of tiles per problem at the top levels;
+    // one thread per problem took ~45 us per launch, profiles/r02_ncu_launches_goe_n16384.csv)
+    for (int p = 0; p < np; ++p) {
         const GemmProblem Pb = w.probs[p];
         if (Pb.M == 0) continue;
-        GemmTile* tl = w.tiles;
-        work_emit_tiles(w, Pb, p, work_off[p], [tl](int t, GemmTile T) { tl[t] = T; });
+        const int cnt = ((Pb.M + w.BM - 1) / w.BM) * ((Pb.N + w.BN - 1) / w.BN), base = work_off[p];
+        for (int q = threadIdx.x; q < cnt; q += blockDim.x)
+            if (base + q < w.tile_cap) w.tiles[base + q] = work_tile_at(w, Pb, p, q);
     }
 }
 #endif
@@ -425,13 +434,22 @@ __global__ void __launch_bounds__(CS_THREADS) compact_scan_kernel(LevelCtx c) {
 enum { TL_TJ = 32, TL_SL = 16, TL_THREADS = TL_TJ * TL_SL, TL_RC = 512, TL_SUB = TL_RC / TL_SL, TILED_MIN_M = 2048 };
 
 // zhat_j = sign(z_j) sqrt( |prod_i (lambda_i - d_j) / prod_{i != j} (d_i - d_j)| / |rho| )
-__global__ void __launch_bounds__(TL_THREADS) loewner_tiled_kernel(LevelCtx c) {
+// (part, nparts, H): several GPUs with peer memory -- this rank computes the outputs [part*per, (part+1)*per) of every
+// merge, per = ceil(k / nparts) rounded up to the tile, and stores them into every rank's copy of the vector
+CUPPEN_D int tl_share(int k, int part, int nparts, int* hi) {
+    const int per = ((k + nparts - 1) / nparts + TL_TJ - 1) / TL_TJ * TL_TJ;
+    const int lo = part * per;
+    *hi = (lo + per < k) ? lo + per : k;
+    return lo;
+}
+__global__ void __launch_bounds__(TL_THREADS) loewner_tiled_kernel(LevelCtx c, int part, int nparts, SymHeap H) {
     __shared__ double s_lam_org[TL_RC], s_tau[TL_RC], s_dl[TL_RC];
     __shared__ double s_part[TL_SL][TL_TJ];
     const MergeDesc& D = c.desc[blockIdx.y];
     const int k = D.k, off = D.off;
-    const int j0 = blockIdx.x * TL_TJ;
-    if (j0 >= k) return;
+    int jhi;
+    const int j0 = tl_share(k, part, nparts, &jhi) + blockIdx.x * TL_TJ;
+    if (j0 >= jhi) return;
     const int out = threadIdx.x & (TL_TJ - 1), slice = threadIdx.x / TL_TJ;
     const int j = j0 + out;
     const double* dl = c.dl + off;
@@ -461,18 +479,21 @@ __global__ void __launch_bounds__(TL_THREADS) loewner_tiled_kernel(LevelCtx c) {
 #pragma unroll
         for (int q = 1; q < TL_SL; ++q) p *= s_part[q][out];
         const double zh = sqrt(fabs(p) / fabs(D.rho));
-        c.zhat[off + j] = (c.zl[off + j] < 0) ? -zh : zh;
+        const double v = (c.zl[off + j] < 0) ? -zh : zh;
+        c.zhat[off + j] = v;
+        for (int r = 0; r < H.G; ++r) if (r != H.me) H.at(r, c.zhat)[off + j] = v;
     }
 }
 
 // N_i = || zhat / (d - lambda_i) ||_2
-__global__ void __launch_bounds__(TL_THREADS) norms_tiled_kernel(LevelCtx c) {
+__global__ void __launch_bounds__(TL_THREADS) norms_tiled_kernel(LevelCtx c, int part, int nparts, SymHeap H) {
     __shared__ double s_dl[TL_RC], s_zh[TL_RC];
     __shared__ double s_part[TL_SL][TL_TJ];
     const MergeDesc& D = c.desc[blockIdx.y];
     const int k = D.k, off = D.off;
-    const int i0 = blockIdx.x * TL_TJ;
-    if (i0 >= k) return;
+    int ihi;
+    const int i0 = tl_share(k, part, nparts, &ihi) + blockIdx.x * TL_TJ;
+    if (i0 >= ihi) return;
     const int out = threadIdx.x & (TL_TJ - 1), slice = threadIdx.x / TL_TJ;
     const int i = i0 + out;
     const double* dl = c.dl + off;
@@ -497,7 +518,9 @@ __global__ void __launch_bounds__(TL_THREADS) norms_tiled_kernel(LevelCtx c) {
         double a = s_part[0][out];
 #pragma unroll
         for (int q = 1; q < TL_SL; ++q) a += s_part[q][out];
-        c.nrm[off + i] = sqrt(a);
+        const double v = sqrt(a);
+        c.nrm[off + i] = v;
+        for (int r = 0; r < H.G; ++r) if (r != H.me) H.at(r, c.nrm)[off + i] = v;
     }
 }
 
@@ -750,31 +773,64 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
 }
 
 // K5b: B[row = arena row of pole j][col = root i - p0] = zhat_j / (((d_j - d_org(i)) - tau_i) N_i)
-// grid.x = arena row (global index), grid.y = a few column lanes; a block strides over the 256-wide
-// column chunks of its row (the live count k is only known on the device).
+// A block owns UG_ROWS consecutive arena rows and strides over 256-wide column chunks: a thread keeps the three
+// per-root constants (origin pole, tau, norm) of its column in registers and walks down the rows, whose per-pole
+// constants sit in shared memory -- one division and 8 stored bytes per element, UG_ROWS independent divisions in
+// flight per thread, rows written as coalesced 2 KB segments.  (The first version spent four dependent L2 loads per
+// element -- dl[org[i]], tau[i], nrm[i] -- on one row per block: 2 TB/s; profiles/README.md.)
+enum { UG_ROWS = 8 };
 __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width, int new_lambda) {
-    const int row = blockIdx.x;
-    // the new eigenvalues of the level (NewLambda, one thread per index) ride along with the first panel: nothing
-    // between here and the next level's z assembly reads lam
-    if (new_lambda && blockIdx.y == 0 && threadIdx.x == 0) NewLambda{c}(row);
-    const int id = c.node_of[row];
-    if (id < 0) return;
-    const MergeDesc& D = c.desc[id];
-    const bool top = row < D.off + D.n1;
-    const int jj = row - (top ? D.off : D.off + D.n1);
-    const int kh = top ? D.ktop : D.kbot;
-    if (jj >= kh) return;
-    const int iend = min(D.k, p0 + width);
-    const int j = top ? c.toplist[row] : c.botlist[row];
-    const double* dl = c.dl + D.off;
-    const double dj = dl[j], zj = c.zhat[D.off + j];
-    double* out = M.B + (long)row * M.ldb - p0;
-    for (int i = p0 + blockIdx.y * 256 + threadIdx.x; i < iend; i += gridDim.y * 256) {
-        double den = ((dj - dl[c.org[D.off + i]]) - c.tau[D.off + i]) * c.nrm[D.off + i];
-        if (den == 0.0) den = 4.9e-324;
-        double v = zj / den;
-        if (!(fabs(v) < 1.7e308)) v = (v > 0) ? 1.7e308 : -1.7e308;
-        out[i] = v;
+    __shared__ double s_dj[UG_ROWS], s_zj[UG_ROWS];
+    __shared__ int s_id[UG_ROWS];
+    const int row0 = blockIdx.x * UG_ROWS;
+    if (threadIdx.x < UG_ROWS) {
+        const int row = row0 + threadIdx.x;
+        int id = -1;
+        if (row < c.n) {
+            // the new eigenvalues of the level (NewLambda, one thread per index) ride along with the first panel: nothing
+            // between here and the next level's z assembly reads lam
+            if (new_lambda && blockIdx.y == 0) NewLambda{c}(row);
+            id = c.node_of[row];
+            if (id >= 0) {
+                const MergeDesc& D = c.desc[id];
+                const bool top = row < D.off + D.n1;
+                const int jj = row - (top ? D.off : D.off + D.n1);
+                const int kh = top ? D.ktop : D.kbot;
+                if (jj >= kh) id = -1;
+                else {
+                    const int j = top ? c.toplist[row] : c.botlist[row];
+                    s_dj[threadIdx.x] = c.dl[D.off + j];
+                    s_zj[threadIdx.x] = c.zhat[D.off + j];
+                }
+            }
+        }
+        s_id[threadIdx.x] = id;
+    }
+    __syncthreads();
+    int cur = -1, off = 0, iend = 0;
+    for (int r0 = 0; r0 < UG_ROWS; ++r0) {            // (usually one pass: all rows of a tile belong to one merge)
+        const int id = s_id[r0];
+        if (id < 0 || id == cur) continue;
+        bool seen = false;
+        for (int q = 0; q < r0; ++q) seen = seen || (s_id[q] == id);
+        if (seen) continue;
+        cur = id;
+        const MergeDesc& D = c.desc[id];
+        off = D.off;
+        iend = min(D.k, p0 + width);
+        const double* dl = c.dl + off;
+        for (int i = p0 + blockIdx.y * 256 + threadIdx.x; i < iend; i += gridDim.y * 256) {
+            const double dorg = dl[c.org[off + i]], tau = c.tau[off + i], nrm = c.nrm[off + i];
+#pragma unroll
+            for (int r = 0; r < UG_ROWS; ++r) {
+                if (s_id[r] != id) continue;
+                double den = ((s_dj[r] - dorg) - tau) * nrm;
+                if (den == 0.0) den = 4.9e-324;
+                double v = s_zj[r] / den;
+                if (!(fabs(v) < 1.7e308)) v = (v > 0) ? 1.7e308 : -1.7e308;
+                M.B[(long)(row0 + r) * M.ldb + (i - p0)] = v;
+            }
+        }
     }
 }
 

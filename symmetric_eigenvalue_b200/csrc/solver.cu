@@ -213,7 +213,7 @@ struct Solver {
     }
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
     int resid_variant = 0;        // residual_kernel variant (0: default); env CUPPEN_RESID
-    int gemm_variant = 1;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA bulk-copy lines, 2: TMA tensor maps (gemm_tma.h); env CUPPEN_GEMM
+    int gemm_variant = 2;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA bulk-copy lines, 2: TMA tensor maps (gemm_tma.h, default); env CUPPEN_GEMM
 #if CUPPEN_CUDA
     CUtensorMap map_qa, map_apack, map_b;      // tensor maps of the two n x n buffers (either can be the pack buffer) and of the U arena
 #endif
@@ -326,7 +326,7 @@ void Solver::allocate() {
         want_p2p = G > 1 && G <= P2P_MAX && S <= P2P_MAX && comm.nccl != nullptr && !(pe && !strcmp(pe, "0"));
     }
     if (want_p2p) {
-        p2p.heap_bytes = (size_t)(5 + 2 * S + G) * (N + 64) * sizeof(double) + 64 * 256;
+        p2p.heap_bytes = (size_t)(7 + 2 * S + G) * (N + 64) * sizeof(double) + 64 * 256;
         CUDA_CHECK(cudaMalloc((void**)&p2p.heap, p2p.heap_bytes));
         CUDA_CHECK(cudaMemsetAsync(p2p.heap, 0, p2p.heap_bytes, stream));
         lam.attach(p2p.carve<double>(N + 64), N + 64);
@@ -334,6 +334,8 @@ void Solver::allocate() {
         lrow.attach(p2p.carve<double>(N + 64), N + 64);
         tau.attach(p2p.carve<double>(N + 64), N + 64);
         org.attach(p2p.carve<int>(N + 64), N + 64);
+        zhat.attach(p2p.carve<double>(N + 64), N + 64);
+        nrm.attach(p2p.carve<double>(N + 64), N + 64);
         p2p.halo_lo = p2p.carve<double>((size_t)S * N);
         p2p.halo_hi = p2p.carve<double>((size_t)S * N);
         p2p.res_part = p2p.carve<double>((size_t)G * N);
@@ -382,12 +384,15 @@ void Solver::allocate() {
         if (rv && atoi(rv) > 0) resid_variant = atoi(rv);
         const char* gv = getenv("CUPPEN_GEMM");
         if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
-        if (gv && !strcmp(gv, "tensor")) gemm_variant = 2;
+        if (gv && !strcmp(gv, "bulk")) gemm_variant = 1;
         if (gemm_variant == 2) {
+            // tensor maps of the operand buffers (35.9 vs 35.5 TFLOP/s with bulk-copy lines at 8192^3, profiles/r02_gemm_bench.txt)
             const long cols = (long)(qelems / (size_t)ldq), brows = (long)(B.n / (size_t)ldb);
             if (!tma_encode_map(&map_qa, Qa.p, ldq, cols, ldq) || !tma_encode_map(&map_apack, Apack.p, ldq, cols, ldq) ||
-                !tma_encode_map(&map_b, B.p, ldb, brows, ldb))
-                CUPPEN_THROW(CUPPEN_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUPPEN_GEMM=tensor)");
+                !tma_encode_map(&map_b, B.p, ldb, brows, ldb)) {
+                if (gv && !strcmp(gv, "tensor")) CUPPEN_THROW(CUPPEN_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUPPEN_GEMM=tensor)");
+                gemm_variant = 1;                   // no tensor maps from this driver: bulk-copy lines
+            }
         }
         cudaDeviceProp prop;
         CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -907,10 +912,27 @@ void Solver::run_level(int li) {
         // faster per launch (measured on `-s 1 -n 4096`, profiles/README.md)
         const bool tiled = L.maxm >= TILED_MIN_M;
         const dim3 tl_grid((unsigned)((L.maxm + TL_TJ - 1) / TL_TJ), (unsigned)nd_cnt);
-        if (tiled) {
-            loewner_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
+        if (tiled && coop && p2p.on) {
+            // cooperative level, peer memory: every rank computes its contiguous share of the Loewner vector and of the
+            // norms (O(k^2 / G) each instead of O(k^2) replicated) and stores it into every rank's copy
+            const int per_out = (int)round_up((L.maxm + G - 1) / G, TL_TJ);
+            const dim3 part_grid((unsigned)(per_out / TL_TJ), (unsigned)nd_cnt);
+            loewner_tiled_kernel<<<part_grid, TL_THREADS, 0, stream>>>(c, comm.rank, G, p2p.H);
             CUDA_CHECK(cudaGetLastError());
-            norms_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c);
+            g_launches.launches++;
+            pt.end(stream);
+            pt.begin(T_COMM, stream); p2p_barrier(); pt.end(stream);
+            pt.begin(T_EVX, stream);
+            norms_tiled_kernel<<<part_grid, TL_THREADS, 0, stream>>>(c, comm.rank, G, p2p.H);
+            CUDA_CHECK(cudaGetLastError());
+            g_launches.launches++;
+            pt.end(stream);
+            pt.begin(T_COMM, stream); p2p_barrier(); pt.end(stream);
+            pt.begin(T_EVX, stream);
+        } else if (tiled) {
+            loewner_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c, 0, 1, SymHeap());
+            CUDA_CHECK(cudaGetLastError());
+            norms_tiled_kernel<<<tl_grid, TL_THREADS, 0, stream>>>(c, 0, 1, SymHeap());
             CUDA_CHECK(cudaGetLastError());
             g_launches.launches += 2;
         } else {
@@ -973,7 +995,7 @@ void Solver::run_level(int li) {
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
         {
-            dim3 grid((unsigned)n, (unsigned)std::min(4, (width + 255) / 256));
+            dim3 grid((unsigned)((n + UG_ROWS - 1) / UG_ROWS), (unsigned)std::max(1, std::min(8, (std::min(width, L.maxm) + 255) / 256)));
             ugen_kernel<<<grid, 256, 0, stream>>>(c, M, p0, width, (!fused && p0 == 0) ? 1 : 0);
             CUDA_CHECK(cudaGetLastError());
         }
@@ -991,7 +1013,7 @@ void Solver::run_level(int li) {
         const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
         pt.begin(T_GEMM, stream);
 #if CUPPEN_CUDA
-        build_gemm_work_kernel<<<1, 256, sizeof(int) * 2 * nd_cnt, stream>>>(w);
+        build_gemm_work_kernel<<<1, 1024, sizeof(int) * 2 * nd_cnt, stream>>>(w);
         CUDA_CHECK(cudaGetLastError());
         const int grid = (int)std::min<long>(worst, small_tiles ? num_sms * 8L : (long)num_sms);
         if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, ntiles_dev.p, grid);

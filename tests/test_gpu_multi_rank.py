@@ -1,4 +1,4 @@
-"""N>1 on hardware: the shipped CUDA library over its NCCL path on 2 / 4 / 8 B200s of one box (one process per GPU,
+"""N>1 on hardware: the shipped CUDA library over its peer-memory / NCCL path on 2 / 3 / 4 / 8 B200s of one box (one process per GPU,
 torch.distributed.run), against the reference's goldens, the one-GPU run and the oracle.  Skipped for world sizes the
 box does not have; tests/test_multi_rank.py covers the host-side logic of the same path over gloo on CPU."""
 import os
@@ -21,7 +21,7 @@ def _free_port():
     return p
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 3, 4, 8])
 def test_sharded_solve_over_nccl(product_lib, oracle, world):
     import torch
     assert torch.cuda.is_available(), "GPU tests need a CUDA device"

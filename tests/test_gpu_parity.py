@@ -157,17 +157,20 @@ def test_gemm_kernels_against_fma_reference(lib, variant, M, N, K):
 
 
 def test_tma_and_cpasync_gemm_paths_agree(lib, oracle):
-    """Same decomposition with the TMA GEMM (default) and with the cp.async GEMM (CUPPEN_GEMM=cpasync)."""
-    D, E = oracle.goe(1500)
-    a = se.cuppens(D, E, ref_leaves=4, lib=lib)
-    os.environ["CUPPEN_GEMM"] = "cpasync"
-    try:
-        b = se.cuppens(D, E, ref_leaves=4, lib=lib)
-    finally:
-        del os.environ["CUPPEN_GEMM"]
-    assert np.array_equal(a["lam"], b["lam"])
-    assert np.abs(a["V"] - b["V"]).max() < 1e-13
-    assert np.abs(a["resid"] - b["resid"]).max() < 1e-12
+    """Same decomposition with the tensor-map TMA GEMM (default), the bulk-copy TMA GEMM (CUPPEN_GEMM=bulk) and the cp.async
+    GEMM (CUPPEN_GEMM=cpasync); n = 1501 with P = 4 gives reference leaves of 376 / 375 rows: odd row offsets."""
+    for n in (1500, 1501):
+        D, E = oracle.goe(n)
+        a = se.cuppens(D, E, ref_leaves=4, lib=lib)
+        for variant in ("bulk", "cpasync"):
+            os.environ["CUPPEN_GEMM"] = variant
+            try:
+                b = se.cuppens(D, E, ref_leaves=4, lib=lib)
+            finally:
+                del os.environ["CUPPEN_GEMM"]
+            assert np.array_equal(a["lam"], b["lam"])
+            assert np.abs(a["V"] - b["V"]).max() < 1e-13
+            assert np.abs(a["resid"] - b["resid"]).max() < 1e-12
 
 
 # ---- selected-eigenvector mode (-eFILE) ---------------------------------------------------------------
