@@ -161,7 +161,8 @@ int cuppen_select_eigenvectors(cuppen_handle h, const int* idx, int cnt);
 int cuppen_copy_selected_eigenvectors(cuppen_handle h, double* V, long ld);
 /* max_ij |(V^T V - I)_ij| of the computed eigenvector matrix, evaluated on the GPU by a DMMA Gram kernel that never
  * writes the product (BASELINE's orthogonality criterion; no counterpart in the reference, which cannot emit V).
- * One GPU, CUPPEN_FLAG_VECTORS.  seconds (may be NULL): device time of the check. */
+ * CUPPEN_FLAG_VECTORS.  seconds (may be NULL): device time of the check.  Several ranks: every rank calls; the row slices
+ * are all-gathered and every rank evaluates its share of the tiles of the Gram triangle (seconds then includes the gather). */
 int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds);
 /* Eigenvector file (binary): "CUPPENV1" | int64 n | int64 ncols | int64 rank[ncols] | double lambda[ncols] |
  * double V[ncols][n].  All n vectors (CUPPEN_FLAG_VECTORS, ascending lambda) or the selected ones (CUPPEN_FLAG_SELECT).

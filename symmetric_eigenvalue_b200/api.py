@@ -280,7 +280,8 @@ class CuppenSolver:
         return a.value, b.value
 
     def write_eigenvectors(self, filename):
-        _chk(self.lib, self.lib.cuppen_write_eigenvectors(self._h, os.fsencode(filename)))
+        """CUPPENV1 file; several ranks: every rank calls, rank 0 writes (filename may be None elsewhere)."""
+        _chk(self.lib, self.lib.cuppen_write_eigenvectors(self._h, None if filename is None else os.fsencode(filename)))
 
     def eigenvalues(self):
         out = np.empty(self.n)

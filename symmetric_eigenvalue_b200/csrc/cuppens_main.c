@@ -13,7 +13,7 @@
  *            redistribution travel through peer memory over NVLink, NCCL ships the IPC handles)
  *   -v FILE  write the computed eigenvectors (all with -e, the selected ones with -eFILE) to FILE
  *            (binary CUPPENV1 layout, include/cuppen_b200.h) -- the reference cannot emit V
- *   -c       print max|V^T V - I| of the computed eigenvectors (evaluated on the GPU; needs -e, one GPU)
+ *   -c       print max|V^T V - I| of the computed eigenvectors (evaluated on the GPUs; needs -e)
  * With -eFILE and few requested indices (count <= n/16) the library's selected-eigenvector
  * mode is used: no n x n matrix is formed (filehandling.c:339-345 computes one vector at a time too).
  */
@@ -68,7 +68,7 @@ static void showHelp(void) {
     printf(" -v FILENAME\n");
     printf("    Write the computed eigenvectors to this file (binary; needs -e).\n");
     printf(" -c\n");
-    printf("    Check the orthogonality of the computed eigenvectors (needs -e, one GPU).\n");
+    printf("    Check the orthogonality of the computed eigenvectors (needs -e).\n");
     printf("\n");
 }
 
@@ -127,10 +127,6 @@ int main(int argc, char** argv) {
         default: return 1;
     }
     if (argc - optind > 1) { fprintf(stderr, "Invalid number of positional arguments. See help.\n"); return 1; }
-    if (gpus > 1 && checkOrth) {
-        fprintf(stderr, "Option -c needs a single GPU (the rows of V are distributed over the GPUs). See help.\n");
-        return 1;
-    }
     outputfile = argv[optind];
 
     if (inputfile != NULL) printf("Input file: %s\n", inputfile);
@@ -233,6 +229,7 @@ int main(int argc, char** argv) {
     if (rank != 0) {
         /* the eigenvector file is written by rank 0 from row slices that every rank contributes */
         if (vectors && vecFile != NULL) cuppen_write_eigenvectors(h, NULL);
+        if (vectors && checkOrth) { double dev = 0, sec = 0; cuppen_orthogonality(h, &dev, &sec); }
         cuppen_destroy(h);
         _exit(0);
     }

@@ -845,64 +845,73 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
 // take a general per-row path.  `accumulate` adds to res2 (a rank holds several slices when the rows are
 // distributed).  RES_NC and the minimum resident blocks per SM are template parameters: the variants were timed
 // on the B200 (cuppen_selftest_residual, profiles/README.md) and launch_residual() picks the default.
-enum { RES_DEFAULT_VARIANT = 25 };
+enum { RES_DEFAULT_VARIANT = 25, RES_MAX_SLICES = 16 };
+// the row slices a rank holds: global rows [g0, g0+cnt) stored at local rows [l0, l0+cnt), with the rows just above /
+// below the slice (halo rows, per output column) -- one slice on one GPU, one per subtree in the multi-GPU slice layout.
+// All slices are handled by ONE launch (a launch per slice left the 256-row slices of 8 GPUs with 2 % of the work of a
+// one-GPU launch each, and the phase took longer on 4 GPUs than on one).
+struct ResSlices {
+    int ns;
+    int g0[RES_MAX_SLICES], l0[RES_MAX_SLICES], cnt[RES_MAX_SLICES];
+    const double* lo[RES_MAX_SLICES];
+    const double* hi[RES_MAX_SLICES];
+};
 template <int RES_NC, int MINB>
-__global__ void __launch_bounds__(256, MINB) residual_kernel(const double* __restrict__ V, long ldq, int n, int g0, int l0, int cnt,
+__global__ void __launch_bounds__(256, MINB) residual_kernel(const double* __restrict__ V, long ldq, int n, ResSlices S,
                                                              const double* __restrict__ OD, const double* __restrict__ OE,
                                                              const double* __restrict__ lam_sorted, const int* __restrict__ perm,
-                                                             const double* __restrict__ halo_lo, const double* __restrict__ halo_hi,
-                                                             double* __restrict__ res2, int accumulate) {
+                                                             double* __restrict__ res2) {
     const int col0 = blockIdx.x * RES_NC;
-    const int g1 = g0 + cnt;
     const int lane = threadIdx.x & 31;
     // per-column constants live in shared memory (broadcast reads) to keep the register budget for loads in flight
-    __shared__ const double* x[RES_NC];
+    __shared__ const double* xb[RES_NC];
     __shared__ double lambda[RES_NC];
-    __shared__ int s_vec_ok;
     double acc[RES_NC];
-    if (threadIdx.x == 0) s_vec_ok = 1;
-    __syncthreads();
     if (threadIdx.x < RES_NC) {
         const int col = min(col0 + (int)threadIdx.x, n - 1);      // columns past the end repeat the last one (not stored)
-        const long xoff = (long)perm[col] * ldq + l0 - g0;
-        x[threadIdx.x] = V + xoff;                                // x[c][r] = element of global row r
-        if (xoff & 1) s_vec_ok = 0;                               // 16-byte loads of (x[r], x[r+1]) with r even
+        xb[threadIdx.x] = V + (long)perm[col] * ldq;              // (ldq is even: the parity of an element's address is that of its row)
         lambda[threadIdx.x] = lam_sorted[col];
     }
     __syncthreads();
-    const bool vec_ok = s_vec_ok != 0;
 #pragma unroll
     for (int c = 0; c < RES_NC; ++c) acc[c] = 0.0;
-    for (int r = (g0 & ~1) + 2 * (int)threadIdx.x; r < g1; r += 2 * 256) {
-        if (vec_ok && r - 1 >= g0 && r + 2 < g1) {
-            // interior pair: rows r-1 .. r+2 are all inside the slice (so 0 < r and r + 1 < n - 1)
-            const double2 dv = *reinterpret_cast<const double2*>(OD + r);
-            const double2 ev = *reinterpret_cast<const double2*>(OE + r);
-            const double em = OE[r - 1];
+    for (int sl = 0; sl < S.ns; ++sl) {
+        const int g0 = S.g0[sl], g1 = g0 + S.cnt[sl];
+        const long shift = (long)S.l0[sl] - g0;                   // element of global row r = xb[c][r + shift]
+        const bool vec_ok = ((shift & 1) == 0) && ((ldq & 1) == 0);   // 16-byte loads of (x[r], x[r+1]) with r even
+        const double* halo_lo = S.lo[sl];
+        const double* halo_hi = S.hi[sl];
+        for (int r = (g0 & ~1) + 2 * (int)threadIdx.x; r < g1; r += 2 * 256) {
+            if (vec_ok && r - 1 >= g0 && r + 2 < g1) {
+                // interior pair: rows r-1 .. r+2 are all inside the slice (so 0 < r and r + 1 < n - 1)
+                const double2 dv = *reinterpret_cast<const double2*>(OD + r);
+                const double2 ev = *reinterpret_cast<const double2*>(OE + r);
+                const double em = OE[r - 1];
 #pragma unroll
-            for (int c = 0; c < RES_NC; ++c) {
-                const double* xc = x[c];
-                const double2 xv = *reinterpret_cast<const double2*>(xc + r);
-                const double xm = xc[r - 1], xp = xc[r + 2];
-                const double lam = lambda[c];
-                const double y0 = fma(dv.x - lam, xv.x, fma(em, xm, ev.x * xv.y));
-                const double y1 = fma(dv.y - lam, xv.y, fma(ev.x, xv.x, ev.y * xp));
-                acc[c] = fma(y0, y0, fma(y1, y1, acc[c]));
-            }
-        } else {
+                for (int c = 0; c < RES_NC; ++c) {
+                    const double* xc = xb[c] + shift;
+                    const double2 xv = *reinterpret_cast<const double2*>(xc + r);
+                    const double xm = xc[r - 1], xp = xc[r + 2];
+                    const double lam = lambda[c];
+                    const double y0 = fma(dv.x - lam, xv.x, fma(em, xm, ev.x * xv.y));
+                    const double y1 = fma(dv.y - lam, xv.y, fma(ev.x, xv.x, ev.y * xp));
+                    acc[c] = fma(y0, y0, fma(y1, y1, acc[c]));
+                }
+            } else {
 #pragma unroll 1
-            for (int rr = max(r, g0); rr < min(r + 2, g1); ++rr) {
-                const double dr = OD[rr];
-                const double el = (rr > 0) ? OE[rr - 1] : 0.0, eu = (rr < n - 1) ? OE[rr] : 0.0;
+                for (int rr = max(r, g0); rr < min(r + 2, g1); ++rr) {
+                    const double dr = OD[rr];
+                    const double el = (rr > 0) ? OE[rr - 1] : 0.0, eu = (rr < n - 1) ? OE[rr] : 0.0;
 #pragma unroll
-                for (int c = 0; c < RES_NC; ++c) {                  // (unrolled: acc[] must stay in registers)
-                    const int col = min(col0 + c, n - 1);
-                    const double* xc = x[c];
-                    const double xr = xc[rr];
-                    double y = (dr - lambda[c]) * xr;
-                    if (rr > 0) y = fma(el, (rr > g0) ? xc[rr - 1] : halo_lo[col], y);
-                    if (rr < n - 1) y = fma(eu, (rr + 1 < g1) ? xc[rr + 1] : halo_hi[col], y);
-                    acc[c] = fma(y, y, acc[c]);
+                    for (int c = 0; c < RES_NC; ++c) {                  // (unrolled: acc[] must stay in registers)
+                        const int col = min(col0 + c, n - 1);
+                        const double* xc = xb[c] + shift;
+                        const double xr = xc[rr];
+                        double y = (dr - lambda[c]) * xr;
+                        if (rr > 0) y = fma(el, (rr > g0) ? xc[rr - 1] : halo_lo[col], y);
+                        if (rr < n - 1) y = fma(eu, (rr + 1 < g1) ? xc[rr + 1] : halo_hi[col], y);
+                        acc[c] = fma(y, y, acc[c]);
+                    }
                 }
             }
         }
@@ -919,19 +928,16 @@ __global__ void __launch_bounds__(256, MINB) residual_kernel(const double* __res
     if (threadIdx.x < RES_NC && col0 + (int)threadIdx.x < n) {
         double sum = 0;
         for (int w = 0; w < 8; ++w) sum += red[w][threadIdx.x];
-        const int col = col0 + threadIdx.x;
-        res2[col] = accumulate ? res2[col] + sum : sum;
+        res2[col0 + threadIdx.x] = sum;
     }
 }
 
 // variant: 0 default, else NC*10 + MINB
-inline void launch_residual(Stream st, int variant, const double* V, long ldq, int n, int g0, int l0, int cnt, const double* OD,
-                            const double* OE, const double* lam_sorted, const int* perm, const double* halo_lo,
-                            const double* halo_hi, double* res2, int accumulate) {
+inline void launch_residual(Stream st, int variant, const double* V, long ldq, int n, const ResSlices& S, const double* OD,
+                            const double* OE, const double* lam_sorted, const int* perm, double* res2) {
 #define CUPPEN_RES_CASE(NC, MB)                                                                                          \
     case NC * 10 + MB:                                                                                                   \
-        residual_kernel<NC, MB><<<(unsigned)((n + NC - 1) / NC), 256, 0, st>>>(V, ldq, n, g0, l0, cnt, OD, OE, lam_sorted, \
-                                                                               perm, halo_lo, halo_hi, res2, accumulate); \
+        residual_kernel<NC, MB><<<(unsigned)((n + NC - 1) / NC), 256, 0, st>>>(V, ldq, n, S, OD, OE, lam_sorted, perm, res2); \
         break;
     switch (variant == 0 ? RES_DEFAULT_VARIANT : variant) {
         CUPPEN_RES_CASE(1, 4) CUPPEN_RES_CASE(1, 6) CUPPEN_RES_CASE(2, 4) CUPPEN_RES_CASE(2, 5) CUPPEN_RES_CASE(4, 3)

@@ -20,6 +20,22 @@ namespace cuppen {
 enum { GR_BT = 128, GR_BK = 16, GR_LDK = GR_BK + 4, GR_STAGES = 4, GR_THREADS = 256 };
 enum { GR_TILE_DOUBLES = GR_BT * GR_LDK, GR_STAGE_DOUBLES = 2 * GR_TILE_DOUBLES };
 
+// gathered row slices [rank][column][ldq] -> one column-major matrix with G*ldq rows per column (rank r's rows at
+// r*ldq, zero beyond its row count: V^T V does not care about the order of the rows)
+struct GramGather {
+    const double* gath;
+    double* V;
+    long ldq;
+    int n, G;
+    int nloc[8];
+    CUPPEN_HD void operator()(long t) const {
+        const long per_col = (long)G * ldq;
+        const long col = t / per_col, rem = t - col * per_col;
+        const int r = (int)(rem / ldq), i = (int)(rem - (long)r * ldq);
+        V[t] = (i < nloc[r]) ? gath[((long)r * n + col) * ldq + i] : 0.0;
+    }
+};
+
 #if CUPPEN_CUDA
 __device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, int src_bytes) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -59,7 +75,7 @@ __device__ __forceinline__ void gram_load_stage(double* stage, const double* __r
 }
 
 __global__ void __launch_bounds__(GR_THREADS, 1)
-gram_check_kernel(const double* __restrict__ V, long ld, int rows, int n, unsigned long long* __restrict__ result) {
+gram_check_kernel(const double* __restrict__ V, long ld, int rows, int n, unsigned long long* __restrict__ result, int part, int nparts) {
     extern __shared__ __align__(16) double gram_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wm = warp & 1, wn = warp >> 1;           // 2 (i) x 4 (j) warps, warp tile 64 x 32
@@ -69,7 +85,8 @@ gram_check_kernel(const double* __restrict__ V, long ld, int rows, int n, unsign
     const int ktiles = (rows + GR_BK - 1) / GR_BK;
     double worst = 0.0;
 
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // several GPUs: every rank holds the gathered V and takes the tiles part, part + nparts, ... of the triangle
+    for (long tile = (long)blockIdx.x * nparts + part; tile < ntiles; tile += (long)gridDim.x * nparts) {
         int ti, tj;
         gram_tile_coords(tile, T, ti, tj);
         const int i0 = ti * GR_BT, j0 = tj * GR_BT;

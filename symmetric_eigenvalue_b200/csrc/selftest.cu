@@ -179,7 +179,10 @@ int cuppen_selftest_residual(int device, int n, int variant, int g0, int l0, int
     float best = 1e30f;
     for (int rep = 0; rep < 3; ++rep) {
         CUDA_CHECK(cudaEventRecord(e0, 0));
-        launch_residual(0, variant, V.p, ldq, n, g0, l0, cnt, OD.p, OE.p, lam.p, perm.p, hlo.p, hhi.p, res.p, 0);
+        ResSlices rs;
+        memset(&rs, 0, sizeof rs);
+        rs.ns = 1; rs.g0[0] = g0; rs.l0[0] = l0; rs.cnt[0] = cnt; rs.lo[0] = hlo.p; rs.hi[0] = hhi.p;
+        launch_residual(0, variant, V.p, ldq, n, rs, OD.p, OE.p, lam.p, perm.p, res.p);
         CUDA_CHECK(cudaEventRecord(e1, 0));
         CUDA_CHECK(cudaEventSynchronize(e1));
         float ms = 0; cudaEventElapsedTime(&ms, e0, e1);

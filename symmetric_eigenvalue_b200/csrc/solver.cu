@@ -1084,15 +1084,22 @@ void Solver::finish() {
                     sl.push_back(x);
                 }
             }
-            for (size_t i = 0; i < sl.size(); ++i) {
 #if CUPPEN_CUDA
-                launch_residual(stream, resid_variant, Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p,
-                                perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
-#else
-                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
-#endif
+            if (sl.size() > RES_MAX_SLICES) CUPPEN_THROW(CUPPEN_ERR_STATE, "%zu row slices per rank (at most %d)", sl.size(), (int)RES_MAX_SLICES);
+            {
+                ResSlices rs;
+                memset(&rs, 0, sizeof rs);
+                rs.ns = (int)sl.size();
+                for (size_t i = 0; i < sl.size(); ++i) { rs.g0[i] = sl[i].g0; rs.l0[i] = sl[i].l0; rs.cnt[i] = sl[i].cnt; rs.lo[i] = sl[i].lo; rs.hi[i] = sl[i].hi; }
+                launch_residual(stream, resid_variant, Qcur, ldq, n, rs, dOD.p, dOE.p, lam_sorted.p, perm.p, res2.p);
                 g_launches.launches++;
             }
+#else
+            for (size_t i = 0; i < sl.size(); ++i) {
+                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
+                g_launches.launches++;
+            }
+#endif
             if (p2p.on) {
                 launch_items(stream, n, PushResidualPartials{p2p.H, res2.p, p2p.res_part, n});
                 p2p_barrier();
@@ -1640,33 +1647,67 @@ int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds) 
     if (!h || !max_abs_dev) CUPPEN_THROW(CUPPEN_ERR_ARG, "null argument");
     Solver& s = h->s;
     if (!s.solved || !s.want_vectors) CUPPEN_THROW(CUPPEN_ERR_STATE, "no eigenvectors (solve with CUPPEN_FLAG_VECTORS)");
-    if (s.G > 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "the orthogonality check runs on one GPU (rows of V are distributed over %d)", s.G);
+    if (s.G > 8) CUPPEN_THROW(CUPPEN_ERR_ARG, "the orthogonality check supports up to 8 ranks");
+    const int G = s.G;
+    // several ranks (every rank calls): the row slices are all-gathered, every rank evaluates its share of the tiles of
+    // the Gram triangle and the maxima are combined -- n^3 / G flop per GPU, 8 n^2 bytes received per GPU
+    DevBuf<double> gath, vfull;
+    const double* V = s.Qcur;
+    long ld = s.ldq;
+    int rows = s.nloc_final;
+    const double t_wall0 = wall_now();
+    if (G > 1) {
+        gath.alloc((size_t)G * s.n * s.ldq);
+        vfull.alloc((size_t)G * s.n * s.ldq);
+        s.comm.allgather(s.Qcur, gath.p, sizeof(double) * (size_t)s.n * s.ldq, s.stream);
+        GramGather gg;
+        gg.gath = gath.p; gg.V = vfull.p; gg.ldq = s.ldq; gg.n = s.n; gg.G = G;
+        for (int r = 0; r < G; ++r) {
+            int c = 0;
+            for (int sub = 0; sub < s.S; ++sub) c += s.slice_lo(sub, r + 1) - s.slice_lo(sub, r);
+            gg.nloc[r] = c;
+        }
+        launch_items(s.stream, (long)G * s.ldq * s.n, gg);
+        V = vfull.p; ld = (long)G * s.ldq; rows = (int)ld;
+    }
 #if CUPPEN_CUDA
     CUDA_CHECK(cudaSetDevice(s.device));
     DevBuf<unsigned long long> res;
-    res.alloc(1);
-    dev_zero(res.p, sizeof(unsigned long long), s.stream);
+    res.alloc(8);
+    dev_zero(res.p, sizeof(unsigned long long) * 8, s.stream);
     const long T = (s.n + GR_BT - 1) / GR_BT, ntiles = T * (T + 1) / 2;
     cudaEvent_t e0, e1;
     CUDA_CHECK(cudaEventCreate(&e0)); CUDA_CHECK(cudaEventCreate(&e1));
     CUDA_CHECK(cudaEventRecord(e0, s.stream));
-    gram_check_kernel<<<(unsigned)std::min<long>(ntiles, s.num_sms), GR_THREADS, gram_smem_bytes(), s.stream>>>(
-        s.Qcur, s.ldq, s.nloc_final, s.n, res.p);
+    gram_check_kernel<<<(unsigned)std::max<long>(1, std::min<long>((ntiles + G - 1) / G, s.num_sms)), GR_THREADS, gram_smem_bytes(), s.stream>>>(
+        V, ld, rows, s.n, res.p, s.comm.rank, G);
     CUDA_CHECK(cudaGetLastError());
     g_launches.launches++;
     CUDA_CHECK(cudaEventRecord(e1, s.stream));
-    unsigned long long bits = 0;
-    dev_d2h(&bits, res.p, sizeof bits, s.stream);
-    dev_sync(s.stream);
+    double worst = 0;
+    if (G > 1) {
+        DevBuf<unsigned long long> all;
+        all.alloc(G);
+        s.comm.allgather(res.p, all.p, sizeof(unsigned long long), s.stream);
+        std::vector<unsigned long long> hb(G);
+        dev_d2h(hb.data(), all.p, sizeof(unsigned long long) * G, s.stream);
+        dev_sync(s.stream);
+        for (int r = 0; r < G; ++r) { double v; memcpy(&v, &hb[r], sizeof v); worst = std::max(worst, v); }
+    } else {
+        unsigned long long bits = 0;
+        dev_d2h(&bits, res.p, sizeof bits, s.stream);
+        dev_sync(s.stream);
+        memcpy(&worst, &bits, sizeof(double));
+    }
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    memcpy(max_abs_dev, &bits, sizeof(double));
-    if (seconds) *seconds = ms * 1e-3;
+    *max_abs_dev = worst;
+    if (seconds) *seconds = (G > 1) ? wall_now() - t_wall0 : ms * 1e-3;
 #else
-    const double t0 = wall_now();
-    *max_abs_dev = gram_check_host(s.Qcur, s.ldq, s.nloc_final, s.n);
-    if (seconds) *seconds = wall_now() - t0;
+    // test-only host build: every rank evaluates the whole Gram matrix of the gathered rows
+    *max_abs_dev = gram_check_host(V, ld, rows, s.n);
+    if (seconds) *seconds = wall_now() - t_wall0;
 #endif
     CUPPEN_API_END
 }

@@ -139,6 +139,18 @@ def main():
         assert bool((cnt == 1).all()), "row ownership is not a partition"
         assert np.abs(V - single["V"][rowmap]).max() <= 1e-13
         assert np.abs(res - single["resid"]).max() <= 1e-12 + 1e-6 * single["resid"].max()
+        # -c and -v on several ranks: Gram check over the gathered row slices, eigenvector file written by rank 0
+        dev, _ = s.orthogonality()
+        want = np.abs(single["V"].T @ single["V"] - np.eye(n)).max()
+        assert abs(dev - want) <= 1e-13, (dev, want)
+        import tempfile
+        path = os.path.join(tempfile.gettempdir(), "cuppen_mr_%d_%d.bin" % (os.getppid(), n)) if rank == 0 else None
+        s.write_eigenvectors(path)
+        if rank == 0:
+            ranks, lamf, Vf = se.read_eigenvector_file(path)
+            os.unlink(path)
+            assert np.array_equal(lamf, lam) and Vf.shape == (n, n)
+            assert np.abs(Vf - single["V"]).max() <= 1e-13
     o = oracle.solve(D, E, P)
     assert np.abs(lam - o["lam"]).max() <= 1e-12 * (np.abs(D).max() + 2 * np.abs(E).max())
     s.close()
