@@ -170,6 +170,20 @@ int cuppen_orthogonality(cuppen_handle h, double* max_abs_dev, double* seconds);
 int cuppen_write_eigenvectors(cuppen_handle h, const char* filename);
 const char* cuppen_last_error(void);
 
+/* ---- dense front end (no counterpart in the reference, whose input is tridiagonal) ----------
+ * Full eigendecomposition A = Z diag(W) Z^T of a dense symmetric matrix on one GPU: blocked Householder
+ * tridiagonalisation (dsytrd / dlatrd structure, symv-bound), the tridiagonal path above under the accurate rule, and the
+ * back-transformation Z = Q V through compact-WY block reflectors (dormtr / dlarft structure, DMMA GEMMs).
+ * A: host, column-major, symmetric, ld = lda (the lower triangle is read); W[n] ascending; Z: n x n column-major, ld = ldz,
+ * or NULL for eigenvalues only; tm may be NULL. */
+typedef struct {
+    double tridiagonalise_s;      /* device time of the Householder reduction */
+    double tridiagonal_solve_s;   /* wall time of the tridiagonal eigenproblem (handle creation + solve) */
+    double tridiagonal_device_s;  /* device time of the tridiagonal solve alone */
+    double backtransform_s;       /* device time of the block-reflector back-transformation */
+} cuppen_dense_timers;
+int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, long ldz, int device, cuppen_dense_timers* tm);
+
 /* ---- host-side helpers of the CLI (no GPU involved) ------------------------------------------- */
 int cuppen_scheme(int scheme, int n, double* D, double* E);
 int cuppen_read_mtx(const char* filename, double** D, double** E, int* n);   /* callee allocates (malloc) */

@@ -34,6 +34,10 @@ class _Timers(ctypes.Structure):
                                        ("comm_mode", ctypes.c_long)]
 
 
+class _DenseTimers(ctypes.Structure):
+    _fields_ = [(k, ctypes.c_double) for k in ("tridiagonalise_s", "tridiagonal_solve_s", "tridiagonal_device_s", "backtransform_s")]
+
+
 _BCAST_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int,
                              ctypes.c_int, ctypes.c_int)
 _ALLRED_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t)
@@ -81,6 +85,7 @@ def _declare(lib):
         "cuppen_copy_selected_eigenvectors": [H, dp, ctypes.c_long],
         "cuppen_orthogonality": [H, dp, dp],
         "cuppen_write_eigenvectors": [H, ctypes.c_char_p],
+        "cuppen_dense_eigh": [ctypes.c_int, dp, ctypes.c_long, dp, dp, ctypes.c_long, ctypes.c_int, ctypes.POINTER(_DenseTimers)],
         "cuppen_scheme": [ctypes.c_int, ctypes.c_int, dp, dp],
         "cuppen_read_mtx": [ctypes.c_char_p, ctypes.POINTER(dp), ctypes.POINTER(dp), ip],
         "cuppen_read_ev_file": [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(ip), ip],
@@ -100,7 +105,7 @@ EXPORTED_SYMBOLS = (
     "cuppen_set_tridiagonal", "cuppen_solve", "cuppen_get_eigenvalues", "cuppen_get_residuals",
     "cuppen_get_merge_stats", "cuppen_get_timers", "cuppen_local_rows", "cuppen_local_row_map", "cuppen_copy_eigenvectors", "cuppen_copy_eigenvector_columns",
     "cuppen_select_eigenvectors", "cuppen_copy_selected_eigenvectors", "cuppen_orthogonality", "cuppen_write_eigenvectors",
-    "cuppen_last_error", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
+    "cuppen_last_error", "cuppen_dense_eigh", "cuppen_scheme", "cuppen_read_mtx", "cuppen_read_ev_file", "cuppen_write_results",
 )
 
 
@@ -416,6 +421,21 @@ def read_eigenvector_file(filename):
     if V.size != n * ncols:
         raise CuppenError(-2, "%s is truncated" % filename)
     return ranks, lam, V.reshape(ncols, n).T
+
+
+def dense_eigh(A, vectors=True, device=0, lib=None):
+    """Dense symmetric eigenproblem on one GPU (Householder tridiagonalisation + the tridiagonal path + back-transformation).
+    Returns (w ascending, Z or None, timers dict)."""
+    lib = lib or load_library()
+    A = np.asfortranarray(A, dtype=np.float64)
+    n = A.shape[0]
+    if A.ndim != 2 or A.shape[1] != n:
+        raise CuppenError(-1, "A must be square")
+    w = np.empty(n)
+    Z = np.empty((n, n), order="F") if vectors else None
+    t = _DenseTimers()
+    _chk(lib, lib.cuppen_dense_eigh(n, _dp(A), max(n, 1), _dp(w), _dp(Z) if vectors else None, max(n, 1), device, ctypes.byref(t)))
+    return w, Z, {f[0]: getattr(t, f[0]) for f in _DenseTimers._fields_}
 
 
 def cuppens(D, E, ref_leaves=1, vectors=True, device=0, lib=None, select=None):

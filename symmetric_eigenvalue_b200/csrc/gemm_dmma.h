@@ -25,6 +25,7 @@ struct GemmProblem {
     long lda, ldb, ldc;
     // coordinates of the same operands inside the Apack / U-arena tensors (TMA version)
     int a_row0, a_col0, b_row0, b_col0;
+    int c_sub;            // 0: C = A B (the merges), 1: C -= A B (rank-2k / block-reflector updates of the dense front end; cp.async kernels)
 };
 
 struct GemmTile { int prob, m0, n0; };
@@ -202,7 +203,7 @@ dgemm_dmma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restr
 #pragma unroll
                 for (int i = 0; i < Cfg::MI; ++i) {
                     const int mm = m0 + wm * Cfg::WM + i * 8 + lr;
-                    if (mm < P.M) ccol[mm] = acc[i][j][h];
+                    if (mm < P.M) ccol[mm] = P.c_sub ? ccol[mm] - acc[i][j][h] : acc[i][j][h];
                 }
             }
         }

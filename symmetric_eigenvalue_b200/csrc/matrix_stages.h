@@ -87,7 +87,7 @@ CUPPEN_HD void work_emit_tiles(const WorkCtx& w, const GemmProblem& Pb, int p, i
 CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
     const MergeDesc& D = w.desc[p >> 1];
     const int half = p & 1;
-    Pb.M = 0; Pb.N = 0; Pb.K = 0;
+    Pb.M = 0; Pb.N = 0; Pb.K = 0; Pb.c_sub = 0;
     if (D.k <= w.p0) return 0;
     const int hs = half ? D.off + D.n1 : D.off;                 // arena row of the half's first pole
     const int rs = half ? D.lsplit : D.lr0, re = half ? D.lr1 : D.lsplit;   // local rows of the half
@@ -126,14 +126,18 @@ __global__ void __launch_bounds__(1024) build_gemm_work_kernel(WorkCtx w) {
         if (run > w.tile_cap) *w.fail = 1;
     }
     __syncthreads();
-    // all threads write the tiles of one problem after the other (thousands of tiles per problem at the top levels;
-    // one thread per problem took ~45 us per launch, profiles/r02_ncu_launches_goe_n16384.csv)
-    for (int p = 0; p < np; ++p) {
-        const GemmProblem Pb = w.probs[p];
-        if (Pb.M == 0) continue;
-        const int cnt = ((Pb.M + w.BM - 1) / w.BM) * ((Pb.N + w.BN - 1) / w.BN), base = work_off[p];
-        for (int q = threadIdx.x; q < cnt; q += blockDim.x)
-            if (base + q < w.tile_cap) w.tiles[base + q] = work_tile_at(w, Pb, p, q);
+    // every thread writes total / blockDim tiles: the problem of a tile index is found by bisection in the prefix sums
+    // (one thread per problem took ~45 us per launch at the top levels -- thousands of tiles in two problems --, a
+    // loop over the problems ~150 us at the bottom levels -- hundreds of problems; profiles/README.md)
+    const int total = min(w.ntiles[0], w.tile_cap);
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        int lo = 0, hi = np - 1;                     // last p with work_off[p] <= t (empty problems share their successor's offset)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (work_off[mid] <= t) lo = mid; else hi = mid - 1;
+        }
+        const GemmProblem& Pb = w.probs[lo];
+        w.tiles[t] = work_tile_at(w, Pb, lo, t - work_off[lo]);
     }
 }
 #endif
@@ -275,14 +279,14 @@ struct SecularStagedEval {
 #pragma unroll 4
             for (; j < npsi; j += 32) {
                 const double t = (sm[j] - dorg) - tau;
-                const double inv = 1.0 / t;
+                const double inv = CUPPEN_RCP(t);
                 const double r = sm[cap + j] * inv;
                 psi += r; dpsi += r * inv; err += fabs(r);
             }
 #pragma unroll 4
             for (; j < cnt; j += 32) {
                 const double t = (sm[j] - dorg) - tau;
-                const double inv = 1.0 / t;
+                const double inv = CUPPEN_RCP(t);
                 const double r = sm[cap + j] * inv;
                 phi += r; dphi += r * inv; err += fabs(r);
             }
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(TL_THREADS) loewner_tiled_kernel(LevelCtx c, i
         for (int t = slice * TL_SUB; t < t1; ++t) {
             const double num = (s_lam_org[t] - dj) + s_tau[t];
             const double den = s_dl[t] - dj;
-            prod *= (i0 + t == j) ? num : num / den;
+            prod *= (i0 + t == j) ? num : num * CUPPEN_RCP(den);
         }
         __syncthreads();
     }
@@ -507,7 +511,7 @@ __global__ void __launch_bounds__(TL_THREADS) norms_tiled_kernel(LevelCtx c, int
         const int q1 = min(cnt, (slice + 1) * TL_SUB);
 #pragma unroll 4
         for (int q = slice * TL_SUB; q < q1; ++q) {
-            const double u = s_zh[q] / ((s_dl[q] - dorg) - t);
+            const double u = s_zh[q] * CUPPEN_RCP((s_dl[q] - dorg) - t);
             s = fma(u, u, s);
         }
         __syncthreads();
@@ -824,10 +828,9 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
 #pragma unroll
             for (int r = 0; r < UG_ROWS; ++r) {
                 if (s_id[r] != id) continue;
-                double den = ((s_dj[r] - dorg) - tau) * nrm;
-                if (den == 0.0) den = 4.9e-324;
-                double v = s_zj[r] / den;
-                if (!(fabs(v) < 1.7e308)) v = (v > 0) ? 1.7e308 : -1.7e308;
+                const double den = ((s_dj[r] - dorg) - tau) * nrm;
+                double v = s_zj[r] * CUPPEN_RCP(den);
+                if (!(fabs(v) < 1.7e308)) v = ((s_zj[r] < 0) != (den < 0)) ? -1.7e308 : 1.7e308;   // a root on its pole: clamp, never inf / NaN
                 M.B[(long)(row0 + r) * M.ldb + (i - p0)] = v;
             }
         }

@@ -36,6 +36,29 @@
 
 namespace cuppen {
 
+// Reciprocal for the Cauchy-like inner loops (one per pole/root pair in the secular, Loewner, norm and U kernels): the
+// hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps -- 5 FP64 instructions, < 1 ulp off the correctly rounded
+// value -- instead of the ~20-instruction IEEE division sequence with its slow-path checks, which made those kernels
+// issue-bound (profiles/r02_ncu_full_vector_kernels_goe_n16384_raw.csv).  x == 0 or subnormal gives NaN / inf: the
+// callers treat a non-finite quotient like the IEEE +-inf (a bracket step, a clamped matrix entry).
+#if CUPPEN_CUDA
+__host__ __device__ __forceinline__ double fast_rcp(double x) {
+#ifdef __CUDA_ARCH__
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+#define CUPPEN_RCP(x) ::cuppen::fast_rcp(x)
+#else
+#define CUPPEN_RCP(x) (1.0 / (x))
+#endif
+
 struct Error {
     int code;
     std::string msg;

@@ -15,6 +15,9 @@
 
 #include <math.h>
 
+#ifndef CUPPEN_RCP
+#define CUPPEN_RCP(x) (1.0 / (x))      // (platform.h supplies the 5-instruction device version)
+#endif
 #ifndef CUPPEN_HD
 #if defined(__CUDACC__)
 #define CUPPEN_HD __host__ __device__ __forceinline__
@@ -51,14 +54,14 @@ CUPPEN_HD SecularSums secular_eval(const Lanes& L, int k, const double* __restri
 #pragma unroll 4
     for (; j < split1; j += nl) {
         const double t = (d[j] - dorg) - tau;
-        const double inv = 1.0 / t;
+        const double inv = CUPPEN_RCP(t);
         const double r = w[j] * inv;
         psi += r; dpsi += r * inv; err += fabs(r);
     }
 #pragma unroll 4
     for (; j < k; j += nl) {
         const double t = (d[j] - dorg) - tau;
-        const double inv = 1.0 / t;
+        const double inv = CUPPEN_RCP(t);
         const double r = w[j] * inv;
         phi += r; dphi += r * inv; err += fabs(r);
     }

@@ -106,7 +106,7 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
     iota_rev_kernel<<<(N + 255) / 256, 256>>>(colidx.p, N);
     GemmProblem P;
     P.A = A.p + row0; P.B = Bm.p; P.C = C.p + row0; P.colidx = colidx.p; P.M = M; P.N = N; P.K = K;
-    P.lda = lda; P.ldb = ldb; P.ldc = ldc; P.a_row0 = row0; P.a_col0 = 0; P.b_row0 = 0; P.b_col0 = 0;
+    P.lda = lda; P.ldb = ldb; P.ldc = ldc; P.a_row0 = row0; P.a_col0 = 0; P.b_row0 = 0; P.b_col0 = 0; P.c_sub = 0;
     std::vector<GemmTile> ht;
     const int BM = variant == 2 ? 64 : 128, BN = BM;
     CUtensorMap mA, mB;

@@ -20,6 +20,7 @@
 #include "host_twins.h"
 #include "comm.h"
 #include "p2p.h"
+#include "dense_stages.h"
 
 namespace cuppen {
 
@@ -1804,6 +1805,144 @@ int cuppen_write_eigenvectors(cuppen_handle h, const char* filename) {
     }
     if (f) ok = (fclose(f) == 0) && ok;
     if (!ok) CUPPEN_THROW(CUPPEN_ERR_IO, "write error on %s", filename ? filename : "(null)");
+    CUPPEN_API_END
+}
+
+// Dense symmetric eigenproblem A = Z diag(W) Z^T on one GPU: blocked Householder
+// tridiagonalisation (dense_stages.h), the tridiagonal path of this library under the accurate rule, and the
+// back-transformation of its eigenvectors through the block reflectors.  A: host, column-major, symmetric (the lower
+// triangle is read); W: n eigenvalues ascending; Z (may be NULL: eigenvalues only): n x n, column-major, ld >= n.
+int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, long ldz, int device, cuppen_dense_timers* tm) {
+    CUPPEN_API_BEGIN
+    if (n < 1 || !A || !W || lda < n || (Z && ldz < n)) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
+    for (long c = 0; c < n; ++c)
+        for (long r = c; r < n; ++r)
+            if (!std::isfinite(A[c * lda + r])) CUPPEN_THROW(CUPPEN_ERR_ARG, "A(%ld,%ld) is not finite", r, c);
+#if CUPPEN_CUDA
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        CUPPEN_THROW(CUPPEN_ERR_CUDA, "no CUDA device available; libcuppen_b200 has no CPU path");
+    if (device < 0 || device >= ndev) CUPPEN_THROW(CUPPEN_ERR_ARG, "device %d out of range (%d devices)", device, ndev);
+    CUDA_CHECK(cudaSetDevice(device));
+    set_kernel_attributes();
+    cudaStream_t st;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    cuppen_handle hs = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    try {
+        for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
+        const long ldA = round_up(n, 16), ldp = round_up(n, 16) + 256;
+        DevBuf<double> dA, Vp, Wp, PW, VT, part, dots, wtmp, wpart, dd, de, dtau, Tm, W1;
+        DevBuf<int> iota, ntl;
+        DevBuf<GemmProblem> probs;
+        DevBuf<GemmTile> tiles;
+        dA.alloc((size_t)ldA * n + 1024);
+        for (DevBuf<double>* b : {&Vp, &Wp, &PW, &VT}) { b->alloc((size_t)ldp * DN_NB + 1024); dev_zero(b->p, b->bytes(), st); }
+        part.alloc((size_t)DN_SPLIT * n); dots.alloc(2 * DN_NB); wtmp.alloc((size_t)n + 256); wpart.alloc((size_t)n / 256 + 8);
+        dd.alloc((size_t)n + 8); de.alloc((size_t)n + 8); dtau.alloc((size_t)n + 8); Tm.alloc(DN_NB * DN_NB);
+        W1.alloc((size_t)DN_NB * ldp + 1024);
+        iota.alloc((size_t)n + 256); ntl.alloc(4); probs.alloc(2);
+        const long maxt = ((n + 127) / 128) * (long)((n + 127) / 128) + 1;
+        tiles.alloc((size_t)maxt);
+        dev_zero(W1.p, W1.bytes(), st);
+        dev_zero(de.p, de.bytes(), st);
+        dense_iota_kernel<<<(unsigned)((n + 256 + 255) / 256), 256, 0, st>>>(iota.p, n + 256);
+        CUDA_CHECK(cudaMemcpy2DAsync(dA.p, sizeof(double) * ldA, A, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, st));
+        dense_mirror_lower_kernel<<<dim3((unsigned)n, (unsigned)((n + 255) / 256)), 256, 0, st>>>(dA.p, ldA, n);
+        CUDA_CHECK(cudaGetLastError());
+        auto gemm_sub = [&](const double* Aop, long lda_, const double* Bop, long ldb_, double* C, long ldc_, int M, int N, int K) {
+            if (M <= 0 || N <= 0) return;
+            GemmProblem P;
+            memset(&P, 0, sizeof P);
+            P.A = Aop; P.B = Bop; P.C = C; P.colidx = iota.p; P.M = M; P.N = N; P.K = K; P.lda = lda_; P.ldb = ldb_; P.ldc = ldc_; P.c_sub = 1;
+            dense_gemm_work_kernel<<<8, 256, 0, st>>>(P, probs.p, tiles.p, ntl.p);
+            CUDA_CHECK(cudaGetLastError());
+            const long nt = (long)((M + 127) / 128) * ((N + 127) / 128);
+            launch_gemm<128, 128, 16, 2, 4, 3>(st, probs.p, tiles.p, ntl.p, std::min<long>(nt, 148L * 2));
+        };
+        // ---- tridiagonalisation ---------------------------------------------------------------------------------
+        CUDA_CHECK(cudaEventRecord(ev[0], st));
+        for (int j0 = 0; j0 < n; j0 += DN_NB) {
+            const int nb = std::min((int)DN_NB, n - j0);
+            dev_zero(Vp.p, sizeof(double) * (size_t)ldp * DN_NB, st);
+            dev_zero(Wp.p, sizeof(double) * (size_t)ldp * DN_NB, st);
+            CUDA_CHECK(cudaMemcpy2DAsync(PW.p, sizeof(double) * ldp, dA.p + (long)j0 * ldA, sizeof(double) * ldA, sizeof(double) * n, nb,
+                                         cudaMemcpyDeviceToDevice, st));
+            for (int c = 0; c < nb; ++c) {
+                const int i = j0 + c;
+                dense_house_kernel<<<1, DN_THREADS, 0, st>>>(dA.p, ldA, n, i, c, PW.p, Vp.p, ldp, dd.p, de.p, dtau.p);
+                if (i >= n - 1) break;
+                const int m = n - (i + 1), rb = (m + 255) / 256;
+                dense_symv_kernel<<<dim3((unsigned)std::max(rb, c), DN_SPLIT + 1), 256, 0, st>>>(dA.p, ldA, n, i, c, Vp.p, Wp.p, ldp, part.p, dots.p);
+                dense_w_kernel<<<rb, 256, 0, st>>>(n, i, c, part.p, dots.p, Vp.p, Wp.p, ldp, dtau.p, wtmp.p, wpart.p);
+                dense_panel_update_kernel<<<dim3((unsigned)rb, (unsigned)(nb - c)), 256, 0, st>>>(n, i, c, rb, dtau.p, wtmp.p, wpart.p, Vp.p, Wp.p, PW.p, ldp);
+            }
+            CUDA_CHECK(cudaGetLastError());
+            const int t0 = j0 + nb;
+            if (t0 < n) {
+                // trailing block (both triangles): A22 -= V W^T + W V^T ; the row-major K x N operand of the GEMM is the
+                // column-major panel of the other vector set
+                double* C = dA.p + (long)t0 * ldA + t0;
+                gemm_sub(Vp.p + t0, ldp, Wp.p + t0, ldp, C, ldA, n - t0, n - t0, DN_NB);
+                gemm_sub(Wp.p + t0, ldp, Vp.p + t0, ldp, C, ldA, n - t0, n - t0, DN_NB);
+            }
+        }
+        CUDA_CHECK(cudaEventRecord(ev[1], st));
+        std::vector<double> hd(n), he(std::max(1, n - 1));
+        dev_d2h(hd.data(), dd.p, sizeof(double) * n, st);
+        if (n > 1) dev_d2h(he.data(), de.p, sizeof(double) * (n - 1), st);
+        dev_sync(st);
+        // ---- the tridiagonal path (accurate rule on every level) -----------------------------------------------------
+        const double t_s0 = wall_now();
+        int rc = create_common(&hs, n, 1, Z ? CUPPEN_FLAG_VECTORS | CUPPEN_FLAG_NO_RESIDUALS : 0, device, Comm());
+        if (rc != 0) CUPPEN_THROW(rc, "%s", g_last_error.c_str());
+        hs->s.set_matrix(hd.data(), he.data());
+        hs->s.solve();
+        memcpy(W, hs->s.h_lam_sorted.data(), sizeof(double) * n);
+        const double t_s1 = wall_now();
+        float ms_back = 0;
+        if (Z) {
+            // ---- back-transformation Z = H_0 ... H_{n-2} V, one block reflector per panel, last panel first ----------------
+            hs->s.materialise_sorted();
+            double* Zd = hs->s.Qcur;
+            const long ldz_d = hs->s.ldq;
+            CUDA_CHECK(cudaEventRecord(ev[2], st));
+            const int last = ((n - 1) / DN_NB) * DN_NB;
+            for (int j0 = last; j0 >= 0; j0 -= DN_NB) {
+                const int nb = std::min((int)DN_NB, n - j0), row0 = j0 + 1;
+                if (row0 >= n) continue;
+                dense_extract_v_kernel<<<dim3((unsigned)((n + 255) / 256), DN_NB), 256, 0, st>>>(dA.p, ldA, n, j0, nb, Vp.p, ldp);
+                dense_larft_kernel<<<1, DN_THREADS, 0, st>>>(n, j0, nb, Vp.p, ldp, dtau.p, Tm.p);
+                dense_vt_kernel<<<(unsigned)((n - row0 + 255) / 256), 256, 0, st>>>(n, row0, nb, Vp.p, ldp, Tm.p, VT.p);
+                dense_vtz_kernel<<<(unsigned)((n + 63) / 64), 256, 0, st>>>(n, row0, n, Vp.p, ldp, Zd, ldz_d, W1.p, ldp);
+                CUDA_CHECK(cudaGetLastError());
+                gemm_sub(VT.p + row0, ldp, W1.p, ldp, Zd + row0, ldz_d, n - row0, n, DN_NB);
+            }
+            CUDA_CHECK(cudaEventRecord(ev[3], st));
+            CUDA_CHECK(cudaMemcpy2DAsync(Z, sizeof(double) * ldz, Zd, sizeof(double) * ldz_d, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st));
+            dev_sync(st);
+            cudaEventElapsedTime(&ms_back, ev[2], ev[3]);
+        }
+        float ms_tri = 0;
+        cudaEventElapsedTime(&ms_tri, ev[0], ev[1]);
+        if (tm) {
+            tm->tridiagonalise_s = ms_tri * 1e-3; tm->tridiagonal_solve_s = t_s1 - t_s0; tm->backtransform_s = ms_back * 1e-3;
+            tm->tridiagonal_device_s = hs->s.timers.device_s;
+        }
+        cuppen_destroy(hs);
+        hs = nullptr;
+    } catch (...) {
+        if (hs) cuppen_destroy(hs);
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+        cudaStreamDestroy(st);
+        throw;
+    }
+    for (auto e : ev) cudaEventDestroy(e);
+    cudaStreamDestroy(st);
+#else
+    (void)Z; (void)ldz; (void)device; (void)tm;
+    CUPPEN_THROW(CUPPEN_ERR_CUDA, "the dense front end has no host build");
+#endif
     CUPPEN_API_END
 }
 
