@@ -449,17 +449,16 @@ def run_ours(a):
     ctx.barrier()
 
     # LAPACK eigenvalues (dsterf, ~1 min at n = 65536) for the extra workloads that have no reference golden: computed
-    # on rank 0's host cores while the GPUs work
-    lapack_threads, lapack_box = {}, {}
+    # on rank 0's host cores while the GPUs work -- in a separate PROCESS (scipy's LAPACK wrappers keep the GIL: a thread
+    # would stall rank 0's solver calls and its peers would time out at the first barrier)
+    lapack_jobs, lapack_box = {}, {}
     if rank == 0 and a.extras and (world == 8 or a.big):
         for k in ("goe32k", "goe64k"):
             if load_golden(WORKLOADS[k].get("golden")) is None:
-                def _lap(k=k):
-                    from scipy.linalg import eigvalsh_tridiagonal
-                    d, e = make_matrix(WORKLOADS[k]["matrix"], WORKLOADS[k]["n"])
-                    lapack_box[k] = eigvalsh_tridiagonal(d, e)
-                lapack_threads[k] = threading.Thread(target=_lap, daemon=True)
-                lapack_threads[k].start()
+                out = os.path.join(tempfile.gettempdir(), "cuppen_bench_lapack_%s_%d.npy" % (k, os.getpid()))
+                code = ("import sys, numpy as np; sys.path.insert(0, %r); import bench; from scipy.linalg import eigvalsh_tridiagonal; "
+                        "w = bench.WORKLOADS[%r]; d, e = bench.make_matrix(w['matrix'], w['n']); np.save(%r, eigvalsh_tridiagonal(d, e))" % (ROOT, k, out))
+                lapack_jobs[k] = (subprocess.Popen([sys.executable, "-c", code], env=dict(os.environ, OMP_NUM_THREADS="4")), out)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -479,8 +478,11 @@ def run_ours(a):
         for k in names:
             w = WORKLOADS[k]
             n = w["n"]
-            if rank == 0 and k in lapack_threads:
-                lapack_threads[k].join()
+            if rank == 0 and k in lapack_jobs:
+                proc, path = lapack_jobs[k]
+                if proc.wait() == 0 and os.path.exists(path):
+                    lapack_box[k] = np.load(path)
+                    os.unlink(path)
             lap = ctx.gather_objects(lapack_box.get(k))[0]
             steps = 10 if n <= 4096 else 5 if n <= 16384 else 3 if n <= 32768 else 2
             r, _ = run_workload(ctx, w, steps, 3, 0, fp64, lapack=lap, want_solo=(n <= 32768))

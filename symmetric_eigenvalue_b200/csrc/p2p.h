@@ -98,7 +98,12 @@ struct PushHaloRows {
 #if CUPPEN_CUDA
 // One block, one thread per peer.  `flags` (heap, [P2P_MAX]) is written by the peers, `epoch` is this rank's barrier
 // counter (device memory, so that a replayed CUDA graph keeps counting).  All ranks run the same barrier sequence.
-enum { P2P_SPIN_LIMIT = 1 << 23 };
+#define P2P_TIMEOUT_NS 30000000000ull      // a peer that has not arrived after 30 s of device time is lost
+__device__ __forceinline__ unsigned long long p2p_now_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __global__ void p2p_barrier_kernel(SymHeap H, unsigned* flags, unsigned* epoch, int* fail) {
     __shared__ unsigned ep_s;
     if (threadIdx.x == 0) { ep_s = *epoch + 1; *epoch = ep_s; }
@@ -111,12 +116,13 @@ __global__ void p2p_barrier_kernel(SymHeap H, unsigned* flags, unsigned* epoch, 
     asm volatile("st.release.sys.global.u32 [%0], %1;\n" :: "l"(remote), "r"(ep) : "memory");
     const unsigned* mine = flags + r;
     unsigned v = 0;
-    int spins = 0;
+    unsigned spins = 0;
+    const unsigned long long t0 = p2p_now_ns();
     for (;;) {
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
         if ((int)(v - ep) >= 0) break;
-        if (++spins > P2P_SPIN_LIMIT || *(volatile int*)fail) { atomicCAS(fail, 0, 1 + r); break; }
-        __nanosleep(128);
+        if ((++spins & 1023u) == 0 && (*(volatile int*)fail || p2p_now_ns() - t0 > P2P_TIMEOUT_NS)) { atomicCAS(fail, 0, 1 + r); break; }
+        __nanosleep(spins < 64 ? 32 : 256);
     }
     __threadfence_system();
 }
