@@ -1,8 +1,9 @@
-// Rank-to-rank exchange of the O(n) vectors of a cooperative merge (child eigenvalues, boundary
-// rows -> z, secular root slices, residual partial sums).  Replaces the blocking MPI_Send/Recv/
-// Bcast traffic of the reference (/root/reference/src/main.c:397-417,504-542,
-// /root/reference/src/filehandling.c:347-348,415-437).  Matrix blocks never move: every rank keeps
-// its own rows of Q at every tree level.
+// Collective layer: the communicator that ships the CUDA IPC handles of the peer-memory back end (p2p.h, the default
+// on several GPUs), the all-gathers of the rarely used collective calls (eigenvector file, orthogonality check,
+// selected vectors), and the FALLBACK exchange of the O(n) vectors of a cooperative merge (child eigenvalues,
+// boundary rows -> z, secular root slices, residual partial sums) when peer memory is not available
+// (CUPPEN_P2P=0).  Replaces the blocking MPI_Send/Recv/Bcast traffic of the reference
+// (/root/reference/src/main.c:397-417,504-542, /root/reference/src/filehandling.c:347-348,415-437).
 //
 // Two back ends: NCCL over NVLink (resolved with dlopen so that single-GPU users need no NCCL),
 // or caller-supplied callbacks (the CPU tests drive those with torch.distributed/gloo).

@@ -21,7 +21,7 @@
 
 namespace cuppen {
 
-enum { DN_NB = 64, DN_SPLIT = 16, DN_THREADS = 1024 };
+enum { DN_NB = 64, DN_SPLIT = 64, DN_THREADS = 1024 };
 
 #if CUPPEN_CUDA
 __device__ __forceinline__ double dn_block_sum(double v, double* sh) {
@@ -74,15 +74,15 @@ __global__ void __launch_bounds__(DN_THREADS) dense_house_kernel(double* __restr
     if (threadIdx.x == 0) { d[i] = col[i]; e[i] = beta; tau[i] = t_i; acol[i] = col[i]; acol[i + 1] = beta; }
 }
 
-// grid (max(row blocks of 256, c), DN_SPLIT + 1):
-//   blockIdx.y < DN_SPLIT   partial sums of y = A[i+1:n, i+1:n] v over a range of columns: part[s][r]   (HBM bound)
-//   blockIdx.y == DN_SPLIT  block t < c: the dots a_t = V[:,t]^T v and b_t = W[:,t]^T v of the panel correction
+// grid (max(row blocks of 512, c), nsplit + 1), nsplit <= DN_SPLIT chosen by the host so that >= 4 blocks per SM exist:
+//   blockIdx.y < nsplit    partial sums of y = A[i+1:n, i+1:n] v over a range of columns: part[s][r]   (HBM bound)
+//   blockIdx.y == nsplit   block t < c: the dots a_t = V[:,t]^T v and b_t = W[:,t]^T v of the panel correction
 __global__ void __launch_bounds__(256) dense_symv_kernel(const double* __restrict__ A, long lda, int n, int i, int c,
                                                          const double* __restrict__ Vp, const double* __restrict__ Wp, long ldp,
                                                          double* __restrict__ part, double* __restrict__ dots) {
     const double* v = Vp + (long)c * ldp;
     __shared__ double sv[256];
-    if (blockIdx.y == DN_SPLIT) {
+    if (blockIdx.y == gridDim.y - 1) {
         const int t = blockIdx.x;
         if (t >= c) return;
         double a = 0, b = 0;
@@ -97,34 +97,54 @@ __global__ void __launch_bounds__(256) dense_symv_kernel(const double* __restric
         if (threadIdx.x == 0) { dots[t] = a; dots[DN_NB + t] = b; }
         return;
     }
-    const int r = i + 1 + blockIdx.x * 256 + threadIdx.x;
-    const int m = n - (i + 1);
-    if ((int)blockIdx.x * 256 >= m) return;
-    const int per = (m + DN_SPLIT - 1) / DN_SPLIT;
+    // two rows per thread (16-byte loads, even global row r), eight columns in flight: enough bytes in flight per SM to
+    // approach the HBM roof (one row and two columns per thread left the kernel latency-bound at ~2 TB/s)
+    const int rbase = (i + 1) & ~1;
+    const int r = rbase + 2 * (blockIdx.x * 256 + threadIdx.x);
+    const int m = n - rbase;
+    if ((int)blockIdx.x * 512 >= m) return;
+    const int nsplit = gridDim.y - 1;
+    const int mc = n - (i + 1);
+    const int per = (mc + nsplit - 1) / nsplit;
     const int c0 = i + 1 + blockIdx.y * per, c1 = min(n, c0 + per);
-    double acc0 = 0, acc1 = 0;
+    double a0[4] = {0, 0, 0, 0}, a1[4] = {0, 0, 0, 0};
+    const bool pair = (r + 1 < n) && ((lda & 1) == 0);
     for (int cb = c0; cb < c1; cb += 256) {
         const int cnt = min(256, c1 - cb);
         __syncthreads();
         if (threadIdx.x < cnt) sv[threadIdx.x] = v[cb + threadIdx.x];
         __syncthreads();
-        if (r < n) {
-            const double* a = A + (long)cb * lda + r;
-            int t = 0;
-#pragma unroll 4
-            for (; t + 1 < cnt; t += 2) {
-                acc0 = fma(a[(long)t * lda], sv[t], acc0);
-                acc1 = fma(a[(long)(t + 1) * lda], sv[t + 1], acc1);
+        if (r >= n) continue;
+        const double* a = A + (long)cb * lda + r;
+        int t = 0;
+        if (pair) {
+            for (; t + 3 < cnt; t += 4) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double2 x = *reinterpret_cast<const double2*>(a + (long)(t + u) * lda);
+                    a0[u] = fma(x.x, sv[t + u], a0[u]);
+                    a1[u] = fma(x.y, sv[t + u], a1[u]);
+                }
             }
-            if (t < cnt) acc0 = fma(a[(long)t * lda], sv[t], acc0);
+            for (; t < cnt; ++t) {
+                const double2 x = *reinterpret_cast<const double2*>(a + (long)t * lda);
+                a0[0] = fma(x.x, sv[t], a0[0]);
+                a1[0] = fma(x.y, sv[t], a1[0]);
+            }
+        } else {
+            for (; t < cnt; ++t) {
+                a0[0] = fma(a[(long)t * lda], sv[t], a0[0]);
+                if (r + 1 < n) a1[0] = fma(a[(long)t * lda + 1], sv[t], a1[0]);
+            }
         }
     }
-    if (r < n) part[(long)blockIdx.y * n + r] = acc0 + acc1;
+    if (r < n && r >= i + 1) part[(long)blockIdx.y * n + r] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+    if (r + 1 < n) part[(long)blockIdx.y * n + r + 1] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
 }
 
 // w' = tau (y - V b - W a) for the rows of this block (a_t = V[:,t]^T v, b_t = W[:,t]^T v), stored in wtmp;
 // wpart[block] = sum over the block's rows of w' v   (for alpha = -(tau/2) w'^T v)
-__global__ void __launch_bounds__(256) dense_w_kernel(int n, int i, int c, const double* __restrict__ part, const double* __restrict__ dots,
+__global__ void __launch_bounds__(256) dense_w_kernel(int n, int i, int c, int nsplit, const double* __restrict__ part, const double* __restrict__ dots,
                                                       const double* __restrict__ Vp, const double* __restrict__ Wp, long ldp,
                                                       const double* __restrict__ tau, double* __restrict__ wtmp, double* __restrict__ wpart) {
     __shared__ double sh[32];
@@ -136,7 +156,7 @@ __global__ void __launch_bounds__(256) dense_w_kernel(int n, int i, int c, const
     double wv = 0;
     if (r < n) {
         double y = 0;
-        for (int s = 0; s < DN_SPLIT; ++s) y += part[(long)s * n + r];
+        for (int s = 0; s < nsplit; ++s) y += part[(long)s * n + r];
         for (int t = 0; t < c; ++t) y -= Vp[(long)t * ldp + r] * sb[t] + Wp[(long)t * ldp + r] * sa[t];
         y *= t_i;
         wtmp[r] = y;

@@ -1,16 +1,16 @@
-// K6 (TMA version): the same contraction as gemm_dmma.h with the operand tiles staged by the TMA
-// engine: a producer warp issues bulk asynchronous copies (cp.async.bulk.shared::cluster.global
-// with mbarrier::complete_tx -> SASS UBLKCP), one 1 KiB line per k of the A tile and of the B tile,
-// into a 4-stage shared-memory ring guarded by full/empty mbarriers; eight consumer warps issue
-// mma.sync.m8n8k4.f64 (DMMA.8x8x4).  setmaxnreg moves the producer warpgroup's registers to the
-// consumers (128 accumulator registers per thread).
-//
-// Why bulk copies and not tensor maps: on this pool (driver 580.159, CUDA 12.9) every
-// cp.async.bulk.tensor (UTMALDG) launch -- including NVIDIA's canonical libcu++ pattern kept in
-// tests/probe/tma_min.cu, for FLOAT64, FLOAT32 and UINT32 maps, swizzled or not -- ends with
-// "an illegal instruction was encountered", while the non-tensor bulk copy works.  A bulk copy
-// needs 16-byte aligned lines, i.e. an even first row of the half; problems that do not satisfy
-// that (odd reference leaf sizes) run on the cp.async kernel of gemm_dmma.h instead.
+// K6 (TMA version): the same contraction as gemm_dmma.h with the operand tiles staged by the TMA engine into a
+// 4-stage shared-memory ring guarded by full/empty mbarriers; eight consumer warps issue mma.sync.m8n8k4.f64
+// (DMMA.8x8x4).  setmaxnreg moves the producer warpgroup's registers to the consumers (128 accumulator registers per
+// thread).  Two producers (template parameter):
+//   TENSOR = true   (default) one tensor-map copy per operand and stage (cp.async.bulk.tensor.2d -> SASS UTMALDG), issued
+//                   by one lane; the box {132, 16} is as wide as the padded shared-memory line, so the tile lands in
+//                   the conflict-free layout directly and tails beyond the buffer are zero-filled;
+//   TENSOR = false  32 bulk-copy lines per stage (cp.async.bulk.shared::cluster.global -> SASS UBLKCP), one 1 KiB line
+//                   per k of the A tile and of the B tile, issued by the 32 lanes of the producer warp.
+// Both need a 16-byte aligned source: tests/probe/tma_probe.cu shows that an fp64 tensor copy works with an EVEN start
+// coordinate and raises "illegal instruction" with an odd one (round 1 had only tried odd starts and concluded that
+// tensor maps were unusable; profiles/r02_tma_probe.txt).  Operands whose first row is odd (odd reference leaf sizes,
+// odd slice offsets) are therefore fetched from one row earlier and read one element further (`ashift`).
 //
 // Shared-memory layout of one stage: A tile [16 k][128 m + 4 pad] doubles, then B tile
 // [16 k][128 n + 4 pad]; the pad of 4 doubles makes the 64-bit fragment loads of mma.m8n8k4

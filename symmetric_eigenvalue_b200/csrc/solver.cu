@@ -1,8 +1,8 @@
 // libcuppen_b200: host orchestration of the divide-and-conquer tree and the C ABI
 // (include/cuppen_b200.h).  Replaces the conquer loop of the reference's main()
 // (/root/reference/src/main.c:495-664) and the back-transformation of writeResults
-// (/root/reference/src/filehandling.c:332-548): one process drives one B200; all merges of a
-// tree level are batched into the same launches.
+// (/root/reference/src/filehandling.c:332-548): one process drives one B200 (several processes / GPUs
+// cooperate through peer memory, p2p.h); all merges of a tree level are batched into the same launches.
 #include <math.h>
 #include <algorithm>
 #include <chrono>
@@ -1873,8 +1873,10 @@ int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, lo
                 dense_house_kernel<<<1, DN_THREADS, 0, st>>>(dA.p, ldA, n, i, c, PW.p, Vp.p, ldp, dd.p, de.p, dtau.p);
                 if (i >= n - 1) break;
                 const int m = n - (i + 1), rb = (m + 255) / 256;
-                dense_symv_kernel<<<dim3((unsigned)std::max(rb, c), DN_SPLIT + 1), 256, 0, st>>>(dA.p, ldA, n, i, c, Vp.p, Wp.p, ldp, part.p, dots.p);
-                dense_w_kernel<<<rb, 256, 0, st>>>(n, i, c, part.p, dots.p, Vp.p, Wp.p, ldp, dtau.p, wtmp.p, wpart.p);
+                const int rb2 = (n - ((i + 1) & ~1) + 511) / 512;                     // symv: two rows per thread
+                const int nsplit = std::max(1, std::min({(int)DN_SPLIT, (4 * 148 + rb2 - 1) / rb2, (m + 63) / 64}));
+                dense_symv_kernel<<<dim3((unsigned)std::max(rb2, c), (unsigned)(nsplit + 1)), 256, 0, st>>>(dA.p, ldA, n, i, c, Vp.p, Wp.p, ldp, part.p, dots.p);
+                dense_w_kernel<<<rb, 256, 0, st>>>(n, i, c, nsplit, part.p, dots.p, Vp.p, Wp.p, ldp, dtau.p, wtmp.p, wpart.p);
                 dense_panel_update_kernel<<<dim3((unsigned)rb, (unsigned)(nb - c)), 256, 0, st>>>(n, i, c, rb, dtau.p, wtmp.p, wpart.p, Vp.p, Wp.p, PW.p, ldp);
             }
             CUDA_CHECK(cudaGetLastError());
