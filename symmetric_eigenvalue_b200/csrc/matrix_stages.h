@@ -612,75 +612,93 @@ __global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
     }
 }
 
-// Fused front end for the small merges at the bottom of the tree: a thread-block CLUSTER of FUSE_CL CTAs per
-// merge runs every vector stage (z assembly ... new eigenvalues, and in eigenvalue-only mode the boundary-row
-// update) back to back with cluster barriers in between, instead of ~12 separate launches per level.  The stages
-// communicate through global memory (L2); the hardware cluster barrier (release/acquire at cluster scope) orders
-// it.  One CTA per merge left 3/4 of the SMs idle at these levels (32 ... 128 merges at n = 4096) and spent
-// ~20 us per level in the secular stage alone (8 roots per warp, one after the other).  Levels with more merges
-// than SMs keep one CTA per merge and plain __syncthreads (launch_fused_front) -- measured: n=4096 deflation phase
-// 0.33 -> 0.29 ms with clusters of 4, while clusters of 4 on the 512- and 256-merge levels of n=16384 cost
-// 0.85 -> 1.07 ms.
-enum { FUSE_MAXM = 128, FUSE_THREADS = 512 };
-template <int FUSE_CL>
-struct FuseSync {
-    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
-    __device__ __forceinline__ void sync() { cl.sync(); }
-};
-template <>
-struct FuseSync<1> {
-    __device__ __forceinline__ void sync() { __syncthreads(); }
-};
-template <int FUSE_CL>
-__device__ __forceinline__ void fused_front_body(LevelCtx c, RowCtx rc, int rows_mode) {
-    FuseSync<FUSE_CL> cl;
-    const int id = blockIdx.x / FUSE_CL;
+// Fused front end for the small merges at the bottom of the tree (m <= FUSE_MAXM): ONE CTA per merge runs every vector
+// stage (z assembly ... new eigenvalues, and in eigenvalue-only mode the boundary-row update) back to back, with all 23
+// per-level vectors of the merge held in SHARED memory: the stage functors of merge_stages.h run unchanged on a LevelCtx
+// whose vector pointers are redirected to shared memory (biased by -off, so that the global index g = off + j still
+// works), __syncthreads between the stages, and the vectors are copied out once at the end for the matrix kernels
+// (pack / U / GEMM) and the selected-eigenvector mode.  Round 1 ran these stages on global memory -- a cluster of 4 CTAs
+// per merge with cluster barriers, ~12 dependent round trips to L2 per level: 32 / 50 / 108 us for the levels m = 32, 64,
+// 128 of n = 4096 -- and launched ~9 separate kernels per level for m = 256 and 512.
+enum { FUSE_MAXM = 512, FUSE_THREADS = 1024, FUSE_NVEC_D = 12, FUSE_NVEC_I = 11 };
+inline size_t fused_front_smem_bytes(int mcap) { return (size_t)mcap * (FUSE_NVEC_D * sizeof(double) + FUSE_NVEC_I * sizeof(int)); }
+
+__global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, RowCtx rc, int rows_mode, int mcap) {
+    extern __shared__ __align__(16) unsigned char fuse_smem[];
+    const int id = blockIdx.x;
     const int off = c.desc[id].off, m = c.desc[id].m;
-    const int nthreads = FUSE_THREADS * FUSE_CL;
-    const int tid = (blockIdx.x % FUSE_CL) * FUSE_THREADS + threadIdx.x, warp = tid >> 5, nwarps = nthreads / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, nthreads = FUSE_THREADS, nwarps = FUSE_THREADS / 32;
+    double* sd = reinterpret_cast<double*>(fuse_smem);
+    int* si = reinterpret_cast<int*>(fuse_smem + (size_t)mcap * FUSE_NVEC_D * sizeof(double));
+    // global homes of the vectors and their shared-memory stand-ins, in the same order
+    double* gd[FUSE_NVEC_D] = {c.d, c.z, c.dn, c.zn, c.gc, c.gs, c.dl, c.wl, c.zl, c.tau, c.zhat, c.nrm};
+    int* gi[FUSE_NVEC_I] = {c.G, c.lsort, c.head, c.sup, c.prev, c.tpos, c.bpos, c.lidx, c.org, c.toplist, c.botlist};
+    LevelCtx s = c;
+    {
+        double** pd[FUSE_NVEC_D] = {&s.d, &s.z, &s.dn, &s.zn, &s.gc, &s.gs, &s.dl, &s.wl, &s.zl, &s.tau, &s.zhat, &s.nrm};
+        int** pi[FUSE_NVEC_I] = {&s.G, &s.lsort, &s.head, &s.sup, &s.prev, &s.tpos, &s.bpos, &s.lidx, &s.org, &s.toplist, &s.botlist};
+#pragma unroll
+        for (int v = 0; v < FUSE_NVEC_D; ++v) *pd[v] = sd + (size_t)v * mcap - off;
+#pragma unroll
+        for (int v = 0; v < FUSE_NVEC_I; ++v) *pi[v] = si + (size_t)v * mcap - off;
+    }
+    // (vectors that a stage reads before any stage of this level wrote them -- lsort / lidx / toplist / botlist beyond the
+    // live counts, gc / gs of unrotated entries -- keep whatever the copy-out of an earlier level left in global memory:
+    // start from the global contents so that the copy-out does not publish uninitialised shared memory)
+    for (int j = tid; j < m; j += nthreads) {
+#pragma unroll
+        for (int v = 0; v < FUSE_NVEC_D; ++v) sd[(size_t)v * mcap + j] = gd[v][off + j];
+#pragma unroll
+        for (int v = 0; v < FUSE_NVEC_I; ++v) si[(size_t)v * mcap + j] = gi[v][off + j];
+    }
+    __syncthreads();
     const WarpLanes L;
-    for (int g = off + tid; g < off + m; g += nthreads) ZAssemble{c}(g);
-    cl.sync();
-    if (warp == 0) MergeTol{c}(id, L);
-    cl.sync();
-    for (int g = off + tid; g < off + m; g += nthreads) FlagDeflate{c}(g);
-    cl.sync();
-    for (int g = off + warp; g < off + m; g += nwarps) RankLive{c}(g, L);
-    cl.sync();
-    for (int g = off + tid; g < off + m; g += nthreads) GivensSweep{c}(g);
-    cl.sync();
-    for (int g = off + warp; g < off + m; g += nwarps) Compact{c}(g, L);
-    cl.sync();
+    for (int g = off + tid; g < off + m; g += nthreads) ZAssemble{s}(g);
+    __syncthreads();
+    if (warp == 0) MergeTol{s}(id, L);
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += nthreads) FlagDeflate{s}(g);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) RankLive{s}(g, L);
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += nthreads) GivensSweep{s}(g);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) Compact{s}(g, L);
+    __syncthreads();
     {
         const MergeDesc& D = c.desc[id];
         const int k = D.k;
         for (int i = warp; i < k; i += nwarps) {
-            SecularRoot r = secular_solve(L, k, c.dl + off, c.wl + off, fabs(D.rho), D.sumw, i);
-            if (L.lane() == 0) { c.org[off + i] = r.origin; c.tau[off + i] = r.tau; }
+            SecularRoot r = secular_solve(L, k, s.dl + off, s.wl + off, fabs(D.rho), D.sumw, i);
+            if (L.lane() == 0) { s.org[off + i] = r.origin; s.tau[off + i] = r.tau; }
         }
     }
-    cl.sync();
-    for (int g = off + warp; g < off + m; g += nwarps) Loewner{c}(g, L);
-    cl.sync();
-    for (int g = off + warp; g < off + m; g += nwarps) Norms{c}(g, L);
-    cl.sync();
-    for (int g = off + tid; g < off + m; g += nthreads) NewLambda{c}(g);
-    if (!rows_mode) return;
-    cl.sync();
-    for (int g = off + tid; g < off + m; g += nthreads) RowPack{c, rc}(g);
-    cl.sync();
-    for (int g = off + warp; g < off + m; g += nwarps) RowGemv{c, rc}(g, L);
-    cl.sync();
-    for (int g = off + tid; g < off + m; g += nthreads) RowCommit{c, rc, const_cast<double*>(c.frow), const_cast<double*>(c.lrow)}(g);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) Loewner{s}(g, L);
+    __syncthreads();
+    for (int g = off + warp; g < off + m; g += nwarps) Norms{s}(g, L);
+    __syncthreads();
+    for (int g = off + tid; g < off + m; g += nthreads) NewLambda{s}(g);
+    if (rows_mode) {
+        __syncthreads();
+        for (int g = off + tid; g < off + m; g += nthreads) RowPack{s, rc}(g);
+        __syncthreads();
+        for (int g = off + warp; g < off + m; g += nwarps) RowGemv{s, rc}(g, L);
+        __syncthreads();
+        for (int g = off + tid; g < off + m; g += nthreads) RowCommit{s, rc, const_cast<double*>(c.frow), const_cast<double*>(c.lrow)}(g);
+    }
+    __syncthreads();
+    for (int j = tid; j < m; j += nthreads) {
+#pragma unroll
+        for (int v = 0; v < FUSE_NVEC_D; ++v) gd[v][off + j] = sd[(size_t)v * mcap + j];
+#pragma unroll
+        for (int v = 0; v < FUSE_NVEC_I; ++v) gi[v][off + j] = si[(size_t)v * mcap + j];
+    }
 }
-__global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, RowCtx rc, int rows_mode) { fused_front_body<1>(c, rc, rows_mode); }
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(FUSE_THREADS) fused_front_cl4_kernel(LevelCtx c, RowCtx rc, int rows_mode) { fused_front_body<4>(c, rc, rows_mode); }
 
-// a cluster of 4 CTAs per merge when one CTA per merge cannot fill the SMs (measured on the B200: -s 1 -n 4096,
-// levels of 128 / 64 / 32 merges, step 1.29 -> 1.23 ms; clusters of 8 or clusters on fuller levels were slower)
-inline void launch_fused_front(Stream st, int num_sms, int merges, LevelCtx c, RowCtx rc, int rows_mode) {
-    if (merges <= num_sms) fused_front_cl4_kernel<<<(unsigned)merges * 4, FUSE_THREADS, 0, st>>>(c, rc, rows_mode);
-    else fused_front_kernel<<<(unsigned)merges, FUSE_THREADS, 0, st>>>(c, rc, rows_mode);
+inline void launch_fused_front(Stream st, int merges, int maxm, LevelCtx c, RowCtx rc, int rows_mode) {
+    const int mcap = (maxm + 31) / 32 * 32;
+    fused_front_kernel<<<(unsigned)merges, FUSE_THREADS, fused_front_smem_bytes(mcap), st>>>(c, rc, rows_mode, mcap);
     CUDA_CHECK(cudaGetLastError());
 }
 

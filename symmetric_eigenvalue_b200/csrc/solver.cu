@@ -311,6 +311,7 @@ static void set_kernel_attributes() {
     CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
     CUDA_CHECK(cudaFuncSetAttribute(dgemm_tma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tma_smem_bytes()));
     CUDA_CHECK(cudaFuncSetAttribute(secular_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * SEC_SMEM_K * sizeof(double))));
+    CUDA_CHECK(cudaFuncSetAttribute(fused_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fused_front_smem_bytes(FUSE_MAXM)));
     CUDA_CHECK(cudaFuncSetAttribute(gram_check_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gram_smem_bytes()));
 #endif
 }
@@ -845,7 +846,7 @@ void Solver::run_level(int li) {
     if (fused) {
 #if CUPPEN_CUDA
         pt.begin(T_DEFL, stream);
-        launch_fused_front(stream, num_sms, nd_cnt, c, rowc, want_vectors ? 0 : 1);
+        launch_fused_front(stream, nd_cnt, L.maxm, c, rowc, want_vectors ? 0 : 1);
         g_launches.launches++;
         pt.end(stream);
 #endif
