@@ -104,9 +104,9 @@ CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
 }
 
 #if CUPPEN_CUDA
-// one block; shared memory: 2*nd ints (tile offsets)
-__global__ void __launch_bounds__(1024) build_gemm_work_kernel(WorkCtx w) {
-    extern __shared__ int work_off[];
+// one block (any size); work_off: 2*nd ints of shared memory (tile offsets).  Runs as the extra last block of ugen_kernel:
+// the work list only needs the descriptors, which are final once the vector front end of the level is done.
+__device__ __forceinline__ void build_gemm_work_body(const WorkCtx& w, int* work_off) {
     __shared__ int misaligned;
     const int np = 2 * w.nd;
     if (threadIdx.x == 0) misaligned = 0;
@@ -139,6 +139,10 @@ __global__ void __launch_bounds__(1024) build_gemm_work_kernel(WorkCtx w) {
         const GemmProblem& Pb = w.probs[lo];
         w.tiles[t] = work_tile_at(w, Pb, lo, t - work_off[lo]);
     }
+}
+__global__ void __launch_bounds__(1024) build_gemm_work_kernel(WorkCtx w) {
+    extern __shared__ int work_off_smem[];
+    build_gemm_work_body(w, work_off_smem);
 }
 #endif
 
@@ -352,6 +356,9 @@ __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int
 enum { CS_THREADS = 1024 };
 __global__ void __launch_bounds__(CS_THREADS) compact_scan_kernel(LevelCtx c) {
     MergeDesc& D = c.desc[blockIdx.x];
+    // the Givens sweep of this merge first (segment heads walk their segments; was a launch of its own)
+    for (int p = threadIdx.x; p < D.m; p += CS_THREADS) GivensSweep{c}(D.off + p);
+    __syncthreads();
     const int off = D.off, nl = D.nlive1, n1 = D.n1;
     const int* ls = c.lsort + off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -619,8 +626,10 @@ __global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
 // works), __syncthreads between the stages, and the vectors are copied out once at the end for the matrix kernels
 // (pack / U / GEMM) and the selected-eigenvector mode.  Round 1 ran these stages on global memory -- a cluster of 4 CTAs
 // per merge with cluster barriers, ~12 dependent round trips to L2 per level: 32 / 50 / 108 us for the levels m = 32, 64,
-// 128 of n = 4096 -- and launched ~9 separate kernels per level for m = 256 and 512.
-enum { FUSE_MAXM = 512, FUSE_THREADS = 1024, FUSE_NVEC_D = 12, FUSE_NVEC_I = 11 };
+// 128 of n = 4096; the shared-memory version takes 26 / 38 / 71 us (profiles/r02_ncu_launches_s1_n4096_fused_smem_512.csv).
+// One CTA per merge stops paying at m = 256 (124 us against ~80 us for the separate kernels, whose O(m^2) stages spread
+// over many CTAs) and m = 512 (186 us), so the fused path ends at m = 128.
+enum { FUSE_MAXM = 128, FUSE_THREADS = 1024, FUSE_NVEC_D = 12, FUSE_NVEC_I = 11 };
 inline size_t fused_front_smem_bytes(int mcap) { return (size_t)mcap * (FUSE_NVEC_D * sizeof(double) + FUSE_NVEC_I * sizeof(int)); }
 
 __global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, RowCtx rc, int rows_mode, int mcap) {
@@ -801,9 +810,14 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
 // flight per thread, rows written as coalesced 2 KB segments.  (The first version spent four dependent L2 loads per
 // element -- dl[org[i]], tau[i], nrm[i] -- on one row per block: 2 TB/s; profiles/README.md.)
 enum { UG_ROWS = 8 };
-__global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width, int new_lambda) {
+__global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width, int new_lambda, WorkCtx w) {
+    extern __shared__ int ugen_dyn_smem[];
     __shared__ double s_dj[UG_ROWS], s_zj[UG_ROWS];
     __shared__ int s_id[UG_ROWS];
+    if (blockIdx.x == gridDim.x - 1) {               // the extra block: GEMM work list of this level and panel (was a launch of its own)
+        if (blockIdx.y == 0) build_gemm_work_body(w, ugen_dyn_smem);
+        return;
+    }
     const int row0 = blockIdx.x * UG_ROWS;
     if (threadIdx.x < UG_ROWS) {
         const int row = row0 + threadIdx.x;

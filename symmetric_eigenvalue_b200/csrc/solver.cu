@@ -867,9 +867,11 @@ void Solver::run_level(int li) {
 #else
         launch_warps(stream, n, RankLive{c});
 #endif
+#if !CUPPEN_CUDA
         launch_items(stream, n, GivensSweep{c});
+#endif
 #if CUPPEN_CUDA
-        compact_scan_kernel<<<(unsigned)nd_cnt, CS_THREADS, 0, stream>>>(c);
+        compact_scan_kernel<<<(unsigned)nd_cnt, CS_THREADS, 0, stream>>>(c);          // (Givens sweep + compaction)
         CUDA_CHECK(cudaGetLastError());
         g_launches.launches++;
 #else
@@ -994,11 +996,17 @@ void Solver::run_level(int li) {
     const int BMN = small_tiles ? 64 : 128;
     for (int p0 = 0; p0 < L.maxm && L.maxm_rows > 0; p0 += W) {
         const int width = std::min(W, L.maxm - p0);
+        WorkCtx w;
+        w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN;
+        w.ldq = ldq; w.ldb = ldb; w.Apack = Awork; w.B = B.p; w.Qnext = Qcur; w.lidx = lidx.p;
+        w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
+        w.fail = fail.p + FAIL_TILES;
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
         {
-            dim3 grid((unsigned)((n + UG_ROWS - 1) / UG_ROWS), (unsigned)std::max(1, std::min(8, (std::min(width, L.maxm) + 255) / 256)));
-            ugen_kernel<<<grid, 256, 0, stream>>>(c, M, p0, width, (!fused && p0 == 0) ? 1 : 0);
+            // (+1 block: the GEMM work list of the panel is built by the last block of the same launch)
+            dim3 grid((unsigned)((n + UG_ROWS - 1) / UG_ROWS) + 1, (unsigned)std::max(1, std::min(8, (std::min(width, L.maxm) + 255) / 256)));
+            ugen_kernel<<<grid, 256, sizeof(int) * 2 * nd_cnt, stream>>>(c, M, p0, width, (!fused && p0 == 0) ? 1 : 0, w);
             CUDA_CHECK(cudaGetLastError());
         }
 #else
@@ -1007,16 +1015,9 @@ void Solver::run_level(int li) {
         g_launches.launches++;
         pt.end(stream);
 
-        WorkCtx w;
-        w.desc = c.desc; w.nd = nd_cnt; w.p0 = p0; w.width = width; w.BM = BMN; w.BN = BMN;
-        w.ldq = ldq; w.ldb = ldb; w.Apack = Awork; w.B = B.p; w.Qnext = Qcur; w.lidx = lidx.p;
-        w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
-        w.fail = fail.p + FAIL_TILES;
         const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
         pt.begin(T_GEMM, stream);
 #if CUPPEN_CUDA
-        build_gemm_work_kernel<<<1, 1024, sizeof(int) * 2 * nd_cnt, stream>>>(w);
-        CUDA_CHECK(cudaGetLastError());
         const int grid = (int)std::min<long>(worst, small_tiles ? num_sms * 8L : (long)num_sms);
         if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, ntiles_dev.p, grid);
         else if (gemm_variant == 2)
@@ -1027,8 +1028,9 @@ void Solver::run_level(int li) {
         (void)worst;
         build_gemm_work_host(w);
         gemm_host(probs.p, tiles.p, ntiles_dev.p, BMN, BMN);
+        g_launches.launches++;
 #endif
-        g_launches.launches += 2;
+        g_launches.launches++;
         pt.end(stream);
     }
 
