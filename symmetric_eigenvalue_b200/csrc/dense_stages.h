@@ -12,7 +12,7 @@
 //                   dense_w_kernel              w' = tau (A22 v - V W^T v - W V^T v) and the partial sums of w'^T v
 //                   dense_panel_update_kernel   w = w' - (tau/2)(w'^T v) v; rank-2 update of the remaining panel columns
 //   per panel:      A22 -= [V W] [W V]^T                                  -> the DMMA GEMM of gemm_dmma.h (subtract epilogue)
-// Back-transformation, panels in reverse: T (dense_larft_kernel), VT = V T (dense_vt_kernel), W1 = V^T Z
+// Back-transformation, panels in reverse: V^T V (dense_gram_kernel), T (dense_larft_kernel), VT = V T (dense_vt_kernel), W1 = V^T Z
 // (dense_vtz_kernel), Z -= VT W1 (DMMA GEMM, subtract epilogue).
 #ifndef CUPPEN_DENSE_STAGES_H
 #define CUPPEN_DENSE_STAGES_H
@@ -188,28 +188,66 @@ __global__ void __launch_bounds__(256) dense_panel_update_kernel(int n, int i, i
     *p -= vr * wc + wr * vc;
 }
 
+// Partial Gram matrices of a panel: block b sums V[r, :]^T V[r, :] over its rows r (DN_GRAM_ROWS each) into
+// Gp[b][q][t] (64 x 64, row-major).  256 threads, thread (tx, ty) of 16 x 16 owns a 4 x 4 patch; rows go through shared
+// memory 32 at a time.  (The first version computed the 2016 dot products of dlarft one after the other inside a single
+// block: 6 ms per panel, 0.67 s of back-transformation at n = 8192.)
+enum { DN_GRAM_ROWS = 512 };
+__global__ void __launch_bounds__(256) dense_gram_kernel(int n, int row0, const double* __restrict__ Vp, long ldp, double* __restrict__ Gp) {
+    __shared__ double sV[32][DN_NB + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int r_begin = row0 + blockIdx.x * DN_GRAM_ROWS, r_end = min(n, r_begin + DN_GRAM_ROWS);
+    double acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int rb = r_begin; rb < r_end; rb += 32) {
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 32 * DN_NB; idx += 256) {
+            const int rr = idx & 31, q = idx >> 5;
+            sV[rr][q] = (rb + rr < r_end) ? Vp[(long)q * ldp + rb + rr] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+            double va[4], vb[4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) va[a] = sV[rr][ty * 4 + a];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) vb[b] = sV[rr][tx * 4 + b];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) acc[a][b] = fma(va[a], vb[b], acc[a][b]);
+        }
+    }
+    double* g = Gp + (size_t)blockIdx.x * DN_NB * DN_NB;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) g[(ty * 4 + a) * DN_NB + tx * 4 + b] = acc[a][b];
+}
+
 // T factor of the block reflector H = I - V T V^T of a panel of nb reflectors (dlarft, forward, columnwise):
-// T[t,t] = tau_t ; T[0:t, t] = -tau_t T[0:t, 0:t] (V[:, 0:t]^T v_t).  One block; T is nb x nb, column-major, ld = DN_NB.
-__global__ void __launch_bounds__(DN_THREADS) dense_larft_kernel(int n, int j0, int nb, const double* __restrict__ Vp, long ldp,
+// T[t,t] = tau_t ; T[0:t, t] = -tau_t T[0:t, 0:t] (V[:, 0:t]^T v_t), with V^T V summed from the partial Gram matrices in a
+// fixed order.  One block; T is nb x nb, column-major, ld = DN_NB.
+__global__ void __launch_bounds__(DN_THREADS) dense_larft_kernel(int j0, int nb, int nparts, double* __restrict__ Gp,
                                                                  const double* __restrict__ tau, double* __restrict__ T) {
-    __shared__ double sh[32];
     __shared__ double sT[DN_NB][DN_NB + 1];
-    __shared__ double sg[DN_NB];
-    for (int idx = threadIdx.x; idx < DN_NB * (DN_NB + 1); idx += blockDim.x) (&sT[0][0])[idx] = 0.0;
+    double* sG = Gp + (size_t)nparts * DN_NB * DN_NB;          // the summed Gram matrix goes to the slot after the partial ones
+    for (int idx = threadIdx.x; idx < DN_NB * DN_NB; idx += blockDim.x) {
+        double g = 0;
+        for (int b = 0; b < nparts; ++b) g += Gp[(size_t)b * DN_NB * DN_NB + idx];
+        sG[idx] = g;
+        sT[idx / DN_NB][idx % DN_NB] = 0.0;
+    }
     __syncthreads();
     for (int t = 0; t < nb; ++t) {
         const double tt = tau[j0 + t];
-        const double* vt = Vp + (long)t * ldp;
-        for (int q = 0; q < t; ++q) {                 // g[q] = V[:, q]^T v_t  (rows j0+t+1 .. n-1: v_t is zero above)
-            double a = 0;
-            for (int r = j0 + t + 1 + threadIdx.x; r < n; r += blockDim.x) a = fma(Vp[(long)q * ldp + r], vt[r], a);
-            a = dn_block_sum(a, sh);
-            if (threadIdx.x == 0) sg[q] = a;
-        }
-        __syncthreads();
-        if (threadIdx.x < t) {                        // T[0:t, t] = -tau_t * T[0:t, 0:t] g   (T upper triangular)
+        if (threadIdx.x < t) {                        // T[0:t, t] = -tau_t * T[0:t, 0:t] G[0:t, t]   (T upper triangular)
             double s = 0;
-            for (int q = threadIdx.x; q < t; ++q) s += sT[threadIdx.x][q] * sg[q];
+            for (int q = threadIdx.x; q < t; ++q) s += sT[threadIdx.x][q] * sG[q * DN_NB + t];
             sT[threadIdx.x][t] = -tt * s;
         }
         if (threadIdx.x == 0) sT[t][t] = tt;

@@ -87,6 +87,7 @@ inline void secular_host(LevelCtx c, int ndesc, int part, int nparts) {
         for (int i = i0; i < i1; ++i) {
             SecularRoot r = secular_solve(L, k, c.dl + D.off, c.wl + D.off, fabs(D.rho), D.sumw, i);
             c.org[D.off + i] = r.origin;
+            c.dorgv[D.off + i] = c.dl[D.off + r.origin];
             c.tau[D.off + i] = r.tau;
         }
     }

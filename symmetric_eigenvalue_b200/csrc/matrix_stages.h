@@ -311,11 +311,11 @@ struct SecularStagedEval {
 };
 
 // several GPUs, peer-memory back end: the root is stored into every peer's (origin, tau) arrays as well (H.G > 0)
-__device__ __forceinline__ void secular_store(const LevelCtx& c, const SymHeap& H, long g, const SecularRoot& r) {
-    c.org[g] = r.origin; c.tau[g] = r.tau;
+__device__ __forceinline__ void secular_store(const LevelCtx& c, const SymHeap& H, long g, const SecularRoot& r, double dorg) {
+    c.org[g] = r.origin; c.tau[g] = r.tau; c.dorgv[g] = dorg;
     for (int p = 0; p < H.G; ++p) {
         if (p == H.me) continue;
-        H.at(p, c.org)[g] = r.origin; H.at(p, c.tau)[g] = r.tau;
+        H.at(p, c.org)[g] = r.origin; H.at(p, c.tau)[g] = r.tau; H.at(p, c.dorgv)[g] = dorg;
     }
 }
 
@@ -337,13 +337,13 @@ __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int
         __syncthreads();
         if (i >= i1) return;
         SecularRoot r = secular_solve(L, k, sec_smem, sec_smem + kcap, fabs(D.rho), D.sumw, i);
-        if (L.lane() == 0) secular_store(c, H, D.off + i, r);
+        if (L.lane() == 0) secular_store(c, H, D.off + i, r, sec_smem[r.origin]);
         return;
     }
     const SecularStagedEval ev{dl, wl, k, kcap, sec_smem};
     if (i < i1) {
         SecularRoot r = secular_solve_ev(ev, k, dl, wl, fabs(D.rho), D.sumw, i);
-        if (L.lane() == 0) secular_store(c, H, D.off + i, r);
+        if (L.lane() == 0) secular_store(c, H, D.off + i, r, dl[r.origin]);
     }
     ev.drain();
 }
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, R
     extern __shared__ __align__(16) unsigned char fuse_smem[];
     const int id = blockIdx.x;
     const int off = c.desc[id].off, m = c.desc[id].m;
-    const int tid = threadIdx.x, warp = tid >> 5, nthreads = FUSE_THREADS, nwarps = FUSE_THREADS / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, nthreads = blockDim.x, nwarps = blockDim.x / 32;
     double* sd = reinterpret_cast<double*>(fuse_smem);
     int* si = reinterpret_cast<int*>(fuse_smem + (size_t)mcap * FUSE_NVEC_D * sizeof(double));
     // global homes of the vectors and their shared-memory stand-ins, in the same order
@@ -679,7 +679,7 @@ __global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, R
         const int k = D.k;
         for (int i = warp; i < k; i += nwarps) {
             SecularRoot r = secular_solve(L, k, s.dl + off, s.wl + off, fabs(D.rho), D.sumw, i);
-            if (L.lane() == 0) { s.org[off + i] = r.origin; s.tau[off + i] = r.tau; }
+            if (L.lane() == 0) { s.org[off + i] = r.origin; s.tau[off + i] = r.tau; c.dorgv[off + i] = s.dl[off + r.origin]; }
         }
     }
     __syncthreads();
@@ -705,9 +705,11 @@ __global__ void __launch_bounds__(FUSE_THREADS) fused_front_kernel(LevelCtx c, R
     }
 }
 
-inline void launch_fused_front(Stream st, int merges, int maxm, LevelCtx c, RowCtx rc, int rows_mode) {
+// few merges: all 1024 threads on each (latency); more merges than SMs: smaller CTAs so that several are resident per SM
+inline void launch_fused_front(Stream st, int num_sms, int merges, int maxm, LevelCtx c, RowCtx rc, int rows_mode) {
     const int mcap = (maxm + 31) / 32 * 32;
-    fused_front_kernel<<<(unsigned)merges, FUSE_THREADS, fused_front_smem_bytes(mcap), st>>>(c, rc, rows_mode, mcap);
+    const int threads = merges <= num_sms ? FUSE_THREADS : (merges <= 2 * num_sms ? 512 : 256);
+    fused_front_kernel<<<(unsigned)merges, threads, fused_front_smem_bytes(mcap), st>>>(c, rc, rows_mode, mcap);
     CUDA_CHECK(cudaGetLastError());
 }
 
@@ -809,7 +811,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
 // constants sit in shared memory -- one division and 8 stored bytes per element, UG_ROWS independent divisions in
 // flight per thread, rows written as coalesced 2 KB segments.  (The first version spent four dependent L2 loads per
 // element -- dl[org[i]], tau[i], nrm[i] -- on one row per block: 2 TB/s; profiles/README.md.)
-enum { UG_ROWS = 8 };
+enum { UG_ROWS = 8, UG_COLS = 4 };
 __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0, int width, int new_lambda, WorkCtx w) {
     extern __shared__ int ugen_dyn_smem[];
     __shared__ double s_dj[UG_ROWS], s_zj[UG_ROWS];
@@ -854,16 +856,30 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
         const MergeDesc& D = c.desc[id];
         off = D.off;
         iend = min(D.k, p0 + width);
-        const double* dl = c.dl + off;
-        for (int i = p0 + blockIdx.y * 256 + threadIdx.x; i < iend; i += gridDim.y * 256) {
-            const double dorg = dl[c.org[off + i]], tau = c.tau[off + i], nrm = c.nrm[off + i];
+        // UG_COLS columns per thread and pass: their (origin pole, tau, norm) -- three independent coalesced loads each -- are
+        // all issued before the first division, so a block pays the L2 latency once per pass instead of once per column
+        // (with a dependent gather dl[org[i]] on top, the first version was latency-bound at 3.2 TB/s)
+        const int stride = gridDim.y * 256;
+        for (int ib = p0 + blockIdx.y * 256 + threadIdx.x; ib < iend; ib += UG_COLS * stride) {
+            double dorg[UG_COLS], tau[UG_COLS], nrm[UG_COLS];
 #pragma unroll
-            for (int r = 0; r < UG_ROWS; ++r) {
-                if (s_id[r] != id) continue;
-                const double den = ((s_dj[r] - dorg) - tau) * nrm;
-                double v = s_zj[r] * CUPPEN_RCP(den);
-                if (!(fabs(v) < 1.7e308)) v = ((s_zj[r] < 0) != (den < 0)) ? -1.7e308 : 1.7e308;   // a root on its pole: clamp, never inf / NaN
-                M.B[(long)(row0 + r) * M.ldb + (i - p0)] = v;
+            for (int u = 0; u < UG_COLS; ++u) {
+                const int i = ib + u * stride;
+                const int ii = i < iend ? i : iend - 1;
+                dorg[u] = c.dorgv[off + ii]; tau[u] = c.tau[off + ii]; nrm[u] = c.nrm[off + ii];
+            }
+#pragma unroll
+            for (int u = 0; u < UG_COLS; ++u) {
+                const int i = ib + u * stride;
+                if (i >= iend) break;
+#pragma unroll
+                for (int r = 0; r < UG_ROWS; ++r) {
+                    if (s_id[r] != id) continue;
+                    const double den = ((s_dj[r] - dorg[u]) - tau[u]) * nrm[u];
+                    double v = s_zj[r] * CUPPEN_RCP(den);
+                    if (!(fabs(v) < 1.7e308)) v = ((s_zj[r] < 0) != (den < 0)) ? -1.7e308 : 1.7e308;   // a root on its pole: clamp, never inf / NaN
+                    M.B[(long)(row0 + r) * M.ldb + (i - p0)] = v;
+                }
             }
         }
     }

@@ -76,6 +76,8 @@ struct LevelCtx {
     int* lidx;             // local index of the element
     int* org;              // secular root: origin pole (canonical index)
     double* tau;           // secular root: lambda = dl[org] + tau
+    double* dorgv;         // dl[org] of every root, stored next to (org, tau) by the root finder so that the U kernel reads
+                           // three independent coalesced vectors instead of a dependent gather per column
     double* zhat;          // Loewner vector
     double* nrm;           // column norms
     int* toplist;          // [n] off+t        -> canonical index of the t-th top-supported live column

@@ -116,7 +116,7 @@ struct Solver {
     double scale = 1.0;
     DevBuf<double> dDm, dE, dOD, dOE;
     DevBuf<double> lam, lam_sorted, frow, lrow, frow2, lrow2, fpack, lpack;
-    DevBuf<double> d, z, dn, zn, gc, gs, dl, wl, zl, tau, zhat, nrm, res2, halo, halo_all;
+    DevBuf<double> d, z, dn, zn, gc, gs, dl, wl, zl, tau, dorgv, zhat, nrm, res2, halo, halo_all;
     DevBuf<int> G_, lsort, head, sup, prev, tpos, bpos, lidx, org, toplist, botlist, perm, fail;
     // selected-eigenvector mode: the per-level scratch vectors above get one slice per level (stride
     // lvl_stride) so that every level's U stays defined after the solve
@@ -328,13 +328,14 @@ void Solver::allocate() {
         want_p2p = G > 1 && G <= P2P_MAX && S <= P2P_MAX && comm.nccl != nullptr && !(pe && !strcmp(pe, "0"));
     }
     if (want_p2p) {
-        p2p.heap_bytes = (size_t)(7 + 2 * S + G) * (N + 64) * sizeof(double) + 64 * 256;
+        p2p.heap_bytes = (size_t)(8 + 2 * S + G) * (N + 64) * sizeof(double) + 64 * 256;
         CUDA_CHECK(cudaMalloc((void**)&p2p.heap, p2p.heap_bytes));
         CUDA_CHECK(cudaMemsetAsync(p2p.heap, 0, p2p.heap_bytes, stream));
         lam.attach(p2p.carve<double>(N + 64), N + 64);
         frow.attach(p2p.carve<double>(N + 64), N + 64);
         lrow.attach(p2p.carve<double>(N + 64), N + 64);
         tau.attach(p2p.carve<double>(N + 64), N + 64);
+        dorgv.attach(p2p.carve<double>(N + 64), N + 64);
         org.attach(p2p.carve<int>(N + 64), N + 64);
         zhat.attach(p2p.carve<double>(N + 64), N + 64);
         nrm.attach(p2p.carve<double>(N + 64), N + 64);
@@ -351,7 +352,7 @@ void Solver::allocate() {
     // scratch vectors of a level: shared by all levels, or one slice per level in selected-eigenvector mode
     lvl_stride = N + 64;
     lvl_cap = select_mode ? (int)plan.by_height.size() + 1 : 1;
-    for (DevBuf<double>* b : {&d, &z, &dn, &zn, &gc, &gs, &dl, &wl, &zl, &tau, &zhat, &nrm})
+    for (DevBuf<double>* b : {&d, &z, &dn, &zn, &gc, &gs, &dl, &wl, &zl, &tau, &dorgv, &zhat, &nrm})
         if (b->p == nullptr) b->alloc(lvl_stride * lvl_cap);
     for (DevBuf<int>* b : {&G_, &lsort, &head, &sup, &prev, &tpos, &bpos, &lidx, &org, &toplist, &botlist})
         if (b->p == nullptr) b->alloc(lvl_stride * lvl_cap);
@@ -565,7 +566,7 @@ LevelCtx Solver::level_ctx(int li) {
     c.ldqz = ldq;
     c.d = d.p + o; c.z = z.p + o; c.dn = dn.p + o; c.zn = zn.p + o; c.G = G_.p + o; c.gc = gc.p + o; c.gs = gs.p + o; c.lsort = lsort.p + o;
     c.head = head.p + o; c.sup = sup.p + o; c.prev = prev.p + o; c.tpos = tpos.p + o; c.bpos = bpos.p + o; c.dl = dl.p + o; c.wl = wl.p + o; c.zl = zl.p + o;
-    c.lidx = lidx.p + o; c.org = org.p + o; c.tau = tau.p + o; c.zhat = zhat.p + o; c.nrm = nrm.p + o; c.toplist = toplist.p + o;
+    c.lidx = lidx.p + o; c.org = org.p + o; c.tau = tau.p + o; c.dorgv = dorgv.p + o; c.zhat = zhat.p + o; c.nrm = nrm.p + o; c.toplist = toplist.p + o;
     c.botlist = botlist.p + o;
     return c;
 }
@@ -846,7 +847,7 @@ void Solver::run_level(int li) {
     if (fused) {
 #if CUPPEN_CUDA
         pt.begin(T_DEFL, stream);
-        launch_fused_front(stream, nd_cnt, L.maxm, c, rowc, want_vectors ? 0 : 1);
+        launch_fused_front(stream, num_sms, nd_cnt, L.maxm, c, rowc, want_vectors ? 0 : 1);
         g_launches.launches++;
         pt.end(stream);
 #endif
@@ -1835,7 +1836,7 @@ int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, lo
     try {
         for (auto& e : ev) CUDA_CHECK(cudaEventCreate(&e));
         const long ldA = round_up(n, 16), ldp = round_up(n, 16) + 256;
-        DevBuf<double> dA, Vp, Wp, PW, VT, part, dots, wtmp, wpart, dd, de, dtau, Tm, W1;
+        DevBuf<double> dA, Vp, Wp, PW, VT, part, dots, wtmp, wpart, dd, de, dtau, Tm, W1, Gp;
         DevBuf<int> iota, ntl;
         DevBuf<GemmProblem> probs;
         DevBuf<GemmTile> tiles;
@@ -1844,6 +1845,7 @@ int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, lo
         part.alloc((size_t)DN_SPLIT * n); dots.alloc(2 * DN_NB); wtmp.alloc((size_t)n + 256); wpart.alloc((size_t)n / 256 + 8);
         dd.alloc((size_t)n + 8); de.alloc((size_t)n + 8); dtau.alloc((size_t)n + 8); Tm.alloc(DN_NB * DN_NB);
         W1.alloc((size_t)DN_NB * ldp + 1024);
+        Gp.alloc((size_t)((n + DN_GRAM_ROWS - 1) / DN_GRAM_ROWS + 1) * DN_NB * DN_NB);
         iota.alloc((size_t)n + 256); ntl.alloc(4); probs.alloc(2);
         const long maxt = ((n + 127) / 128) * (long)((n + 127) / 128) + 1;
         tiles.alloc((size_t)maxt);
@@ -1917,7 +1919,9 @@ int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, lo
                 const int nb = std::min((int)DN_NB, n - j0), row0 = j0 + 1;
                 if (row0 >= n) continue;
                 dense_extract_v_kernel<<<dim3((unsigned)((n + 255) / 256), DN_NB), 256, 0, st>>>(dA.p, ldA, n, j0, nb, Vp.p, ldp);
-                dense_larft_kernel<<<1, DN_THREADS, 0, st>>>(n, j0, nb, Vp.p, ldp, dtau.p, Tm.p);
+                const int gparts = (n - row0 + DN_GRAM_ROWS - 1) / DN_GRAM_ROWS;
+                dense_gram_kernel<<<gparts, 256, 0, st>>>(n, row0, Vp.p, ldp, Gp.p);
+                dense_larft_kernel<<<1, DN_THREADS, 0, st>>>(j0, nb, gparts, Gp.p, dtau.p, Tm.p);
                 dense_vt_kernel<<<(unsigned)((n - row0 + 255) / 256), 256, 0, st>>>(n, row0, nb, Vp.p, ldp, Tm.p, VT.p);
                 dense_vtz_kernel<<<(unsigned)((n + 63) / 64), 256, 0, st>>>(n, row0, n, Vp.p, ldp, Zd, ldz_d, W1.p, ldp);
                 CUDA_CHECK(cudaGetLastError());
