@@ -1006,7 +1006,11 @@ void Solver::run_level(int li) {
 #if CUPPEN_CUDA
         {
             // (+1 block: the GEMM work list of the panel is built by the last block of the same launch)
-            dim3 grid((unsigned)((n + UG_ROWS - 1) / UG_ROWS) + 1, (unsigned)std::max(1, std::min(8, (std::min(width, L.maxm) + 255) / 256)));
+            // column chunks per row tile: enough blocks to fill the SMs a few times over, but no more -- a block's prologue
+            // (node -> descriptor -> K list -> pole, four dependent L2 round trips) is amortised over its columns
+            const int row_tiles = (n + UG_ROWS - 1) / UG_ROWS;
+            const int ychunks = std::max(1, std::min({8, (std::min(width, L.maxm) + 255) / 256, (12 * num_sms + row_tiles - 1) / row_tiles}));
+            dim3 grid((unsigned)row_tiles + 1, (unsigned)ychunks);
             ugen_kernel<<<grid, 256, sizeof(int) * 2 * nd_cnt, stream>>>(c, M, p0, width, (!fused && p0 == 0) ? 1 : 0, w);
             CUDA_CHECK(cudaGetLastError());
         }
@@ -1035,11 +1039,14 @@ void Solver::run_level(int li) {
         pt.end(stream);
     }
 
-    if (c.Qz == nullptr) launch_items(stream, n, ExtractRows{c, Qcur, ldq, frow.p, lrow.p, (coop && p2p.on) ? p2p.H : SymHeap()});
+    // (the boundary rows are pushed to the peers only when another level follows: a push after the last barrier of a solve
+    // could land in a heap that its owner is already tearing down)
+    const bool more_levels = li + 1 < (int)levels.size();
+    if (c.Qz == nullptr) launch_items(stream, n, ExtractRows{c, Qcur, ldq, frow.p, lrow.p, (coop && p2p.on && more_levels) ? p2p.H : SymHeap()});
     if (coop && p2p.on) {
         // (first rows were pushed by rank 0, last rows by rank G-1, straight from the GEMM output)
-        if (li + 1 < (int)levels.size()) { pt.begin(T_COMM, stream); p2p_barrier(); pt.end(stream); }
-    } else if (coop && li + 1 < (int)levels.size()) {
+        if (more_levels) { pt.begin(T_COMM, stream); p2p_barrier(); pt.end(stream); }
+    } else if (coop && more_levels) {
         // first rows live on rank 0, last rows on rank G-1 (slice layout): replicate them for the next level
         comm.group_bcast(frow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), 0, 0, G, stream);
         comm.group_bcast(lrow.p + lo_idx, sizeof(double) * (hi_idx - lo_idx), G - 1, 0, G, stream);
