@@ -716,7 +716,7 @@ inline void launch_fused_front(Stream st, int num_sms, int merges, int maxm, Lev
 // K5a: walk every rotation chain once per row.  grid.x = global column, grid.y = row chunk.
 // Columns without a rotation (z-deflated, or live and unrotated: the common cases) take a fast path
 // that issues the loads of all PACK_ROWS rows before the stores.
-enum { PACK_THREADS = 128, PACK_ROWS = 4 };
+enum { PACK_THREADS = 128, PACK_ROWS = 8 };
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M) {
     const int g = blockIdx.x;
     const int id = c.node_of[g];

@@ -383,3 +383,20 @@ def test_hostemu_power_of_two_scaling_is_exact(hostemu, oracle, expo):
     assert np.array_equal(out["V"], base["V"])
     assert np.allclose(out["resid"], base["resid"] * f, rtol=1e-12, atol=0)
     assert [(x.m, x.offset, x.zdefl, x.givens) for x in out["stats"]] == [(x.m, x.offset, x.zdefl, x.givens) for x in base["stats"]]
+
+
+def test_cli_rejects_non_finite_and_missing_entries(product_lib, tmp_path):
+    """an .mtx file that omits a sub-diagonal entry (the reader pre-filled E with NaN) or holds a literal nan
+    must stop at the CLI's input checks (src/main.c:196-200 asserts on zero entries) instead of reaching the solver."""
+    exe = os.path.join(ROOT, "cuppens")
+    p = tmp_path / "gap.mtx"
+    # 3 x 3, the (3,2)/(2,3) pair is missing: that entry of the matrix is zero
+    p.write_text("%%MatrixMarket matrix coordinate real general\n3 3 5\n1 1 2\n2 1 -1\n1 2 -1\n2 2 2\n3 3 2\n")
+    D, E = se.readSymmTriadiagonalMatrixFromSparseMTX(str(p), lib=product_lib)
+    assert E.tolist() == [-1.0, 0.0]
+    r = subprocess.run([exe, "-i", str(p)], capture_output=True, text=True)
+    assert r.returncode != 0 and "Assertion `E[i] != 0' failed" in r.stderr
+    q = tmp_path / "nan.mtx"
+    q.write_text("%%MatrixMarket matrix coordinate real general\n2 2 4\n1 1 nan\n2 1 -1\n1 2 -1\n2 2 2\n")
+    r = subprocess.run([exe, "-i", str(q)], capture_output=True, text=True)
+    assert r.returncode == 2 and "not finite" in r.stdout
