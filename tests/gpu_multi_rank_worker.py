@@ -118,7 +118,7 @@ def run_case(rank, world, local, case):
             assert np.abs(Vs.T @ Vs - np.eye(len(sel))).max() < 1e-12
     t = s.timers()
     s.close()
-    return "ok launches=%d" % t["kernel_launches"]
+    return "ok launches=%d backend=%d" % (t["kernel_launches"], t["comm_mode"])
 
 
 def main():

@@ -303,3 +303,17 @@ def test_select_mode_against_reference_efile_goldens(lib, name):
     g = load_golden(name)
     out = se.cuppens(g["D"], g["E"], ref_leaves=g["P"], lib=lib, select=(g["sel"] - 1).tolist())
     check_select_against_efile_golden(g, out)
+
+
+def test_eigenvector_columns(lib, oracle):
+    """cuppen_copy_eigenvector_columns (gather_sel_cols_kernel) against the full copy, before and after the sorted gather."""
+    D, E = oracle.goe(1300)
+    s = se.CuppenSolver(1300, ref_leaves=4, lib=lib)
+    s.set_tridiagonal(D, E)
+    s.solve()
+    idx = [1299, 0, 7, 7, 650]
+    a = s.eigenvector_columns(idx)
+    V = s.eigenvectors()
+    b = s.eigenvector_columns(idx)
+    s.close()
+    assert np.array_equal(a, V[:, idx]) and np.array_equal(b, V[:, idx])

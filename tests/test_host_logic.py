@@ -400,3 +400,21 @@ def test_cli_rejects_non_finite_and_missing_entries(product_lib, tmp_path):
     q.write_text("%%MatrixMarket matrix coordinate real general\n2 2 4\n1 1 nan\n2 1 -1\n1 2 -1\n2 2 2\n")
     r = subprocess.run([exe, "-i", str(q)], capture_output=True, text=True)
     assert r.returncode == 2 and "not finite" in r.stdout
+
+
+def test_hostemu_eigenvector_columns(hostemu, oracle):
+    """cuppen_copy_eigenvector_columns: the listed columns (ascending-lambda ranks, any order, duplicates) of V, before and
+    after the sorted copy has been materialised."""
+    D, E = oracle.goe(180)
+    s = se.CuppenSolver(180, ref_leaves=2, lib=hostemu)
+    s.set_tridiagonal(D, E)
+    s.solve()
+    idx = [179, 0, 5, 5, 90]
+    a = s.eigenvector_columns(idx)              # storage order + permutation
+    V = s.eigenvectors()                        # materialises the sorted copy
+    b = s.eigenvector_columns(idx)
+    assert np.array_equal(a, V[:, idx]) and np.array_equal(b, V[:, idx])
+    with pytest.raises(se.CuppenError) as ei:
+        s.eigenvector_columns([180])
+    assert ei.value.code == -1
+    s.close()
