@@ -52,7 +52,7 @@ struct WorkCtx {
     const int* lidx;
     GemmProblem* probs;     // [2*nd]
     GemmTile* tiles;
-    int* ntiles;            // [0] tile count, [1] number of problems whose lines are not 16-byte aligned
+    int* ntiles;            // [0] tile count, [1] number of problems with an odd first row (the TMA kernels fetch those from one row earlier)
     int tile_cap;
     int* fail;              // set to 1 when the level needs more than tile_cap tiles (the solve then reports an error)
 };

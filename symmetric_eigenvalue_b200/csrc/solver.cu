@@ -231,7 +231,7 @@ struct Solver {
         int height = 0;
         bool coop = false;
         int maxm = 0, maxm_rows = 0;
-        bool any_accurate = false, aligned = true;
+        bool any_accurate = false;
         long worst_tiles_big = 0, worst_tiles_small = 0;
     };
     std::vector<LevelInfo> levels;
@@ -698,7 +698,6 @@ void Solver::prepare_levels() {
             for (int half = 0; half < 2; ++half) {
                 const int rs = half ? D.lsplit : D.lr0, re = half ? D.lr1 : D.lsplit;
                 if (re <= rs) continue;
-                if (rs & 1) L.aligned = false;
                 L.worst_tiles_big += (long)((re - rs + 127) / 128) * ((N + 127) / 128);
                 L.worst_tiles_small += (long)((re - rs + 63) / 64) * ((N + 63) / 64);
             }
@@ -1859,7 +1858,8 @@ int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, lo
         dev_zero(W1.p, W1.bytes(), st);
         dev_zero(de.p, de.bytes(), st);
         dense_iota_kernel<<<(unsigned)((n + 256 + 255) / 256), 256, 0, st>>>(iota.p, n + 256);
-        CUDA_CHECK(cudaMemcpy2DAsync(dA.p, sizeof(double) * ldA, A, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, st));
+        if (lda == ldA) CUDA_CHECK(cudaMemcpyAsync(dA.p, A, sizeof(double) * (size_t)lda * n, cudaMemcpyHostToDevice, st));     // one contiguous block
+        else CUDA_CHECK(cudaMemcpy2DAsync(dA.p, sizeof(double) * ldA, A, sizeof(double) * lda, sizeof(double) * n, n, cudaMemcpyHostToDevice, st));
         dense_mirror_lower_kernel<<<dim3((unsigned)n, (unsigned)((n + 255) / 256)), 256, 0, st>>>(dA.p, ldA, n);
         CUDA_CHECK(cudaGetLastError());
         auto gemm_sub = [&](const double* Aop, long lda_, const double* Bop, long ldb_, double* C, long ldc_, int M, int N, int K) {
@@ -1935,7 +1935,8 @@ int cuppen_dense_eigh(int n, const double* A, long lda, double* W, double* Z, lo
                 gemm_sub(VT.p + row0, ldp, W1.p, ldp, Zd + row0, ldz_d, n - row0, n, DN_NB);
             }
             CUDA_CHECK(cudaEventRecord(ev[3], st));
-            CUDA_CHECK(cudaMemcpy2DAsync(Z, sizeof(double) * ldz, Zd, sizeof(double) * ldz_d, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st));
+            if (ldz == ldz_d) CUDA_CHECK(cudaMemcpyAsync(Z, Zd, sizeof(double) * (size_t)ldz * n, cudaMemcpyDeviceToHost, st));
+            else CUDA_CHECK(cudaMemcpy2DAsync(Z, sizeof(double) * ldz, Zd, sizeof(double) * ldz_d, sizeof(double) * n, n, cudaMemcpyDeviceToHost, st));
             dev_sync(st);
             cudaEventElapsedTime(&ms_back, ev[2], ev[3]);
         }
