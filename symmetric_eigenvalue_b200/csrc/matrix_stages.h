@@ -57,12 +57,14 @@ struct WorkCtx {
     int* fail;              // set to 1 when the level needs more than tile_cap tiles (the solve then reports an error)
 };
 
-// Tile order of one problem: super-columns of `nsw` n-tiles whose B panel (K x nsw*BN doubles) fits
-// in a third of the 126 MB L2, all m-tiles inside a super-column, n fastest -- so B is read from
-// DRAM once and A once per super-column instead of B once per m-tile.
+// Tile order of one problem: super-columns of `nsw` n-tiles, all m-tiles inside a super-column, n fastest -- so B is
+// read from DRAM about once and A once per super-column instead of B once per m-tile.  nsw: the B panel (K x nsw*BN
+// doubles) takes at most ~3/4 of the 126 MB L2 (14 n-tiles at K = 6.7k): the 148 tiles in flight then cover about
+// a 11 x 14 block of (A strip, B strip) pairs instead of 25 x 6 (ncu at n=16384, K=6.7k, nsw=6: 24 GB of DRAM traffic for
+// 4.3 GB of operands, profiles/traffic.json).
 CUPPEN_HD int work_supercol(const WorkCtx& w, const GemmProblem& Pb) {
     const int ntn = (Pb.N + w.BN - 1) / w.BN;
-    long nsw = (48L << 20) / ((long)(Pb.K > 0 ? Pb.K : 1) * 8 * w.BN);
+    long nsw = (96L << 20) / ((long)(Pb.K > 0 ? Pb.K : 1) * 8 * w.BN);
     if (nsw < 1) nsw = 1;
     return nsw < ntn ? (int)nsw : ntn;
 }
