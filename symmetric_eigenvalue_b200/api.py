@@ -142,7 +142,7 @@ def nccl_unique_id(lib=None):
 # ---- test / bench only: lib/libcuppen_selftest.so (csrc/selftest.cu, csrc/cuppen_selftest.h) --------------------
 _SELFTEST = None
 SELFTEST_SYMBOLS = ("cuppen_measure_fp64_peak", "cuppen_measure_fp64_mix", "cuppen_selftest_gemm", "cuppen_selftest_residual",
-                    "cuppen_selftest_last_error")
+                    "cuppen_selftest_rcp", "cuppen_selftest_last_error")
 
 
 def selftest_library_path():
@@ -161,7 +161,8 @@ def load_selftest_library():
         i = ctypes.c_int
         for name, args in {"cuppen_measure_fp64_peak": [i, i, dp, dp], "cuppen_measure_fp64_mix": [i, dp, dp, dp, dp],
                            "cuppen_selftest_gemm": [i, i, i, i, i, i, dp, dp],
-                           "cuppen_selftest_residual": [i, i, i, i, i, i, dp, dp]}.items():
+                           "cuppen_selftest_residual": [i, i, i, i, i, i, dp, dp],
+                           "cuppen_selftest_rcp": [i, ctypes.c_long, dp, dp, dp]}.items():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = ctypes.c_int
@@ -206,6 +207,14 @@ def selftest_residual(n, g0, l0, cnt, variant=0, device=0):
     e, t = ctypes.c_double(0), ctypes.c_double(0)
     _chk_st(lib, lib.cuppen_selftest_residual(device, n, variant, g0, l0, cnt, ctypes.byref(e), ctypes.byref(t)))
     return e.value, t.value
+
+
+def selftest_rcp(count=1 << 24, device=0):
+    """(max |1 - x*seed|, max ulps off 1/x with two Newton steps, with the cubic step) of the kernels' reciprocal."""
+    lib = load_selftest_library()
+    v = [ctypes.c_double(0) for _ in range(3)]
+    _chk_st(lib, lib.cuppen_selftest_rcp(device, count, *[ctypes.byref(x) for x in v]))
+    return tuple(x.value for x in v)
 
 
 class CuppenSolver:

@@ -24,6 +24,10 @@ int cuppen_selftest_gemm(int device, int variant, int M, int N, int K, int reps,
  * loop.  variant: 0 = the default, else 10*columns-per-block + min-blocks-per-SM.  seconds (may be NULL): best of 3. */
 int cuppen_selftest_residual(int device, int n, int variant, int g0, int l0, int cnt, double* max_rel_err, double* seconds);
 
+/* Reciprocal of the Cauchy-like inner loops (platform.h) on `count` random operands: max |1 - x*seed| of the hardware
+ * seed, and the max distance in ulps from the correctly rounded 1/x of the two-Newton-step and of the cubic-step form. */
+int cuppen_selftest_rcp(int device, long count, double* seed_max_rel_err, double* newton2_max_ulp, double* cubic_max_ulp);
+
 const char* cuppen_selftest_last_error(void);
 
 #ifdef __cplusplus

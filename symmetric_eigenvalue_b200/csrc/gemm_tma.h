@@ -79,6 +79,25 @@ __device__ __forceinline__ void tma_tensor_load(void* dst, const CUtensorMap* ma
                  :: "r"(smem_u32(dst)), "l"(map), "r"(c_in), "r"(c_out), "r"(smem_u32(bar)) : "memory");
 }
 
+// The same copy with an L2 eviction-priority hint (createpolicy): in the super-column tile order the B panel is re-used by
+// every m-tile of the super-column, so its lines are loaded `evict_last`; the C tile is written with streaming stores so
+// that 0.9 GB of output per half does not push the panel out of the L2 (`hints` kernel argument; large merges only --
+// on small ones the output SHOULD stay in L2 for the next kernel).
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;\n" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void tma_tensor_load_hint(void* dst, const CUtensorMap* map, int c_in, int c_out, uint64_t* bar, uint64_t pol) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;\n"
+                 :: "r"(smem_u32(dst)), "l"(map), "r"(c_in), "r"(c_out), "r"(smem_u32(bar)), "l"(pol) : "memory");
+}
+
 // Operand tiles whose first row is odd (odd reference leaf sizes, odd slice offsets): a TMA copy needs a 16-byte
 // aligned source, so the A lines are fetched from one row earlier (`ashift` = 1: 130 doubles per line instead of 128;
 // the 4 pad doubles of the shared-memory line absorb them) and the consumers read their fragments one element further.
@@ -88,7 +107,7 @@ __device__ __forceinline__ void tma_tensor_load(void* dst, const CUtensorMap* ma
 template <bool TENSOR>
 __global__ void __launch_bounds__(TMA_THREADS, 1)
 dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restrict__ tiles, const int* __restrict__ ntiles_ptr, int* abort_flags,
-                 const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB) {
+                 const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int hints) {
     extern __shared__ __align__(128) double tma_smem[];
     uint64_t* full = (uint64_t*)(tma_smem + TMA_STAGES * TMA_STAGE_DOUBLES);
     uint64_t* empty = full + TMA_STAGES;
@@ -117,6 +136,20 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
             if (TENSOR) {
                 if (lane != 0) continue;
                 const int ain = P.a_row0 + T.m0 - ashift, bin = P.b_col0 + T.n0;
+                if (hints) {
+                    // hints & 1: B panel evict_last; hints & 2: A strips evict_first
+                    const uint64_t polB = l2_policy_evict_last(), polA = l2_policy_evict_first();
+                    for (int kt = 0; kt < ktiles; ++kt) {
+                        if (!mbar_wait(&empty[stage], phase ^ 1, 0, stage, tile, kt, abort_flags)) return;
+                        mbar_expect_tx(&full[stage], 2 * TMA_TILE_DOUBLES * 8);
+                        double* st = tma_smem + stage * TMA_STAGE_DOUBLES;
+                        if (hints & 2) tma_tensor_load_hint(st, &mapA, ain, P.a_col0 + kt * TMA_BK, &full[stage], polA);
+                        else tma_tensor_load(st, &mapA, ain, P.a_col0 + kt * TMA_BK, &full[stage]);
+                        tma_tensor_load_hint(st + TMA_TILE_DOUBLES, &mapB, bin, P.b_row0 + kt * TMA_BK, &full[stage], polB);
+                        if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
+                    }
+                    continue;
+                }
                 for (int kt = 0; kt < ktiles; ++kt) {
                     if (!mbar_wait(&empty[stage], phase ^ 1, 0, stage, tile, kt, abort_flags)) return;
                     mbar_expect_tx(&full[stage], 2 * TMA_TILE_DOUBLES * 8);
@@ -199,7 +232,10 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int mm = T.m0 + wm * 64 + i * 8 + lr;
-                    if (mm < P.M) ccol[mm] = acc[i][j][h];
+                    if (mm < P.M) {
+                        if (hints) __stcs(&ccol[mm], acc[i][j][h]);      // streaming: the output must not evict the B panel
+                        else ccol[mm] = acc[i][j][h];
+                    }
                 }
             }
         }
@@ -232,12 +268,12 @@ inline bool tma_encode_map(CUtensorMap* map, const double* base, long inner, lon
 // (the >48 KB dynamic shared memory opt-in is a per-device attribute: set_kernel_attributes() in solver.cu)
 // mapA / mapB == nullptr: bulk-copy lines; else one tensor copy per operand and stage through the two maps
 inline void launch_gemm_tma(Stream s, const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, int grid, int* abort_flags,
-                            const CUtensorMap* mapA = nullptr, const CUtensorMap* mapB = nullptr) {
+                            const CUtensorMap* mapA = nullptr, const CUtensorMap* mapB = nullptr, int hints = 0) {
     if (grid < 1) return;
-    if (mapA && mapB) dgemm_tma_kernel<true><<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags, *mapA, *mapB);
+    if (mapA && mapB) dgemm_tma_kernel<true><<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags, *mapA, *mapB, hints);
     else {
         static const CUtensorMap none = {};
-        dgemm_tma_kernel<false><<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags, none, none);
+        dgemm_tma_kernel<false><<<grid, TMA_THREADS, tma_smem_bytes(), s>>>(probs, tiles, ntiles_ptr, abort_flags, none, none, 0);
     }
     CUDA_CHECK(cudaGetLastError());
 }

@@ -55,16 +55,18 @@ struct WorkCtx {
     int* ntiles;            // [0] tile count, [1] number of problems with an odd first row (the TMA kernels fetch those from one row earlier)
     int tile_cap;
     int* fail;              // set to 1 when the level needs more than tile_cap tiles (the solve then reports an error)
+    int supercol_mb;        // L2 budget (MiB) of the B panel of one super-column (work_supercol)
 };
 
 // Tile order of one problem: super-columns of `nsw` n-tiles, all m-tiles inside a super-column, n fastest -- so B is
 // read from DRAM about once and A once per super-column instead of B once per m-tile.  nsw: the B panel (K x nsw*BN
-// doubles) takes at most ~3/4 of the 126 MB L2 (14 n-tiles at K = 6.7k): the 148 tiles in flight then cover about
-// a 11 x 14 block of (A strip, B strip) pairs instead of 25 x 6 (ncu at n=16384, K=6.7k, nsw=6: 24 GB of DRAM traffic for
-// 4.3 GB of operands, profiles/traffic.json).
+// doubles) takes at most `supercol_mb` MiB of the L2 -- 48 by default (6 n-tiles at K = 6.7k).  Measured with ncu on the
+// top merge of GOE n=16384 (4.3 GB of operand bytes): 48 MiB -> 24.1 GB of DRAM traffic; 96 MiB (14 n-tiles, fewer passes
+// over A) -> 28.7 GB: a 96 MiB panel does not stay resident in the 126 MB L2 (two partitions, C write-allocates), so B
+// is re-read as well (profiles/README.md, r02 call I).  CUPPEN_SUPERCOL_MB overrides the budget.
 CUPPEN_HD int work_supercol(const WorkCtx& w, const GemmProblem& Pb) {
     const int ntn = (Pb.N + w.BN - 1) / w.BN;
-    long nsw = (96L << 20) / ((long)(Pb.K > 0 ? Pb.K : 1) * 8 * w.BN);
+    long nsw = ((long)w.supercol_mb << 20) / ((long)(Pb.K > 0 ? Pb.K : 1) * 8 * w.BN);
     if (nsw < 1) nsw = 1;
     return nsw < ntn ? (int)nsw : ntn;
 }
@@ -586,9 +588,13 @@ __global__ void __launch_bounds__(TL_THREADS) rowgemv_tiled_kernel(LevelCtx c, R
 
 // RankLive (stable enumeration sort, merge_stages.h) in the same tiled shape: a thread owns one
 // element and one slice of every staged chunk of keys; z-deflated entries are staged as NaN (never "before").
+// One DSETP per pair: the tie-break by index is decided per CHUNK -- keys staged from indices below the CTA's outputs
+// count with `<=`, keys from above with `<`, only the chunk that contains the outputs pays the full (d, index)
+// comparison -- and the live total is counted while staging, not per pair (round 1 issued three DSETPs per pair and
+// was bound by them, VERDICT weak #4).
 __global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
     __shared__ double s_d[TL_RC];
-    __shared__ int s_cnt[TL_SL][TL_TJ], s_tot[TL_SL][TL_TJ];
+    __shared__ int s_cnt[TL_SL][TL_TJ], s_tot[TL_THREADS / 32];
     MergeDesc& D = c.desc[blockIdx.y];
     const int m = D.m, off = D.off;
     const int j0 = blockIdx.x * TL_TJ;
@@ -599,25 +605,45 @@ __global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
     int cnt = 0, tot = 0;
     for (int t0 = 0; t0 < m; t0 += TL_RC) {
         const int n_here = min((int)TL_RC, m - t0);
-        for (int t = threadIdx.x; t < n_here; t += TL_THREADS)
-            s_d[t] = (c.G[off + t0 + t] != -2) ? c.d[off + t0 + t] : __longlong_as_double(0x7ff8000000000000LL);
+        for (int t = threadIdx.x; t < n_here; t += TL_THREADS) {
+            const bool live = c.G[off + t0 + t] != -2;
+            s_d[t] = live ? c.d[off + t0 + t] : __longlong_as_double(0x7ff8000000000000LL);
+            tot += live ? 1 : 0;
+        }
         __syncthreads();
         const int t1 = min(n_here, (slice + 1) * TL_SUB);
+        if (t0 + n_here <= j0) {                     // every staged index is below every output of this CTA
 #pragma unroll 4
-        for (int t = slice * TL_SUB; t < t1; ++t) {
-            const double dt = s_d[t];
-            cnt += ((dt < dj) || (dt == dj && t0 + t < j)) ? 1 : 0;
-            tot += (dt == dt) ? 1 : 0;
+            for (int t = slice * TL_SUB; t < t1; ++t) cnt += (s_d[t] <= dj) ? 1 : 0;
+        } else if (t0 >= j0 + TL_TJ) {               // every staged index is above
+#pragma unroll 4
+            for (int t = slice * TL_SUB; t < t1; ++t) cnt += (s_d[t] < dj) ? 1 : 0;
+        } else {
+#pragma unroll 4
+            for (int t = slice * TL_SUB; t < t1; ++t) {
+                const double dt = s_d[t];
+                cnt += ((dt < dj) || (dt == dj && t0 + t < j)) ? 1 : 0;
+            }
         }
         __syncthreads();
     }
-    s_cnt[slice][out] = cnt; s_tot[slice][out] = tot;
+    s_cnt[slice][out] = cnt;
+    if (blockIdx.x == 0) {                           // live total of the merge: block 0 staged every key exactly once
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if ((threadIdx.x & 31) == 0) s_tot[threadIdx.x >> 5] = tot;
+    }
     __syncthreads();
     if (slice == 0 && j < m) {
 #pragma unroll
-        for (int q = 1; q < TL_SL; ++q) { cnt += s_cnt[q][out]; tot += s_tot[q][out]; }
+        for (int q = 1; q < TL_SL; ++q) cnt += s_cnt[q][out];
         if (c.G[off + j] != -2) c.lsort[off + cnt] = j;
-        if (j == 0) D.nlive1 = tot;
+        if (j == 0) {
+            int total = 0;
+#pragma unroll
+            for (int w = 0; w < TL_THREADS / 32; ++w) total += s_tot[w];
+            D.nlive1 = total;
+        }
     }
 }
 

@@ -361,6 +361,18 @@ struct Norms {
     }
 };
 
+// collective fall-back on several ranks: (org, tau) of the other ranks' root ranges arrive through an all-reduce; the
+// origin poles that go with them are looked up locally (the peer-memory back end pushes dorgv next to org and tau)
+struct FillDorg {
+    LevelCtx c;
+    CUPPEN_HD void operator()(long g) const {
+        int id = c.node_of[g];
+        if (id < 0) return;
+        const MergeDesc& D = c.desc[id];
+        if ((int)g - D.off < D.k) c.dorgv[g] = c.dl[D.off + c.org[g]];
+    }
+};
+
 struct NewLambda {
     LevelCtx c;
     CUPPEN_HD void operator()(long g) const {
@@ -500,7 +512,10 @@ struct FinalRank {
     CUPPEN_HD void operator()(long g, const L& lanes) const {
         const double v = lam[g];
         int cnt = 0;
-        for (int j = lanes.lane(); j < n; j += lanes.lanes()) cnt += before(lam[j], j, v, (int)g) ? 1 : 0;
+        // one comparison per pair: indices below g come first on ties (`<=`), indices above do not (`<`)
+        const int nl = lanes.lanes(), me = (int)g;
+        for (int j = lanes.lane(); j < me; j += nl) cnt += (lam[j] <= v) ? 1 : 0;
+        for (int j = me + 1 + (lanes.lane() + nl - (me + 1) % nl) % nl; j < n; j += nl) cnt += (lam[j] < v) ? 1 : 0;
         cnt = lanes.isum(cnt);
         if (lanes.lane() == 0) { perm[cnt] = (int)g; lam_sorted[cnt] = v; }
     }

@@ -37,19 +37,38 @@
 namespace cuppen {
 
 // Reciprocal for the Cauchy-like inner loops (one per pole/root pair in the secular, Loewner, norm and U kernels): the
-// hardware seed (MUFU.RCP64H, ~20 bits) and two Newton steps -- 5 FP64 instructions, < 1 ulp off the correctly rounded
-// value -- instead of the ~20-instruction IEEE division sequence with its slow-path checks, which made those kernels
-// issue-bound (profiles/r02_ncu_full_vector_kernels_goe_n16384_raw.csv).  x == 0 or subnormal gives NaN / inf: the
+// hardware seed (MUFU.RCP64H: the low 32 mantissa bits of the operand are ignored, ~20 bits) and ONE cubic step
+// r (1 + e + e^2), e = 1 - x r -- 4 FP64 instructions, within 1 ulp of the correctly rounded value (relative error e^3 ~ 2^-60
+// before the final rounding; `cuppen_selftest_rcp` measures seed and result on the device, tests/test_gpu_parity.py) --
+// instead of the ~20-instruction IEEE division sequence with its slow-path checks, which made those kernels
+// issue-bound (profiles/r02_ncu_full_vector_kernels_goe_n16384_raw.csv).  Two Newton steps (5 instructions) were the
+// first version; -DCUPPEN_RCP_NEWTON2 brings them back.  x == 0 or subnormal gives NaN / inf: the
 // callers treat a non-finite quotient like the IEEE +-inf (a bracket step, a clamped matrix entry).
 #if CUPPEN_CUDA
-__host__ __device__ __forceinline__ double fast_rcp(double x) {
-#ifdef __CUDA_ARCH__
+__device__ __forceinline__ double rcp_seed(double x) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double rcp_newton2(double x) {
+    double r = rcp_seed(x);
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
+}
+__device__ __forceinline__ double rcp_cubic(double x) {
+    const double r = rcp_seed(x);
+    const double e = fma(-x, r, 1.0);
+    return fma(r, fma(e, e, e), r);
+}
+__host__ __device__ __forceinline__ double fast_rcp(double x) {
+#ifdef __CUDA_ARCH__
+#ifdef CUPPEN_RCP_NEWTON2
+    return rcp_newton2(x);
+#else
+    return rcp_cubic(x);
+#endif
 #else
     return 1.0 / x;
 #endif

@@ -3,6 +3,7 @@
 // Declarations: cuppen_selftest.h.  Loaded by tests/ (kernel parity against plain loops) and by bench.py (the FP64
 // peak that the GEMM roofline is quoted against; MEASURED_PEAKS.json has no FP64 entry).
 #include <math.h>
+#include <string.h>
 #include <algorithm>
 
 #include "../../include/cuppen_b200.h"
@@ -70,6 +71,26 @@ __global__ void residual_check_kernel(const double* V, long ldq, int n, int ncol
     }
     double rel = fabs(got[col] - acc) / fmax(acc, 1e-300);
     atomicMax((unsigned long long*)err, (unsigned long long)__double_as_longlong(rel));
+}
+// cuppen_selftest_rcp: seed and results of the two reciprocal forms of platform.h against the IEEE quotient, over random
+// mantissas, both signs and binary exponents in [-500, 500].  out[0] max |1 - x seed|, out[1] / out[2] max distance in
+// ulps (difference of the bit patterns) of the two-Newton-step / cubic-step result from __drcp_rn(x).
+__global__ void rcp_check_kernel(long count, unsigned seed, unsigned long long* out) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    unsigned long long h = (unsigned long long)i * 6364136223846793005ull + seed * 1442695040888963407ull + 1013904223ull;
+    h ^= h >> 29; h *= 0xbf58476d1ce4e5b9ull; h ^= h >> 32;
+    const unsigned long long mant = h & 0x000fffffffffffffull;
+    const int ex = 1023 - 500 + (int)((h >> 52) % 1001);
+    const unsigned long long sign = (h >> 63) << 63;
+    const double x = __longlong_as_double((long long)(sign | ((unsigned long long)ex << 52) | mant));
+    const double exact = __drcp_rn(x);
+    const double e0 = fabs(fma(-x, rcp_seed(x), 1.0));
+    const long long d2 = llabs(__double_as_longlong(rcp_newton2(x)) - __double_as_longlong(exact));
+    const long long d3 = llabs(__double_as_longlong(rcp_cubic(x)) - __double_as_longlong(exact));
+    atomicMax(&out[0], (unsigned long long)__double_as_longlong(e0));
+    atomicMax(&out[1], (unsigned long long)d2);
+    atomicMax(&out[2], (unsigned long long)d3);
 }
 }  // namespace cuppen
 #endif
@@ -195,6 +216,31 @@ int cuppen_selftest_residual(int device, int n, int variant, int g0, int l0, int
     CUDA_CHECK(cudaMemcpy(max_rel_err, err.p, sizeof(double), cudaMemcpyDeviceToHost));
 #else
     (void)device; (void)n; (void)variant; (void)g0; (void)l0; (void)cnt; (void)max_rel_err; (void)seconds;
+    CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
+#endif
+    CUPPEN_API_END
+}
+
+int cuppen_selftest_rcp(int device, long count, double* seed_max_rel_err, double* newton2_max_ulp, double* cubic_max_ulp) {
+    CUPPEN_API_BEGIN
+#if CUPPEN_CUDA
+    if (!seed_max_rel_err || !newton2_max_ulp || !cubic_max_ulp || count < 1) CUPPEN_THROW(CUPPEN_ERR_ARG, "bad argument");
+    CUDA_CHECK(cudaSetDevice(device));
+    unsigned long long* out = nullptr;
+    CUDA_CHECK(cudaMalloc(&out, 3 * sizeof(unsigned long long)));
+    CUDA_CHECK(cudaMemset(out, 0, 3 * sizeof(unsigned long long)));
+    rcp_check_kernel<<<(unsigned)((count + 255) / 256), 256>>>(count, 12345u, out);
+    CUDA_CHECK(cudaGetLastError());
+    unsigned long long h[3];
+    CUDA_CHECK(cudaMemcpy(h, out, sizeof h, cudaMemcpyDeviceToHost));
+    cudaFree(out);
+    double e0;
+    memcpy(&e0, &h[0], sizeof e0);
+    *seed_max_rel_err = e0;
+    *newton2_max_ulp = (double)h[1];
+    *cubic_max_ulp = (double)h[2];
+#else
+    (void)device; (void)count; (void)seed_max_rel_err; (void)newton2_max_ulp; (void)cubic_max_ulp;
     CUPPEN_THROW(CUPPEN_ERR_CUDA, "no GPU in the host test build");
 #endif
     CUPPEN_API_END

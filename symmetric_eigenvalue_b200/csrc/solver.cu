@@ -35,6 +35,7 @@ static double wall_now() {
 // fail buffer of a solve (device, read back with the results): [0] leaf QL did not converge (1 + row),
 // [1] GEMM tile list overflow, [2] peer barrier timed out (1 + peer rank), [4..11] watchdog record of the TMA GEMM pipeline
 enum { FAIL_LEAF = 0, FAIL_TILES = 1, FAIL_COMM = 2, FAIL_TMA = 4, FAIL_INTS = 16 };
+enum { GEMM_HINT_MIN_ROWS = 8192 };      // merges from this size on run the tensor-map GEMM with its L2 eviction hints (gemm_tma.h)
 enum { T_LEAF, T_DEFL, T_ROOT, T_EVX, T_PACK, T_UGEN, T_GEMM, T_RESID, T_APPLY, T_COMM, T_NCAT };
 struct PhaseTimers {
     double acc[T_NCAT] = {0};
@@ -214,6 +215,8 @@ struct Solver {
     }
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
     int resid_variant = 0;        // residual_kernel variant (0: default); env CUPPEN_RESID
+    int gemm_hints = 0;           // L2 eviction hints of the tensor-map GEMM on merges of >= GEMM_HINT_MIN_ROWS rows (1: B evict_last + streaming C stores, 3: + A evict_first); env CUPPEN_GEMM_HINT
+    int supercol_mb = 48;         // L2 budget of a super-column's B panel (work_supercol); env CUPPEN_SUPERCOL_MB
     int gemm_variant = 2;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA bulk-copy lines, 2: TMA tensor maps (gemm_tma.h, default); env CUPPEN_GEMM
 #if CUPPEN_CUDA
     CUtensorMap map_qa, map_apack, map_b;      // tensor maps of the two n x n buffers (either can be the pack buffer) and of the U arena
@@ -388,6 +391,10 @@ void Solver::allocate() {
         const char* gv = getenv("CUPPEN_GEMM");
         if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
         if (gv && !strcmp(gv, "bulk")) gemm_variant = 1;
+        const char* hv = getenv("CUPPEN_GEMM_HINT");
+        if (hv) gemm_hints = atoi(hv) & 3;
+        const char* sv = getenv("CUPPEN_SUPERCOL_MB");
+        if (sv && atoi(sv) >= 1 && atoi(sv) <= 120) supercol_mb = atoi(sv);
         if (gemm_variant == 2) {
             // tensor maps of the operand buffers (35.9 vs 35.5 TFLOP/s with bulk-copy lines at 8192^3, profiles/r02_gemm_bench.txt)
             const long cols = (long)(qelems / (size_t)ldq), brows = (long)(B.n / (size_t)ldb);
@@ -909,6 +916,7 @@ void Solver::run_level(int li) {
         } else if (coop) {
             comm.allreduce_sum(tau.p + lo_idx, hi_idx - lo_idx, stream);
             comm.allreduce_sum_i32(org.p + lo_idx, hi_idx - lo_idx, stream);
+            launch_items(stream, n, FillDorg{c});
         }
         pt.begin(T_EVX, stream);
 #if CUPPEN_CUDA
@@ -1001,6 +1009,7 @@ void Solver::run_level(int li) {
         w.ldq = ldq; w.ldb = ldb; w.Apack = Awork; w.B = B.p; w.Qnext = Qcur; w.lidx = lidx.p;
         w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
         w.fail = fail.p + FAIL_TILES;
+        w.supercol_mb = supercol_mb;
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
         {
@@ -1025,7 +1034,8 @@ void Solver::run_level(int li) {
         const int grid = (int)std::min<long>(worst, small_tiles ? num_sms * 8L : (long)num_sms);
         if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, ntiles_dev.p, grid);
         else if (gemm_variant == 2)
-            launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA, Awork == Apack.p ? &map_apack : &map_qa, &map_b);
+            launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA, Awork == Apack.p ? &map_apack : &map_qa, &map_b,
+                            L.maxm >= GEMM_HINT_MIN_ROWS ? gemm_hints : 0);
         else if (gemm_variant == 1) launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA);
         else launch_gemm<128, 128, 16, 2, 4, 3>(stream, probs.p, tiles.p, ntiles_dev.p, std::min<long>(worst, num_sms * 2L));
 #else

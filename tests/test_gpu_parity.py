@@ -297,6 +297,18 @@ def test_residual_kernel_slices(lib, n, g0, l0, cnt):
         assert api.selftest_residual(n, g0, l0, cnt, variant=variant)[0] < 1e-10
 
 
+def test_fast_reciprocal_accuracy(lib):
+    """The reciprocal of the Cauchy-like inner loops (platform.h: hardware seed + one cubic step) against the correctly
+    rounded 1/x on 16 M random operands (random mantissas, both signs, binary exponents -500..500): the seed carries
+    about 20 bits, so the cubic step leaves e^3 ~ 2^-60 before the final rounding -- within one ulp, like the two-Newton-
+    step form it replaced."""
+    from symmetric_eigenvalue_b200 import api
+    seed_err, newton_ulp, cubic_ulp = api.selftest_rcp(1 << 24)
+    assert seed_err < 2.0 ** -18, seed_err
+    assert newton_ulp <= 1.0, newton_ulp
+    assert cubic_ulp <= 1.0, cubic_ulp
+
+
 @pytest.mark.parametrize("name", ["s1_n4096_p8_sel", "goe_n4096_p8_sel"])
 def test_select_mode_against_reference_efile_goldens(lib, name):
     """Selected-eigenvector mode against the reference's own `-eFILE` output at n=4096, P=8."""
