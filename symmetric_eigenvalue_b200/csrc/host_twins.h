@@ -60,7 +60,7 @@ inline int host_leaf_ql(int nl, double* d, double* e, double* q /* row-major nl 
 }
 
 inline void leaf_ql_host(const LeafDesc* leaves, int nleaves, const double* Dm, const double* E, double* lam,
-                         double* frow, double* lrow, double* Q, long ldq, int R0, int* fail, int compact) {
+                         double* frow, double* lrow, double* Q, long ldq, int R0, int* fail, int compact, RowSpan* span) {
     for (int leaf = 0; leaf < nleaves; ++leaf) {
         const int off = leaves[leaf].off, nl = leaves[leaf].n;
         std::vector<double> d(Dm + off, Dm + off + nl), e(nl, 0.0), q((size_t)nl * nl, 0.0);
@@ -72,6 +72,7 @@ inline void leaf_ql_host(const LeafDesc* leaves, int nleaves, const double* Dm, 
             lam[off + c] = d[c];
             frow[off + c] = q[c];
             lrow[off + c] = q[(size_t)(nl - 1) * nl + c];
+            if (span) span[off + c] = RowSpan{off, off + nl};
             if (Q) for (int r = 0; r < nl; ++r) Q[(long)(off + r - R0) + (long)(compact ? c : off + c) * ldq] = q[(size_t)r * nl + c];
         }
     }
@@ -100,6 +101,7 @@ inline void pack_host(LevelCtx c, MatCtx M) {
         const MergeDesc& D = c.desc[id];
         const int off = D.off, e = g - off;
         const bool zdefl = c.G[g] == -2;
+        if (M.span && !zdefl) M.span[g] = RowSpan{off, off + D.m};
         if (!zdefl && !c.head[g]) continue;
         for (int r = D.lr0; r < D.lr1; ++r) {
             const long rl = r;
@@ -196,13 +198,19 @@ inline void gemm_host(const GemmProblem* probs, const GemmTile* tiles, const int
 
 inline void residual_host(const double* V, long ldq, int n, int g0, int l0, int cnt, const double* OD, const double* OE,
                           const double* lam_sorted, const int* perm, const double* halo_lo, const double* halo_hi, double* res2,
-                          int accumulate) {
+                          int accumulate, const RowSpan* span) {
     const int g1 = g0 + cnt;
     for (int col = 0; col < n; ++col) {
         const double* x = V + (long)perm[col] * ldq + l0 - g0;
         const double lambda = lam_sorted[col];
         double acc = 0;
-        for (int r = g0; r < g1; ++r) {
+        const int ra = span ? std::max(g0, span[perm[col]].lo - 1) : g0, rb = span ? std::min(g1, span[perm[col]].hi + 1) : g1;
+        if (span)      // (test build: the rows that the device kernel skips must hold exact zeros)
+            for (int r = g0; r < g1; ++r)
+                if ((r < span[perm[col]].lo || r >= span[perm[col]].hi) && x[r] != 0.0)
+                    CUPPEN_THROW(CUPPEN_ERR_STATE, "column %d (storage %d) is non-zero at row %d outside its span [%d, %d)", col, perm[col], r,
+                                 span[perm[col]].lo, span[perm[col]].hi);
+        for (int r = ra; r < rb; ++r) {
             const double xc = x[r];
             double y = OD[r] * xc - lambda * xc;
             if (r > 0) y += OE[r - 1] * ((r > g0) ? x[r - 1] : halo_lo[col]);

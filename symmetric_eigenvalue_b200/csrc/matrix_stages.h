@@ -28,6 +28,13 @@ enum { LEAF_MAX = 32 };         // largest leaf handled by one warp
 
 struct LeafDesc { int off, n; };
 
+// Row support of a column of the block-diagonal eigenvector matrix, in GLOBAL rows.  A column is non-zero only inside
+// the block of the last merge at which it was not z-deflated (a leaf block if never): the leaf kernel writes the leaf
+// spans, pack_kernel widens the span of every column that a merge rewrites (live roots and rotated columns), z-deflated
+// columns keep theirs.  The residual kernel reads only the rows lo-1 .. hi of a column -- on heavily deflating matrices
+// (Wilkinson n=16384: a few hundred live columns at the top merges) that is a small part of the n rows.
+struct RowSpan { int lo, hi; };
+
 struct MatCtx {
     int n;                // global size
     long ldq;             // leading dimension of the Q buffers and of Apack (local rows, padded)
@@ -36,6 +43,7 @@ struct MatCtx {
     double* Apack;        // packed live columns (K order), same shape as Q plus K_PAD columns
     double* B;            // U arena, row-major [n + pad][ldb]
     long ldb;
+    RowSpan* span;        // per storage column: global rows outside [lo, hi) are exactly zero (nullptr: not tracked)
 };
 
 // GEMM work list of one level and one panel, built on the device from the merge descriptors so that
@@ -160,7 +168,7 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
                                                       const double* __restrict__ Dm, const double* __restrict__ E,
                                                       double* __restrict__ lam, double* __restrict__ frow,
                                                       double* __restrict__ lrow, double* __restrict__ Q, long ldq,
-                                                      int R0, int* __restrict__ fail, int compact) {
+                                                      int R0, int* __restrict__ fail, int compact, RowSpan* __restrict__ span) {
     __shared__ double sq[4][LEAF_MAX][LEAF_MAX + 1];
     __shared__ double sd[4][LEAF_MAX];
     __shared__ double se[4][LEAF_MAX + 1];
@@ -252,6 +260,7 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
         lam[off + lane] = d[lane] * unscl;
         frow[off + lane] = q[0][lane];
         lrow[off + lane] = q[nl - 1][lane];
+        if (span != nullptr) span[off + lane] = RowSpan{off, off + nl};
     }
     const int grow = off + lane;          // global row of this lane
     if (Q != nullptr && lane < nl)
@@ -753,6 +762,9 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
     const int off = D.off, e = g - off;
     const int Gg = c.G[g];
     const bool zdefl = (Gg == -2);
+    // row support (RowSpan): every column that this merge rewrites -- a root column of the GEMM or a rotated column --
+    // spans the parent block from now on
+    if (M.span != nullptr && !zdefl && blockIdx.y == 0 && threadIdx.x == 0) M.span[g] = RowSpan{off, off + D.m};
     const int rbase = D.lr0 + blockIdx.y * PACK_ROWS * PACK_THREADS + threadIdx.x;      // local row
     if (rbase >= D.lr1) return;
     const bool etop = e < D.n1;
@@ -939,19 +951,28 @@ template <int RES_NC, int MINB>
 __global__ void __launch_bounds__(256, MINB) residual_kernel(const double* __restrict__ V, long ldq, int n, ResSlices S,
                                                              const double* __restrict__ OD, const double* __restrict__ OE,
                                                              const double* __restrict__ lam_sorted, const int* __restrict__ perm,
-                                                             double* __restrict__ res2) {
+                                                             double* __restrict__ res2, const RowSpan* __restrict__ span) {
     const int col0 = blockIdx.x * RES_NC;
     const int lane = threadIdx.x & 31;
     // per-column constants live in shared memory (broadcast reads) to keep the register budget for loads in flight
     __shared__ const double* xb[RES_NC];
     __shared__ double lambda[RES_NC];
+    __shared__ int slo[RES_NC], shi[RES_NC];
     double acc[RES_NC];
     if (threadIdx.x < RES_NC) {
         const int col = min(col0 + (int)threadIdx.x, n - 1);      // columns past the end repeat the last one (not stored)
         xb[threadIdx.x] = V + (long)perm[col] * ldq;              // (ldq is even: the parity of an element's address is that of its row)
         lambda[threadIdx.x] = lam_sorted[col];
+        slo[threadIdx.x] = span ? span[perm[col]].lo : 0;
+        shi[threadIdx.x] = span ? span[perm[col]].hi : n;
     }
     __syncthreads();
+    // rows that can contribute: the union of the block's column supports, widened by one row on either side (the rows
+    // next to a support see it through the off-diagonal); everything else is (d - lambda) 0 + e 0 + e 0
+    int blo = slo[0], bhi = shi[0];
+#pragma unroll
+    for (int c = 1; c < RES_NC; ++c) { blo = min(blo, slo[c]); bhi = max(bhi, shi[c]); }
+    blo -= 1; bhi += 1;
 #pragma unroll
     for (int c = 0; c < RES_NC; ++c) acc[c] = 0.0;
     for (int sl = 0; sl < S.ns; ++sl) {
@@ -960,7 +981,8 @@ __global__ void __launch_bounds__(256, MINB) residual_kernel(const double* __res
         const bool vec_ok = ((shift & 1) == 0) && ((ldq & 1) == 0);   // 16-byte loads of (x[r], x[r+1]) with r even
         const double* halo_lo = S.lo[sl];
         const double* halo_hi = S.hi[sl];
-        for (int r = (g0 & ~1) + 2 * (int)threadIdx.x; r < g1; r += 2 * 256) {
+        const int ra = max(g0, blo), rb = min(g1, bhi);
+        for (int r = (ra & ~1) + 2 * (int)threadIdx.x; r < rb; r += 2 * 256) {
             if (vec_ok && r - 1 >= g0 && r + 2 < g1) {
                 // interior pair: rows r-1 .. r+2 are all inside the slice (so 0 < r and r + 1 < n - 1)
                 const double2 dv = *reinterpret_cast<const double2*>(OD + r);
@@ -1013,10 +1035,10 @@ __global__ void __launch_bounds__(256, MINB) residual_kernel(const double* __res
 
 // variant: 0 default, else NC*10 + MINB
 inline void launch_residual(Stream st, int variant, const double* V, long ldq, int n, const ResSlices& S, const double* OD,
-                            const double* OE, const double* lam_sorted, const int* perm, double* res2) {
+                            const double* OE, const double* lam_sorted, const int* perm, double* res2, const RowSpan* span = nullptr) {
 #define CUPPEN_RES_CASE(NC, MB)                                                                                          \
     case NC * 10 + MB:                                                                                                   \
-        residual_kernel<NC, MB><<<(unsigned)((n + NC - 1) / NC), 256, 0, st>>>(V, ldq, n, S, OD, OE, lam_sorted, perm, res2); \
+        residual_kernel<NC, MB><<<(unsigned)((n + NC - 1) / NC), 256, 0, st>>>(V, ldq, n, S, OD, OE, lam_sorted, perm, res2, span); \
         break;
     switch (variant == 0 ? RES_DEFAULT_VARIANT : variant) {
         CUPPEN_RES_CASE(1, 4) CUPPEN_RES_CASE(1, 6) CUPPEN_RES_CASE(2, 4) CUPPEN_RES_CASE(2, 5) CUPPEN_RES_CASE(4, 3)

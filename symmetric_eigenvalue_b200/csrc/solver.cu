@@ -133,6 +133,7 @@ struct Solver {
     DevBuf<double> Vgath, res_gath;
     int sel_per() const { return ((int)h_sel.size() + sel_world - 1) / sel_world; }
     DevBuf<int> sel_dev, leaf_off_dev, leaf_n_dev;
+    DevBuf<RowSpan> colspan, colspan_sub;    // row support per storage column (matrix_stages.h); the subtree blocks (several ranks: the spans at the transition)
     DevBuf<double> Qleaf, selX, selY, selXS, selGam, sel_dorg, Vsel, res_sel;
     std::vector<double> h_res_sel;
     void enqueue_apply();
@@ -352,6 +353,20 @@ void Solver::allocate() {
     for (DevBuf<double>* b : {&dDm, &dE, &dOD, &dOE, &lam, &lam_sorted, &frow, &lrow, &frow2, &lrow2, &fpack, &lpack, &res2})
         if (b->p == nullptr) b->alloc(N + 64);
     perm.alloc(N + 64);
+    colspan.alloc(N + 64);
+    {
+        // (defined before the first leaf kernel has run; several ranks: a rank tracks the columns of its own subtrees only,
+        // so the cooperative phase starts from the subtree blocks on every rank)
+        std::vector<RowSpan> full(N + 64, RowSpan{0, n});
+        dev_h2d(colspan.p, full.data(), sizeof(RowSpan) * full.size(), stream);
+        if (G > 1) {
+            for (int t = 0; t < S; ++t)
+                for (int g = sub_off[t]; g < sub_off[t] + sub_n[t]; ++g) full[g] = RowSpan{sub_off[t], sub_off[t] + sub_n[t]};
+            colspan_sub.alloc(N + 64);
+            dev_h2d(colspan_sub.p, full.data(), sizeof(RowSpan) * full.size(), stream);
+        }
+        dev_sync(stream);
+    }
     // scratch vectors of a level: shared by all levels, or one slice per level in selected-eigenvector mode
     lvl_stride = N + 64;
     lvl_cap = select_mode ? (int)plan.by_height.size() + 1 : 1;
@@ -581,6 +596,7 @@ LevelCtx Solver::level_ctx(int li) {
 MatCtx Solver::mat_ctx() {
     MatCtx M;
     M.n = n; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qcur; M.Apack = Awork; M.B = B.p; M.ldb = ldb;       // in place
+    M.span = want_vectors ? colspan.p : nullptr;
     return M;
 }
 
@@ -596,10 +612,10 @@ void Solver::run_leaves() {
     const int compact = select_mode ? 1 : 0;
 #if CUPPEN_CUDA
     leaf_ql_kernel<<<(unsigned)((hl.size() + 3) / 4), 128, 0, stream>>>(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p,
-                                                                       lrow.p, Q, ldleaf, R0, fail.p, compact);
+                                                                       lrow.p, Q, ldleaf, R0, fail.p, compact, want_vectors ? colspan.p : nullptr);
     CUDA_CHECK(cudaGetLastError());
 #else
-    leaf_ql_host(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p, lrow.p, Q, ldleaf, R0, fail.p, compact);
+    leaf_ql_host(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p, lrow.p, Q, ldleaf, R0, fail.p, compact, want_vectors ? colspan.p : nullptr);
 #endif
     g_launches.launches++;
     pt.end(stream);
@@ -775,6 +791,7 @@ void Solver::enter_cooperative_p2p() {
 
 void Solver::enter_cooperative() {
     if (G <= 1) return;
+    if (want_vectors) dev_d2d(colspan.p, colspan_sub.p, sizeof(RowSpan) * n, stream);     // row supports: the subtree blocks
     if (p2p.on) { enter_cooperative_p2p(); return; }
     // every rank has lam / first row / last row of its own subtree: zero the rest and sum
     for (DevBuf<double>* b : {&lam, &frow, &lrow}) {
@@ -1112,12 +1129,12 @@ void Solver::finish() {
                 memset(&rs, 0, sizeof rs);
                 rs.ns = (int)sl.size();
                 for (size_t i = 0; i < sl.size(); ++i) { rs.g0[i] = sl[i].g0; rs.l0[i] = sl[i].l0; rs.cnt[i] = sl[i].cnt; rs.lo[i] = sl[i].lo; rs.hi[i] = sl[i].hi; }
-                launch_residual(stream, resid_variant, Qcur, ldq, n, rs, dOD.p, dOE.p, lam_sorted.p, perm.p, res2.p);
+                launch_residual(stream, resid_variant, Qcur, ldq, n, rs, dOD.p, dOE.p, lam_sorted.p, perm.p, res2.p, colspan.p);
                 g_launches.launches++;
             }
 #else
             for (size_t i = 0; i < sl.size(); ++i) {
-                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0);
+                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0, colspan.p);
                 g_launches.launches++;
             }
 #endif
