@@ -68,10 +68,14 @@ struct WorkCtx {
 
 // Tile order of one problem: super-columns of `nsw` n-tiles, all m-tiles inside a super-column, n fastest -- so B is
 // read from DRAM about once and A once per super-column instead of B once per m-tile.  nsw: the B panel (K x nsw*BN
-// doubles) takes at most `supercol_mb` MiB of the L2 -- 48 by default (6 n-tiles at K = 6.7k).  Measured with ncu on the
-// top merge of GOE n=16384 (4.3 GB of operand bytes): 48 MiB -> 24.1 GB of DRAM traffic; 96 MiB (14 n-tiles, fewer passes
-// over A) -> 28.7 GB: a 96 MiB panel does not stay resident in the 126 MB L2 (two partitions, C write-allocates), so B
-// is re-read as well (profiles/README.md, r02 call I).  CUPPEN_SUPERCOL_MB overrides the budget.
+// doubles) takes at most `supercol_mb` MiB of the L2.  Measured with ncu on the top merge of GOE n=16384 (4.3 GB of
+// operand bytes, 81 ms, DMMA-bound either way; profiles/README.md, r02 calls I and J): DRAM read + write
+//   48 MiB, no hints 24.7 + 1.7 GB | 96 MiB, no hints 27.0 + 1.7 (the panel does not stay resident: two L2 partitions, C
+//   write-allocates) | 48 MiB, B evict_last + streaming C stores 22.1 + 1.7 | 72 MiB with the same hints 20.9 + 1.7
+//   | A evict_first on top 32.3 + 1.7 (the A strip is shared by the n-tiles in flight and must survive them).
+// The hints cost 0.1 % of GEMM time in every run (112.81 -> 112.91 ms per solve; the kernel is DMMA-bound, DRAM at 0.3 TB/s),
+// so the default stays 48 MiB without hints; CUPPEN_GEMM_HINT=1 CUPPEN_SUPERCOL_MB=72 selects the low-traffic variant.
+// The floor of this order is |B| + |C| + (N / nsw BN) |A| = 17 GB at 48 MiB: A is streamed once per super-column.
 CUPPEN_HD int work_supercol(const WorkCtx& w, const GemmProblem& Pb) {
     const int ntn = (Pb.N + w.BN - 1) / w.BN;
     long nsw = ((long)w.supercol_mb << 20) / ((long)(Pb.K > 0 ? Pb.K : 1) * 8 * w.BN);
@@ -611,6 +615,10 @@ __global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
     const int out = threadIdx.x & (TL_TJ - 1), slice = threadIdx.x / TL_TJ;
     const int j = j0 + out;
     const double dj = (j < m) ? c.d[off + j] : 0.0;
+    // a CTA whose outputs are all z-deflated has nothing to rank (heavily deflating matrices: most CTAs of the upper
+    // levels); block 0 always runs, it counts the live entries of the merge
+    const bool live_out = (j < m) && c.G[off + j] != -2;
+    if (!__syncthreads_or(live_out ? 1 : 0) && blockIdx.x != 0) return;
     int cnt = 0, tot = 0;
     for (int t0 = 0; t0 < m; t0 += TL_RC) {
         const int n_here = min((int)TL_RC, m - t0);
@@ -646,7 +654,7 @@ __global__ void __launch_bounds__(TL_THREADS) rank_tiled_kernel(LevelCtx c) {
     if (slice == 0 && j < m) {
 #pragma unroll
         for (int q = 1; q < TL_SL; ++q) cnt += s_cnt[q][out];
-        if (c.G[off + j] != -2) c.lsort[off + cnt] = j;
+        if (live_out) c.lsort[off + cnt] = j;
         if (j == 0) {
             int total = 0;
 #pragma unroll
@@ -756,39 +764,48 @@ inline void launch_fused_front(Stream st, int num_sms, int merges, int maxm, Lev
 enum { PACK_THREADS = 128, PACK_ROWS = 8 };
 __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M) {
     const int g = blockIdx.x;
-    const int id = c.node_of[g];
-    if (id < 0) return;
-    const MergeDesc& D = c.desc[id];
-    const int off = D.off, e = g - off;
+    // The blocks are short and bound by their dependent L2 round trips: node_of[g] -> descriptor -> G[g] / head[g] were
+    // three of them (the compiler sinks loads below the early exits).  G[g] and head[g] depend on g only, and the
+    // descriptor fields sit in three different 32-byte sectors: the two exit tests below are written so that they
+    // consume everything that can be requested at that point -- two round trips.  (G >= -2, head in {0, 1} and the
+    // descriptor fields are >= 0, so the extra terms never fire.  L1 prefetches -- CCTL.PF1 -- instead: 4x slower.)
     const int Gg = c.G[g];
-    const bool zdefl = (Gg == -2);
-    // row support (RowSpan): every column that this merge rewrites -- a root column of the GEMM or a rotated column --
-    // spans the parent block from now on
-    if (M.span != nullptr && !zdefl && blockIdx.y == 0 && threadIdx.x == 0) M.span[g] = RowSpan{off, off + D.m};
+    const int headg = c.head[g];
+    const int id = c.node_of[g];
+    if ((id | (Gg + 2) | headg) < 0) return;
+    const MergeDesc& D = c.desc[id];
+    const int off = D.off, Dm = D.m, Dn1 = D.n1, Dkt = D.ktop, Dkb = D.kbot, Dlr1 = D.lr1, Dlsplit = D.lsplit;
     const int rbase = D.lr0 + blockIdx.y * PACK_ROWS * PACK_THREADS + threadIdx.x;      // local row
-    if (rbase >= D.lr1) return;
-    const bool etop = e < D.n1;
+    if (((Dlr1 - 1 - rbase) | off | Dm | Dn1 | Dkt | Dkb | Dlsplit) < 0) return;      // rbase >= lr1: no rows of the node here
+    const int e = g - off;
+    const bool zdefl = (Gg == -2);
+    const bool etop = e < Dn1;
     // (the zdefl / head early return was moved below the tail zeroing)
     {
         // zero the K tail of Apack: columns [kh, round_up(kh, K_PAD)) of each half -- the GEMM reads K in multiples
         // of K_PAD.  Column off+e is handled by this block; a tail that runs past the node's last column (m not a
         // multiple of K_PAD) is finished by the block of the last column.  (Was a separate launch, pack_tail_kernel.)
-        const int kt = D.ktop, kb = D.kbot;
+        const int kt = Dkt, kb = Dkb;
         const int kt_end = (kt + K_PAD - 1) / K_PAD * K_PAD, kb_end = (kb + K_PAD - 1) / K_PAD * K_PAD;
-        const int last = (e == D.m - 1) ? max(kt_end, kb_end) : e + 1;
+        const int last = (e == Dm - 1) ? max(kt_end, kb_end) : e + 1;
         for (int kk = e; kk < last; ++kk) {
             if (!((kk >= kt && kk < kt_end) || (kk >= kb && kk < kb_end))) continue;
 #pragma unroll
             for (int t = 0; t < PACK_ROWS; ++t) {
                 const int r = rbase + t * PACK_THREADS;
-                if (r >= D.lr1) break;
-                const bool rtop = r < D.lsplit;
+                if (r >= Dlr1) break;
+                const bool rtop = r < Dlsplit;
                 const int kh = rtop ? kt : kb, kend = rtop ? kt_end : kb_end;
                 if (kk >= kh && kk < kend) M.Apack[(long)r + (long)(off + kk) * M.ldq] = 0.0;
             }
         }
     }
-    if (!zdefl && !c.head[g]) return;
+    // row support (RowSpan): every column that this merge rewrites -- a root column of the GEMM or a rotated column --
+    // spans the parent block from now on.  (Placed here, after the descriptor fields have been consumed: a store at the
+    // top of the kernel made the warp wait for G[g] before it issued the other descriptor loads -- one more dependent L2
+    // round trip per block, 1.08 -> 1.41 ms of pack time at n = 16384, gpurun_out r02 call K.)
+    if (M.span != nullptr && !zdefl && blockIdx.y == 0 && threadIdx.x == 0) M.span[g] = RowSpan{off, off + Dm};
+    if (!zdefl && !headg) return;
     if (zdefl && M.Qnew == M.Qold) {
         // in place: a z-deflated column keeps its own-half rows where they are; only the other half's rows of the
         // parent block are new and must read zero (they may hold the previous solve's V)
@@ -796,7 +813,7 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
 #pragma unroll
         for (int t = 0; t < PACK_ROWS; ++t) {
             const int r = rbase + t * PACK_THREADS;
-            if (r < D.lr1 && ((r < D.lsplit) != etop)) dst[r] = 0.0;
+            if (r < Dlr1 && ((r < Dlsplit) != etop)) dst[r] = 0.0;
         }
         return;
     }
@@ -816,26 +833,26 @@ __global__ void __launch_bounds__(PACK_THREADS) pack_kernel(LevelCtx c, MatCtx M
 #pragma unroll
         for (int t = 0; t < PACK_ROWS; ++t) {
             const int r = rbase + t * PACK_THREADS;
-            v[t] = (r < D.lr1 && ((r < D.lsplit) == etop)) ? src[r] : 0.0;
+            v[t] = (r < Dlr1 && ((r < Dlsplit) == etop)) ? src[r] : 0.0;
         }
 #pragma unroll
         for (int t = 0; t < PACK_ROWS; ++t) {
             const int r = rbase + t * PACK_THREADS;
-            if (r < D.lr1 && (write_other || ((r < D.lsplit) == etop))) dst[r] = v[t];
+            if (r < Dlr1 && (write_other || ((r < Dlsplit) == etop))) dst[r] = v[t];
         }
         return;
     }
     for (int t = 0; t < PACK_ROWS; ++t) {
         const int r = rbase + t * PACK_THREADS;
-        if (r >= D.lr1) return;
+        if (r >= Dlr1) return;
         const long rl = r;
-        const bool rtop = r < D.lsplit;
+        const bool rtop = r < Dlsplit;
         int a = e;
-        double carry = ((a < D.n1) == rtop) ? M.Qold[rl + (long)(off + a) * M.ldq] : 0.0;
+        double carry = ((a < Dn1) == rtop) ? M.Qold[rl + (long)(off + a) * M.ldq] : 0.0;
         int b;
         while ((b = c.G[off + a]) >= 0) {
             const double cs = c.gc[off + a], sn = c.gs[off + a];
-            const double x = ((b < D.n1) == rtop) ? M.Qold[rl + (long)(off + b) * M.ldq] : 0.0;
+            const double x = ((b < Dn1) == rtop) ? M.Qold[rl + (long)(off + b) * M.ldq] : 0.0;
             M.Qnew[rl + (long)(off + a) * M.ldq] = cs * carry - sn * x;
             carry = sn * carry + cs * x;
             a = b;

@@ -217,6 +217,7 @@ struct Solver {
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
     int resid_variant = 0;        // residual_kernel variant (0: default); env CUPPEN_RESID
     int gemm_hints = 0;           // L2 eviction hints of the tensor-map GEMM on merges of >= GEMM_HINT_MIN_ROWS rows (1: B evict_last + streaming C stores, 3: + A evict_first); env CUPPEN_GEMM_HINT
+    bool track_spans = true;      // row support per column (RowSpan, matrix_stages.h); env CUPPEN_SPAN=0 switches it off
     int supercol_mb = 48;         // L2 budget of a super-column's B panel (work_supercol); env CUPPEN_SUPERCOL_MB
     int gemm_variant = 2;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA bulk-copy lines, 2: TMA tensor maps (gemm_tma.h, default); env CUPPEN_GEMM
 #if CUPPEN_CUDA
@@ -406,6 +407,8 @@ void Solver::allocate() {
         const char* gv = getenv("CUPPEN_GEMM");
         if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
         if (gv && !strcmp(gv, "bulk")) gemm_variant = 1;
+        const char* tv = getenv("CUPPEN_SPAN");
+        if (tv && atoi(tv) == 0) track_spans = false;
         const char* hv = getenv("CUPPEN_GEMM_HINT");
         if (hv) gemm_hints = atoi(hv) & 3;
         const char* sv = getenv("CUPPEN_SUPERCOL_MB");
@@ -596,7 +599,7 @@ LevelCtx Solver::level_ctx(int li) {
 MatCtx Solver::mat_ctx() {
     MatCtx M;
     M.n = n; M.ldq = ldq; M.Qold = Qcur; M.Qnew = Qcur; M.Apack = Awork; M.B = B.p; M.ldb = ldb;       // in place
-    M.span = want_vectors ? colspan.p : nullptr;
+    M.span = (want_vectors && track_spans) ? colspan.p : nullptr;
     return M;
 }
 
@@ -612,10 +615,10 @@ void Solver::run_leaves() {
     const int compact = select_mode ? 1 : 0;
 #if CUPPEN_CUDA
     leaf_ql_kernel<<<(unsigned)((hl.size() + 3) / 4), 128, 0, stream>>>(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p,
-                                                                       lrow.p, Q, ldleaf, R0, fail.p, compact, want_vectors ? colspan.p : nullptr);
+                                                                       lrow.p, Q, ldleaf, R0, fail.p, compact, (want_vectors && track_spans) ? colspan.p : nullptr);
     CUDA_CHECK(cudaGetLastError());
 #else
-    leaf_ql_host(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p, lrow.p, Q, ldleaf, R0, fail.p, compact, want_vectors ? colspan.p : nullptr);
+    leaf_ql_host(leaves.p, (int)hl.size(), dDm.p, dE.p, lam.p, frow.p, lrow.p, Q, ldleaf, R0, fail.p, compact, (want_vectors && track_spans) ? colspan.p : nullptr);
 #endif
     g_launches.launches++;
     pt.end(stream);
@@ -791,7 +794,7 @@ void Solver::enter_cooperative_p2p() {
 
 void Solver::enter_cooperative() {
     if (G <= 1) return;
-    if (want_vectors) dev_d2d(colspan.p, colspan_sub.p, sizeof(RowSpan) * n, stream);     // row supports: the subtree blocks
+    if (want_vectors && track_spans) dev_d2d(colspan.p, colspan_sub.p, sizeof(RowSpan) * n, stream);     // row supports: the subtree blocks
     if (p2p.on) { enter_cooperative_p2p(); return; }
     // every rank has lam / first row / last row of its own subtree: zero the rest and sum
     for (DevBuf<double>* b : {&lam, &frow, &lrow}) {
@@ -1129,12 +1132,12 @@ void Solver::finish() {
                 memset(&rs, 0, sizeof rs);
                 rs.ns = (int)sl.size();
                 for (size_t i = 0; i < sl.size(); ++i) { rs.g0[i] = sl[i].g0; rs.l0[i] = sl[i].l0; rs.cnt[i] = sl[i].cnt; rs.lo[i] = sl[i].lo; rs.hi[i] = sl[i].hi; }
-                launch_residual(stream, resid_variant, Qcur, ldq, n, rs, dOD.p, dOE.p, lam_sorted.p, perm.p, res2.p, colspan.p);
+                launch_residual(stream, resid_variant, Qcur, ldq, n, rs, dOD.p, dOE.p, lam_sorted.p, perm.p, res2.p, track_spans ? colspan.p : nullptr);
                 g_launches.launches++;
             }
 #else
             for (size_t i = 0; i < sl.size(); ++i) {
-                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0, colspan.p);
+                residual_host(Qcur, ldq, n, sl[i].g0, sl[i].l0, sl[i].cnt, dOD.p, dOE.p, lam_sorted.p, perm.p, sl[i].lo, sl[i].hi, res2.p, i > 0 ? 1 : 0, track_spans ? colspan.p : nullptr);
                 g_launches.launches++;
             }
 #endif
