@@ -885,15 +885,18 @@ __global__ void __launch_bounds__(256) ugen_kernel(LevelCtx c, MatCtx M, int p0,
             // the new eigenvalues of the level (NewLambda, one thread per index) ride along with the first panel: nothing
             // between here and the next level's z assembly reads lam
             if (new_lambda && blockIdx.y == 0) NewLambda{c}(row);
+            // (the K-list entries depend on the row only: requested together with node_of[row] -- the test below consumes
+            // them, or the compiler sinks the loads behind the descriptor -- three dependent round trips instead of four)
+            const int jt = c.toplist[row], jb = c.botlist[row];
             id = c.node_of[row];
-            if (id >= 0) {
+            if (id >= 0 && (jt | jb) != (int)0x80000000) {       // (list entries are indices or stale non-negative values: always true)
                 const MergeDesc& D = c.desc[id];
                 const bool top = row < D.off + D.n1;
                 const int jj = row - (top ? D.off : D.off + D.n1);
                 const int kh = top ? D.ktop : D.kbot;
                 if (jj >= kh) id = -1;
                 else {
-                    const int j = top ? c.toplist[row] : c.botlist[row];
+                    const int j = top ? jt : jb;
                     s_dj[threadIdx.x] = c.dl[D.off + j];
                     s_zj[threadIdx.x] = c.zhat[D.off + j];
                 }

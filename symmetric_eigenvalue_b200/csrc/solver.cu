@@ -375,6 +375,9 @@ void Solver::allocate() {
         if (b->p == nullptr) b->alloc(lvl_stride * lvl_cap);
     for (DevBuf<int>* b : {&G_, &lsort, &head, &sup, &prev, &tpos, &bpos, &lidx, &org, &toplist, &botlist})
         if (b->p == nullptr) b->alloc(lvl_stride * lvl_cap);
+    // (ugen_kernel reads both K-list entries of a row before it knows which one is defined: never uninitialised memory)
+    dev_zero(toplist.p, toplist.bytes(), stream);
+    dev_zero(botlist.p, botlist.bytes(), stream);
     if (select_mode) {
         Qleaf.alloc(N * LEAF_MAX + 64);
         leaf_off_dev.alloc(N + 64);
