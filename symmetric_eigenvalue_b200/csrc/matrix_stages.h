@@ -367,25 +367,50 @@ __global__ void __launch_bounds__(SEC_WARPS * 32) secular_kernel(LevelCtx c, int
 
 // Compact as a scan: the canonical index of a live element is the number of live elements before it in the
 // sorted z-live list -- a prefix sum, not the O(m^2) count of the per-warp Compact functor (which stays in use
-// for the small merges of fused_front_kernel and in the host test build).  One CTA per merge: a reduction pass
-// for the totals (k is needed up front: rho < 0 problems are stored reflected), then a tiled exclusive scan of
-// the three flags (live, top-supported, bottom-supported) with running carries.
-enum { CS_THREADS = 1024 };
+// for the small merges of fused_front_kernel and in the host test build).  One thread-block CLUSTER per merge (1 CTA
+// below 4096 entries, up to 8 at 16384 and more): every CTA takes a contiguous range of the sorted list -- its share of the
+// Givens sweep, then a reduction pass for the totals (k is needed up front: rho < 0 problems are stored reflected;
+// the CTAs exchange their partial totals through distributed shared memory), then a tiled exclusive scan of the three
+// flags (live, top-supported, bottom-supported) that starts from the totals of the CTAs before it.  With one CTA per
+// merge every pass walked m / 1024 elements per thread with two dependent L2 round trips each: 154 us at m = 16384,
+// 92 us at 8192 (profiles/r02_ncu_launches_goe_n16384.csv) -- on every rank, the stage is replicated.
+enum { CS_THREADS = 1024, CS_MAX_CLUSTER = 8 };
+inline int compact_cluster_size(int maxm) { return maxm >= 8192 ? 8 : maxm >= 4096 ? 4 : maxm >= 2048 ? 2 : 1; }
+// cluster barrier, or the block barrier of the one-CTA instantiation (launched without the cluster attribute: the three
+// cluster barriers and the cluster launch cost a few microseconds per level on the small merges)
+template <bool CLUSTER>
+__device__ __forceinline__ void cs_sync() {
+    if (CLUSTER) cooperative_groups::this_cluster().sync();
+    else __syncthreads();
+}
+template <bool CLUSTER>
 __global__ void __launch_bounds__(CS_THREADS) compact_scan_kernel(LevelCtx c) {
-    MergeDesc& D = c.desc[blockIdx.x];
-    // the Givens sweep of this merge first (segment heads walk their segments; was a launch of its own)
-    for (int p = threadIdx.x; p < D.m; p += CS_THREADS) GivensSweep{c}(D.off + p);
-    __syncthreads();
+    namespace cg = cooperative_groups;
+    const int csize = CLUSTER ? (int)cg::this_cluster().num_blocks() : 1, crank = CLUSTER ? (int)cg::this_cluster().block_rank() : 0;
+    MergeDesc& D = c.desc[blockIdx.x / csize];
+    // the Givens sweep of this merge first (segment heads walk their segments, also into the ranges of the other CTAs;
+    // was a launch of its own)
+    {
+        const int per = (D.m + csize - 1) / csize;
+        const int p1 = min(D.m, (crank + 1) * per);
+        for (int p = crank * per + threadIdx.x; p < p1; p += CS_THREADS) GivensSweep{c}(D.off + p);
+    }
+    if (CLUSTER) __threadfence();
+    cs_sync<CLUSTER>();
     const int off = D.off, nl = D.nlive1, n1 = D.n1;
     const int* ls = c.lsort + off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int perq = ((nl + csize - 1) / csize + CS_THREADS - 1) / CS_THREADS * CS_THREADS;     // whole tiles per CTA
+    const int q0 = min(nl, crank * perq), q1 = min(nl, q0 + perq);
     __shared__ int s_cnt[3][32];
     __shared__ double s_sw[32];
-    __shared__ int s_tot[3];
-    // ---- pass 1: totals -------------------------------------------------------------------------------
+    __shared__ int s_part[3];          // this CTA's totals (read by the other CTAs of the cluster)
+    __shared__ double s_partw;
+    __shared__ int s_base[3], s_tot[3];
+    // ---- pass 1: totals of the own range ----------------------------------------------------------------
     int k = 0, kt = 0, kb = 0;
     double sw = 0;
-    for (int q = tid; q < nl; q += CS_THREADS) {
+    for (int q = q0 + tid; q < q1; q += CS_THREADS) {
         const int eq = ls[q];
         if (c.G[off + eq] != -1) continue;
         const int sp = c.sup[off + eq];
@@ -404,17 +429,32 @@ __global__ void __launch_bounds__(CS_THREADS) compact_scan_kernel(LevelCtx c) {
         a = __reduce_add_sync(0xffffffffu, a); b = __reduce_add_sync(0xffffffffu, b); d3 = __reduce_add_sync(0xffffffffu, d3);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
-        if (lane == 0) { s_tot[0] = a; s_tot[1] = b; s_tot[2] = d3; D.k = a; D.ktop = b; D.kbot = d3; D.sumw = w; }
+        if (lane == 0) { s_part[0] = a; s_part[1] = b; s_part[2] = d3; s_partw = w; }
     }
-    __syncthreads();
+    cs_sync<CLUSTER>();                                    // every CTA's partial totals are in its shared memory
+    if (tid == 0) {
+        int base[3] = {0, 0, 0}, tot[3] = {0, 0, 0};
+        double w = 0;
+        for (int r = 0; r < csize; ++r) {                  // fixed order: the sum of z^2 does not depend on timing
+            const int* rp = CLUSTER ? cg::this_cluster().map_shared_rank(s_part, r) : s_part;
+            const double* rw = CLUSTER ? cg::this_cluster().map_shared_rank(&s_partw, r) : &s_partw;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) { const int x = rp[v]; if (r < crank) base[v] += x; tot[v] += x; }
+            w += *rw;
+        }
+#pragma unroll
+        for (int v = 0; v < 3; ++v) { s_base[v] = base[v]; s_tot[v] = tot[v]; }
+        if (crank == 0) { D.k = tot[0]; D.ktop = tot[1]; D.kbot = tot[2]; D.sumw = w; }
+    }
+    cs_sync<CLUSTER>();                                    // remote reads done (no CTA may exit before), s_base / s_tot visible
     const int ktot = s_tot[0];
     const bool neg = D.rho < 0;
-    // ---- pass 2: tiled exclusive scan -------------------------------------------------------------------
-    int carry0 = 0, carry1 = 0, carry2 = 0;
-    for (int base = 0; base < nl; base += CS_THREADS) {
+    // ---- pass 2: tiled exclusive scan of the own range --------------------------------------------------
+    int carry0 = s_base[0], carry1 = s_base[1], carry2 = s_base[2];
+    for (int base = q0; base < q1; base += CS_THREADS) {
         const int q = base + tid;
         int e = -1, sp = 0, f0 = 0, f1 = 0, f2 = 0;
-        if (q < nl) {
+        if (q < q1) {
             e = ls[q];
             if (c.G[off + e] == -1) { sp = c.sup[off + e]; f0 = 1; f1 = (sp & SUP_TOP) ? 1 : 0; f2 = (sp & SUP_BOT) ? 1 : 0; }
         }
@@ -448,6 +488,26 @@ __global__ void __launch_bounds__(CS_THREADS) compact_scan_kernel(LevelCtx c) {
         }
         carry0 += t0; carry1 += t1; carry2 += t2;
     }
+}
+// one cluster of compact_cluster_size(maxm) CTAs per merge
+inline void launch_compact_scan(Stream st, int merges, int maxm, LevelCtx c) {
+    const int cs = compact_cluster_size(maxm);
+    if (cs == 1) {
+        compact_scan_kernel<false><<<(unsigned)merges, CS_THREADS, 0, st>>>(c);
+        CUDA_CHECK(cudaGetLastError());
+        return;
+    }
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(merges * cs), 1, 1);
+    cfg.blockDim = dim3(CS_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CUDA_CHECK(cudaLaunchKernelEx(&cfg, compact_scan_kernel<true>, c));
 }
 
 // ---- the O(k^2) stages as tiled kernels -----------------------------------------------------------------
@@ -596,6 +656,27 @@ __global__ void __launch_bounds__(TL_THREADS) rowgemv_tiled_kernel(LevelCtx c, R
         const double rn = 1.0 / c.nrm[off + i];
         r.frow_new[off + c.lidx[off + i]] = a * rn;
         r.lrow_new[off + c.lidx[off + i]] = b * rn;
+    }
+}
+
+// MergeTol (merge_stages.h) with one CTA per merge instead of one warp: the warp walked m / 32 dependent pairs of loads
+// (20 us at m = 2048 for a stage that every accurate-rule level waits on)
+__global__ void __launch_bounds__(256) merge_tol_kernel(LevelCtx c) {
+    MergeDesc& D = c.desc[blockIdx.x];
+    if (D.mode == MODE_REFERENCE) return;
+    __shared__ double s_d[8], s_z[8];
+    double dmax = 0, zmax = 0;
+    const double* dd = c.d + D.off;
+    const double* zz = c.z + D.off;
+    for (int t = threadIdx.x; t < D.m; t += 256) { dmax = fmax(dmax, fabs(dd[t])); zmax = fmax(zmax, fabs(zz[t])); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o)); zmax = fmax(zmax, __shfl_xor_sync(0xffffffffu, zmax, o)); }
+    if ((threadIdx.x & 31) == 0) { s_d[threadIdx.x >> 5] = dmax; s_z[threadIdx.x >> 5] = zmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int w = 1; w < 8; ++w) { dmax = fmax(dmax, s_d[w]); zmax = fmax(zmax, s_z[w]); }
+        D.tol = 8.0 * 2.220446049250313e-16 * fmax(dmax, D.sigma * zmax);
     }
 }
 

@@ -884,7 +884,13 @@ void Solver::run_level(int li) {
         pt.begin(T_DEFL, stream);
         if (L.any_accurate) {
             launch_items(stream, n, ZAssemble{c});
+#if CUPPEN_CUDA
+            merge_tol_kernel<<<(unsigned)nd_cnt, 256, 0, stream>>>(c);
+            CUDA_CHECK(cudaGetLastError());
+            g_launches.launches++;
+#else
             launch_warps(stream, nd_cnt, MergeTol{c});
+#endif
             launch_items(stream, n, FlagDeflate{c});
         } else launch_items(stream, n, ZAssembleFlag{c});
 #if CUPPEN_CUDA
@@ -901,8 +907,7 @@ void Solver::run_level(int li) {
         launch_items(stream, n, GivensSweep{c});
 #endif
 #if CUPPEN_CUDA
-        compact_scan_kernel<<<(unsigned)nd_cnt, CS_THREADS, 0, stream>>>(c);          // (Givens sweep + compaction)
-        CUDA_CHECK(cudaGetLastError());
+        launch_compact_scan(stream, nd_cnt, L.maxm, c);                                // (Givens sweep + compaction)
         g_launches.launches++;
 #else
         launch_warps(stream, n, Compact{c});
