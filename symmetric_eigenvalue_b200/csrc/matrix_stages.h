@@ -288,7 +288,7 @@ struct SecularStagedEval {
     // CTA-collective; `math` = false for a drained warp (takes part in loads and barriers only)
     __device__ __forceinline__ SecularSums run(double dorg, double tau, int split, bool math) const {
         const int lane = threadIdx.x & 31;
-        double psi = 0, dpsi = 0, phi = 0, dphi = 0, err = 0;
+        double psi = 0, dpsi = 0, phi = 0, dphi = 0;          // (err = |psi| + |phi|, see secular_eval)
         for (int c0 = 0; c0 < k; c0 += cap) {
             const int cnt = min(cap, k - c0);
             __syncthreads();                                   // the previous chunk has been consumed by every warp
@@ -302,19 +302,19 @@ struct SecularStagedEval {
                 const double t = (sm[j] - dorg) - tau;
                 const double inv = CUPPEN_RCP(t);
                 const double r = sm[cap + j] * inv;
-                psi += r; dpsi += r * inv; err += fabs(r);
+                psi += r; dpsi += r * inv;
             }
 #pragma unroll 4
             for (; j < cnt; j += 32) {
                 const double t = (sm[j] - dorg) - tau;
                 const double inv = CUPPEN_RCP(t);
                 const double r = sm[cap + j] * inv;
-                phi += r; dphi += r * inv; err += fabs(r);
+                phi += r; dphi += r * inv;
             }
         }
         SecularSums s;
         WarpLanes L;
-        s.psi = L.sum(psi); s.dpsi = L.sum(dpsi); s.phi = L.sum(phi); s.dphi = L.sum(dphi); s.err = L.sum(err);
+        s.psi = L.sum(psi); s.dpsi = L.sum(dpsi); s.phi = L.sum(phi); s.dphi = L.sum(dphi); s.err = fabs(s.psi) + fabs(s.phi);
         return s;
     }
     // an active warp announces itself (the drained ones are waiting in the same vote), then evaluates
