@@ -643,7 +643,7 @@ __global__ void __launch_bounds__(TL_THREADS) rowgemv_tiled_kernel(LevelCtx c, R
             __syncthreads();
             const int q1 = min(cnt, (slice + 1) * TL_SUB);
 #pragma unroll 4
-            for (int q = slice * TL_SUB; q < q1; ++q) s += s_w[q] / ((s_dl[q] - dorg) - t);
+            for (int q = slice * TL_SUB; q < q1; ++q) s = fma(s_w[q], CUPPEN_RCP((s_dl[q] - dorg) - t), s);
             __syncthreads();
         }
         s_part[half][slice][out] = s;

@@ -331,7 +331,7 @@ struct Loewner {
         double prod = 1.0;
         for (int i = lanes.lane(); i < D.k; i += lanes.lanes()) {
             if (i == j) continue;
-            prod *= ((dl[org[i]] - dj) + tau[i]) / (dl[i] - dj);
+            prod *= CUPPEN_DIV((dl[org[i]] - dj) + tau[i], dl[i] - dj);
         }
         prod = lanes.prod(prod) * ((dl[org[j]] - dj) + tau[j]);
         double zh = sqrt(fabs(prod) / fabs(D.rho));
@@ -353,7 +353,7 @@ struct Norms {
         const double dorg = dl[c.org[g]], t = c.tau[g];
         double s = 0;
         for (int j = lanes.lane(); j < D.k; j += lanes.lanes()) {
-            double u = zh[j] / ((dl[j] - dorg) - t);
+            double u = CUPPEN_DIV(zh[j], (dl[j] - dorg) - t);
             s += u * u;
         }
         s = lanes.sum(s);
@@ -448,11 +448,11 @@ struct RowGemv {
         double sf = 0, sl = 0;
         for (int q = lanes.lane(); q < D.ktop; q += lanes.lanes()) {
             int j = c.toplist[off + q];
-            sf += r.fpack[off + q] * (zh[j] / (((dl[j] - dorg) - t) * nn));
+            sf += r.fpack[off + q] * CUPPEN_DIV(zh[j], ((dl[j] - dorg) - t) * nn);
         }
         for (int q = lanes.lane(); q < D.kbot; q += lanes.lanes()) {
             int j = c.botlist[off + D.n1 + q];
-            sl += r.lpack[off + D.n1 + q] * (zh[j] / (((dl[j] - dorg) - t) * nn));
+            sl += r.lpack[off + D.n1 + q] * CUPPEN_DIV(zh[j], ((dl[j] - dorg) - t) * nn);
         }
         sf = lanes.sum(sf);
         sl = lanes.sum(sl);

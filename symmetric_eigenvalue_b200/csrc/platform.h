@@ -73,9 +73,21 @@ __host__ __device__ __forceinline__ double fast_rcp(double x) {
     return 1.0 / x;
 #endif
 }
+// a / x for the stage functors that the host test build shares with the device (merge_stages.h): the reciprocal form on
+// the device, the plain IEEE quotient on the host -- where the eigenvalue-only path (RowGemv) and the matrix path
+// (ugen + GEMM twins) are required to agree to the last bit (tests/test_host_logic.py)
+__host__ __device__ __forceinline__ double fast_div(double a, double x) {
+#ifdef __CUDA_ARCH__
+    return a * fast_rcp(x);
+#else
+    return a / x;
+#endif
+}
 #define CUPPEN_RCP(x) ::cuppen::fast_rcp(x)
+#define CUPPEN_DIV(a, x) ::cuppen::fast_div((a), (x))
 #else
 #define CUPPEN_RCP(x) (1.0 / (x))
+#define CUPPEN_DIV(a, x) ((a) / (x))
 #endif
 
 struct Error {
