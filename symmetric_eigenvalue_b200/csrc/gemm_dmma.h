@@ -29,6 +29,9 @@ struct GemmProblem {
 };
 
 struct GemmTile { int prob, m0, n0; };
+// `prob` carries a flag: a HALF tile covers only the 64 columns [n0, n0 + 64) -- the tiles of an under-filled last wave are
+// emitted as two halves each (work list builder, matrix_stages.h; tensor-map TMA kernel only)
+enum { GEMM_TILE_HALF = 0x40000000, GEMM_TILE_PROB_MASK = 0x3fffffff };
 
 #if CUPPEN_CUDA
 
@@ -144,7 +147,7 @@ dgemm_dmma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restr
 
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const GemmTile T = tiles[tile];
-        const GemmProblem P = probs[T.prob];
+        const GemmProblem P = probs[T.prob & GEMM_TILE_PROB_MASK];
         const int m0 = T.m0, n0 = T.n0;
         const int ktiles = (P.K + BK - 1) / BK;
 

@@ -130,7 +130,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
         const int kk = lane & (TMA_BK - 1);
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const GemmTile T = tiles[tile];
-            const GemmProblem& P = probs[T.prob];
+            const GemmProblem& P = probs[T.prob & GEMM_TILE_PROB_MASK];
             const int ktiles = (P.K + TMA_BK - 1) / TMA_BK;
             const int ashift = P.a_row0 & 1;
             if (TENSOR) {
@@ -192,9 +192,13 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
     unsigned phase = 0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const GemmTile T = tiles[tile];
-        const GemmProblem P = probs[T.prob];
+        const GemmProblem P = probs[T.prob & GEMM_TILE_PROB_MASK];
         const int ktiles = (P.K + TMA_BK - 1) / TMA_BK;
         const int aofs = aofs0 + (P.a_row0 & 1);
+        // half tile (64 columns): the warps of the upper two n-quarters only keep the ring moving; one warp per SM
+        // sub-partition still issues its 32 independent DMMAs per k-step back to back, so the tile takes about half the time
+        const int nw = (T.prob & GEMM_TILE_HALF) ? 64 : TMA_BN;
+        const bool active = wn * 32 < nw;
         double acc[8][4][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -205,6 +209,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
             if (!mbar_wait(&full[stage], phase, 1, stage, tile, kt, abort_flags)) return;
             const double* sA = tma_smem + stage * TMA_STAGE_DOUBLES + aofs;
             const double* sB = tma_smem + stage * TMA_STAGE_DOUBLES + bofs;
+            if (active)
 #pragma unroll
             for (int k4 = 0; k4 < TMA_BK / 4; ++k4) {
                 double af[8], bf[4];
@@ -222,6 +227,7 @@ dgemm_tma_kernel(const GemmProblem* __restrict__ probs, const GemmTile* __restri
             if (++stage == TMA_STAGES) { stage = 0; phase ^= 1; }
         }
         // epilogue: C[m = lr][n = 2*lk + {0,1}] of every 8x8 sub-tile, column-scattered
+        if (active)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
 #pragma unroll

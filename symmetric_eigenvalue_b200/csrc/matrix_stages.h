@@ -64,6 +64,8 @@ struct WorkCtx {
     int tile_cap;
     int* fail;              // set to 1 when the level needs more than tile_cap tiles (the solve then reports an error)
     int supercol_mb;        // L2 budget (MiB) of the B panel of one super-column (work_supercol)
+    int split_grid;         // > 0: persistent CTAs of the consuming kernel, which accepts half tiles (tensor-map TMA GEMM): the
+                            // tiles of an under-filled last wave are emitted as two 64-column halves each (build_gemm_work_body)
 };
 
 // Tile order of one problem: super-columns of `nsw` n-tiles, all m-tiles inside a super-column, n fastest -- so B is
@@ -134,26 +136,39 @@ __device__ __forceinline__ void build_gemm_work_body(const WorkCtx& w, int* work
         if (Pb.M > 0 && (Pb.a_row0 & 1)) atomicAdd(&misaligned, 1);
     }
     __syncthreads();
+    __shared__ int s_run, s_tail;
     if (threadIdx.x == 0) {
         int run = 0;
         for (int p = 0; p < np; ++p) { int c = work_off[p]; work_off[p] = run; run += c; }
-        w.ntiles[0] = run < w.tile_cap ? run : w.tile_cap;
+        // Wave quantisation: the persistent kernel takes the tiles round-robin, `split_grid` at a time; when the last wave
+        // fills at most half of the CTAs, its R tiles are emitted as 2R half tiles (64 columns each), so that the wave
+        // takes about half a tile time (8 GPUs, top merge of GOE n=16384: 1680 tiles per rank = 11.35 waves on 148 SMs)
+        int tail = 0;
+        if (w.split_grid > 0 && run > w.split_grid) {
+            tail = run % w.split_grid;
+            if (2 * tail > w.split_grid) tail = 0;
+        }
+        if (run + tail > w.tile_cap) { *w.fail = 1; tail = 0; if (run > w.tile_cap) run = w.tile_cap; }
+        s_run = run; s_tail = tail;
+        w.ntiles[0] = run + tail;
         w.ntiles[1] = misaligned;
-        if (run > w.tile_cap) *w.fail = 1;
     }
     __syncthreads();
     // every thread writes total / blockDim tiles: the problem of a tile index is found by bisection in the prefix sums
     // (one thread per problem took ~45 us per launch at the top levels -- thousands of tiles in two problems --, a
     // loop over the problems ~150 us at the bottom levels -- hundreds of problems; profiles/README.md)
-    const int total = min(w.ntiles[0], w.tile_cap);
-    for (int t = threadIdx.x; t < total; t += blockDim.x) {
-        int lo = 0, hi = np - 1;                     // last p with work_off[p] <= t (empty problems share their successor's offset)
+    const int run = s_run, tail = s_tail, whole = run - tail;
+    for (int t = threadIdx.x; t < run + tail; t += blockDim.x) {
+        const int src = t < whole ? t : whole + ((t - whole) >> 1);       // tile of the plain order that entry t comes from
+        int lo = 0, hi = np - 1;                     // last p with work_off[p] <= src (empty problems share their successor's offset)
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (work_off[mid] <= t) lo = mid; else hi = mid - 1;
+            if (work_off[mid] <= src) lo = mid; else hi = mid - 1;
         }
         const GemmProblem& Pb = w.probs[lo];
-        w.tiles[t] = work_tile_at(w, Pb, lo, t - work_off[lo]);
+        GemmTile T = work_tile_at(w, Pb, lo, src - work_off[lo]);
+        if (t >= whole) { T.prob |= GEMM_TILE_HALF; T.n0 += ((t - whole) & 1) * 64; }
+        w.tiles[t] = T;
     }
 }
 __global__ void __launch_bounds__(1024) build_gemm_work_kernel(WorkCtx w) {

@@ -217,6 +217,7 @@ struct Solver {
     double acc_pack_bytes = 0, acc_ugen_bytes = 0, acc_gemm_flop = 0;
     int resid_variant = 0;        // residual_kernel variant (0: default); env CUPPEN_RESID
     int gemm_hints = 0;           // L2 eviction hints of the tensor-map GEMM on merges of >= GEMM_HINT_MIN_ROWS rows (1: B evict_last + streaming C stores, 3: + A evict_first); env CUPPEN_GEMM_HINT
+    bool split_tail = true;       // half tiles for an under-filled last GEMM wave (build_gemm_work_body); env CUPPEN_SPLIT_TAIL=0 switches it off
     bool track_spans = true;      // row support per column (RowSpan, matrix_stages.h); env CUPPEN_SPAN=0 switches it off
     int supercol_mb = 48;         // L2 budget of a super-column's B panel (work_supercol); env CUPPEN_SUPERCOL_MB
     int gemm_variant = 2;         // 0: cp.async kernel (gemm_dmma.h), 1: TMA bulk-copy lines, 2: TMA tensor maps (gemm_tma.h, default); env CUPPEN_GEMM
@@ -410,6 +411,8 @@ void Solver::allocate() {
         const char* gv = getenv("CUPPEN_GEMM");
         if (gv && (!strcmp(gv, "cpasync") || !strcmp(gv, "v1"))) gemm_variant = 0;
         if (gv && !strcmp(gv, "bulk")) gemm_variant = 1;
+        const char* stv = getenv("CUPPEN_SPLIT_TAIL");
+        if (stv && atoi(stv) == 0) split_tail = false;
         const char* tv = getenv("CUPPEN_SPAN");
         if (tv && atoi(tv) == 0) track_spans = false;
         const char* hv = getenv("CUPPEN_GEMM_HINT");
@@ -743,7 +746,7 @@ void Solver::prepare_levels() {
             worst_t = std::max(worst_t, std::max(L.worst_tiles_big, L.worst_tiles_small));
             worst_p = std::max(worst_p, 2 * L.ids.size());
         }
-        if (tiles.n < (size_t)worst_t) tiles.alloc((size_t)worst_t);
+        if (tiles.n < (size_t)worst_t + 256) tiles.alloc((size_t)worst_t + 256);      // (+ the half tiles of a split last wave: at most one per two SMs)
         if (probs.n < worst_p) probs.alloc(worst_p);
     }
     if (ntiles_dev.n < 4) ntiles_dev.alloc(4);
@@ -1038,6 +1041,11 @@ void Solver::run_level(int li) {
         w.probs = probs.p; w.tiles = tiles.p; w.ntiles = ntiles_dev.p; w.tile_cap = (int)std::min<size_t>(tiles.n, 0x7fffffff);
         w.fail = fail.p + FAIL_TILES;
         w.supercol_mb = supercol_mb;
+#if CUPPEN_CUDA
+        w.split_grid = (!small_tiles && gemm_variant == 2 && split_tail) ? num_sms : 0;
+#else
+        w.split_grid = 0;
+#endif
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
         {
