@@ -143,8 +143,9 @@ __device__ __forceinline__ void build_gemm_work_body(const WorkCtx& w, int* work
         // Wave quantisation: the persistent kernel takes the tiles round-robin, `split_grid` at a time; when the last wave
         // fills at most half of the CTAs, its R tiles are emitted as 2R half tiles (64 columns each), so that the wave
         // takes about half a tile time (8 GPUs, top merge of GOE n=16384: 1680 tiles per rank = 11.35 waves on 148 SMs)
+        // (a level with fewer tiles than half the CTAs is one short wave: every tile is split)
         int tail = 0;
-        if (w.split_grid > 0 && run > w.split_grid) {
+        if (w.split_grid > 0) {
             tail = run % w.split_grid;
             if (2 * tail > w.split_grid) tail = 0;
         }

@@ -1067,7 +1067,8 @@ void Solver::run_level(int li) {
         const long worst = small_tiles ? L.worst_tiles_small : L.worst_tiles_big;
         pt.begin(T_GEMM, stream);
 #if CUPPEN_CUDA
-        const int grid = (int)std::min<long>(worst, small_tiles ? num_sms * 8L : (long)num_sms);
+        // (tensor-map kernel: up to twice the worst-case tile count, a short level is split into half tiles)
+        const int grid = (int)std::min<long>((!small_tiles && w.split_grid > 0) ? 2 * worst : worst, small_tiles ? num_sms * 8L : (long)num_sms);
         if (small_tiles) launch_gemm<64, 64, 16, 2, 2, 3>(stream, probs.p, tiles.p, ntiles_dev.p, grid);
         else if (gemm_variant == 2)
             launch_gemm_tma(stream, probs.p, tiles.p, ntiles_dev.p, grid, fail.p + FAIL_TMA, Awork == Apack.p ? &map_apack : &map_qa, &map_b,

@@ -4,7 +4,7 @@
 O=gpurun_out/r02; mkdir -p $O
 timeout 1500 python -m pytest tests -m gpu -x -q > $O/pytest_t.txt 2>&1; echo "pytest rc $?" >> $O/pytest_t.txt; tail -3 $O/pytest_t.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke_t.txt 2>&1; echo "smoke rc $?" >> $O/smoke_t.txt; tail -2 $O/smoke_t.txt
-timeout 600 python tools/dense_bench.py 4096 8192 16384 > $O/dense_bench_t.txt 2>&1; tail -3 $O/dense_bench_t.txt
+timeout 600 python tools/dense_bench.py 4096 8192 > $O/dense_bench_t.txt 2>&1; tail -3 $O/dense_bench_t.txt
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > $O/bench_t.json 2> $O/bench_t.err; echo "bench rc $?" >> $O/bench_t.err; tail -1 $O/bench_t.err
 timeout 300 python tools/select_bench.py --sizes 16384,65536 --ks 1,16 > $O/select_bench_t.jsonl 2> $O/select_bench_t.err
 python tools/profile_step.py --size 16384 --matrix goe > $O/prof_plain_t.log 2>&1 && \
