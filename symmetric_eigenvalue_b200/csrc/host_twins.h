@@ -161,28 +161,37 @@ inline void ugen_host(LevelCtx c, MatCtx M, int p0, int width) {
 }
 
 inline void build_gemm_work_host(WorkCtx w) {
-    int run = 0, mis = 0;
-    for (int p = 0; p < 2 * w.nd; ++p) {
+    // same list as build_gemm_work_body: the tiles of all problems in order, the last `tail` of them as two half tiles each
+    const int np = 2 * w.nd;
+    std::vector<int> off(np + 1, 0);
+    int mis = 0;
+    for (int p = 0; p < np; ++p) {
         GemmProblem Pb;
-        work_fill_problem(w, p, Pb);
+        off[p + 1] = off[p] + work_fill_problem(w, p, Pb);
         w.probs[p] = Pb;
-        if (Pb.M == 0) continue;
-        if (Pb.a_row0 & 1) mis++;
-        GemmTile* tl = w.tiles;
-        work_emit_tiles(w, Pb, p, run, [tl](int t, GemmTile T) { tl[t] = T; });
-        run += ((Pb.M + w.BM - 1) / w.BM) * ((Pb.N + w.BN - 1) / w.BN);
+        if (Pb.M > 0 && (Pb.a_row0 & 1)) mis++;
     }
-    w.ntiles[0] = run < w.tile_cap ? run : w.tile_cap;
+    int run = off[np];
+    int tail = work_tail_tiles(w, run);
+    if (run + tail > w.tile_cap) { *w.fail = 1; tail = 0; if (run > w.tile_cap) run = w.tile_cap; }
+    int p = 0;
+    for (int t = 0; t < run + tail; ++t) {
+        int half;
+        const int src = work_entry_source(run, tail, t, &half);
+        while (p > 0 && off[p] > src) --p;
+        while (off[p + 1] <= src) ++p;
+        w.tiles[t] = work_entry_tile(work_tile_at(w, w.probs[p], p, src - off[p]), half);
+    }
+    w.ntiles[0] = run + tail;
     w.ntiles[1] = mis;
-    if (run > w.tile_cap) *w.fail = 1;
 }
 
 // consumes the same (problem, tile) list as the device kernels
 inline void gemm_host(const GemmProblem* probs, const GemmTile* tiles, const int* ntiles_ptr, int BM, int BN) {
     for (int t = 0; t < ntiles_ptr[0]; ++t) {
-        const GemmProblem& P = probs[tiles[t].prob];
+        const GemmProblem& P = probs[tiles[t].prob & GEMM_TILE_PROB_MASK];
         const int m0 = tiles[t].m0, n0 = tiles[t].n0;
-        const int m1 = std::min(P.M, m0 + BM), n1 = std::min(P.N, n0 + BN);
+        const int m1 = std::min(P.M, m0 + BM), n1 = std::min(P.N, n0 + ((tiles[t].prob & GEMM_TILE_HALF) ? 64 : BN));
         const int Kpad = (P.K + K_PAD - 1) / K_PAD * K_PAD;     // read the padded K like the device kernel
         for (int nn = n0; nn < n1; ++nn) {
             double* ccol = P.C + (long)P.colidx[nn] * P.ldc;

@@ -95,11 +95,28 @@ CUPPEN_HD GemmTile work_tile_at(const WorkCtx& w, const GemmProblem& Pb, int p, 
     const int mt = rem / wd, nt = ns + (rem - mt * wd);
     return GemmTile{p, mt * w.BM, nt * w.BN};
 }
-template <class Emit>
-CUPPEN_HD void work_emit_tiles(const WorkCtx& w, const GemmProblem& Pb, int p, int t, Emit emit) {
-    const int ntm = (Pb.M + w.BM - 1) / w.BM, ntn = (Pb.N + w.BN - 1) / w.BN;
-    for (int q = 0; q < ntm * ntn; ++q, ++t)
-        if (t < w.tile_cap) emit(t, work_tile_at(w, Pb, p, q));
+// Wave quantisation: the persistent kernel takes the tiles round-robin, `split_grid` at a time; when the last wave fills at
+// most half of the CTAs, its R tiles are emitted as 2R half tiles (64 columns each), so that the wave takes about half a
+// tile time (8 GPUs, top merge of GOE n=16384: 1696 tiles per rank = 11 waves of 148 + 68).  A level with fewer tiles
+// than half the CTAs is one short wave: every tile is split.  Returns R (0: no split).
+CUPPEN_HD int work_tail_tiles(const WorkCtx& w, int run) {
+    int tail = 0;
+    if (w.split_grid > 0) {
+        tail = run % w.split_grid;
+        if (2 * tail > w.split_grid) tail = 0;
+    }
+    return tail;
+}
+// entry t of the emitted list (run + tail entries): which tile of the plain order it comes from, and which half
+CUPPEN_HD int work_entry_source(int run, int tail, int t, int* half) {
+    const int whole = run - tail;
+    if (t < whole) { *half = -1; return t; }
+    *half = (t - whole) & 1;
+    return whole + ((t - whole) >> 1);
+}
+CUPPEN_HD GemmTile work_entry_tile(GemmTile T, int half) {
+    if (half >= 0) { T.prob |= GEMM_TILE_HALF; T.n0 += half * 64; }
+    return T;
 }
 
 CUPPEN_HD int work_fill_problem(const WorkCtx& w, int p, GemmProblem& Pb) {
@@ -140,15 +157,7 @@ __device__ __forceinline__ void build_gemm_work_body(const WorkCtx& w, int* work
     if (threadIdx.x == 0) {
         int run = 0;
         for (int p = 0; p < np; ++p) { int c = work_off[p]; work_off[p] = run; run += c; }
-        // Wave quantisation: the persistent kernel takes the tiles round-robin, `split_grid` at a time; when the last wave
-        // fills at most half of the CTAs, its R tiles are emitted as 2R half tiles (64 columns each), so that the wave
-        // takes about half a tile time (8 GPUs, top merge of GOE n=16384: 1680 tiles per rank = 11.35 waves on 148 SMs)
-        // (a level with fewer tiles than half the CTAs is one short wave: every tile is split)
-        int tail = 0;
-        if (w.split_grid > 0) {
-            tail = run % w.split_grid;
-            if (2 * tail > w.split_grid) tail = 0;
-        }
+        int tail = work_tail_tiles(w, run);
         if (run + tail > w.tile_cap) { *w.fail = 1; tail = 0; if (run > w.tile_cap) run = w.tile_cap; }
         s_run = run; s_tail = tail;
         w.ntiles[0] = run + tail;
@@ -158,18 +167,17 @@ __device__ __forceinline__ void build_gemm_work_body(const WorkCtx& w, int* work
     // every thread writes total / blockDim tiles: the problem of a tile index is found by bisection in the prefix sums
     // (one thread per problem took ~45 us per launch at the top levels -- thousands of tiles in two problems --, a
     // loop over the problems ~150 us at the bottom levels -- hundreds of problems; profiles/README.md)
-    const int run = s_run, tail = s_tail, whole = run - tail;
+    const int run = s_run, tail = s_tail;
     for (int t = threadIdx.x; t < run + tail; t += blockDim.x) {
-        const int src = t < whole ? t : whole + ((t - whole) >> 1);       // tile of the plain order that entry t comes from
+        int half;
+        const int src = work_entry_source(run, tail, t, &half);           // tile of the plain order that entry t comes from
         int lo = 0, hi = np - 1;                     // last p with work_off[p] <= src (empty problems share their successor's offset)
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
             if (work_off[mid] <= src) lo = mid; else hi = mid - 1;
         }
         const GemmProblem& Pb = w.probs[lo];
-        GemmTile T = work_tile_at(w, Pb, lo, src - work_off[lo]);
-        if (t >= whole) { T.prob |= GEMM_TILE_HALF; T.n0 += ((t - whole) & 1) * 64; }
-        w.tiles[t] = T;
+        w.tiles[t] = work_entry_tile(work_tile_at(w, Pb, lo, src - work_off[lo]), half);
     }
 }
 __global__ void __launch_bounds__(1024) build_gemm_work_kernel(WorkCtx w) {

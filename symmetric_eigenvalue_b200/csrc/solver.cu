@@ -1044,7 +1044,7 @@ void Solver::run_level(int li) {
 #if CUPPEN_CUDA
         w.split_grid = (!small_tiles && gemm_variant == 2 && split_tail) ? num_sms : 0;
 #else
-        w.split_grid = 0;
+        w.split_grid = (!small_tiles && split_tail) ? 148 : 0;      // (host test build: the split tile list of a 148-SM device)
 #endif
         pt.begin(T_UGEN, stream);
 #if CUPPEN_CUDA
