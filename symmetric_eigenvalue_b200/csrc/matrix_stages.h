@@ -296,9 +296,10 @@ __global__ void __launch_bounds__(128) leaf_ql_kernel(const LeafDesc* __restrict
 }
 
 // K3: one warp per secular root.  The poles and weights of the merge are staged in shared memory: all of
-// them when they fit (k <= kcap <= SEC_SMEM_K; 64 KB, three CTAs per SM -- with the whole 227 KB per CTA the
-// 16 warps of the single resident CTA left the FP64 pipe 32 % active, ncu), otherwise chunk by chunk through a
-// CTA-collective evaluator --
+// them when they fit (k <= kcap <= SEC_SMEM_K; 64 KB per CTA; the 64 registers per thread allow two CTAs = 32 warps
+// per SM -- with the whole 227 KB per CTA the 16 warps of the single resident CTA left the FP64 pipe 32 % active, ncu;
+// forcing three CTAs with __launch_bounds__(512, 3) spills and is 12 % slower, profiles/r02_session2_ab_runs.txt call R),
+// otherwise chunk by chunk through a CTA-collective evaluator --
 // the SEC_WARPS roots of a CTA then iterate in lockstep (a warp whose root has converged keeps taking part in
 // the chunk loads and barriers until the slowest root of the CTA is done), so every chunk is read from L2 once
 // per CTA and evaluation instead of once per warp.

@@ -16,7 +16,7 @@
 #include <math.h>
 
 #ifndef CUPPEN_RCP
-#define CUPPEN_RCP(x) (1.0 / (x))      // (platform.h supplies the 5-instruction device version)
+#define CUPPEN_RCP(x) (1.0 / (x))      // (platform.h supplies the device version: hardware seed + one cubic step)
 #endif
 #ifndef CUPPEN_HD
 #if defined(__CUDACC__)
