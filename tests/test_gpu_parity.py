@@ -173,6 +173,25 @@ def test_tma_and_cpasync_gemm_paths_agree(lib, oracle):
             assert np.abs(a["resid"] - b["resid"]).max() < 1e-12
 
 
+@pytest.mark.parametrize("gen,n,P", [("goe", 4096, 4), ("s2", 4096, 8), ("wilk", 3000, 4)])
+def test_tile_split_row_support_and_l2_hint_switches_agree(lib, oracle, gen, n, P):
+    """The diagnostic switches of INTEGRATION.md section 5 against the defaults.  Half tiles for a short last GEMM wave
+    (GOE n=4096 P=4: 464 tiles at the 2048 level = 3 waves + 20; s2 n=4096: 512 = 3 waves + 68) and the L2 eviction hints
+    compute every element with the same K order: bit-identical eigenvectors.  The row supports only skip rows that hold
+    exact zeros: the same residuals up to the summation order."""
+    D, E = {"goe": oracle.goe, "s2": lambda k: oracle.scheme(2, k), "wilk": lambda k: oracle.wilkinson(k, norm=64.0)}[gen](n)
+    a = se.cuppens(D, E, ref_leaves=P, lib=lib)
+    for var, val in (("CUPPEN_SPLIT_TAIL", "0"), ("CUPPEN_GEMM_HINT", "1"), ("CUPPEN_SPAN", "0")):
+        os.environ[var] = val
+        try:
+            b = se.cuppens(D, E, ref_leaves=P, lib=lib)
+        finally:
+            del os.environ[var]
+        assert np.array_equal(a["lam"], b["lam"]), var
+        assert np.array_equal(a["V"], b["V"]), var
+        assert np.allclose(a["resid"], b["resid"], rtol=1e-6, atol=1e-13 * norm_T(D, E)), var
+
+
 # ---- selected-eigenvector mode (-eFILE) ---------------------------------------------------------------
 def sign_invariant_diff(A, B):
     return float(np.minimum(np.abs(A - B).max(axis=0), np.abs(A + B).max(axis=0)).max()) if A.size else 0.0
